@@ -1,0 +1,132 @@
+/*
+ * pacmann_cuda.h -- C-ABI of libpacmann_cuda.so: the B200 (sm_100a) implementation of Pacmann's
+ * data-parallel hot path.  This is the drop-in boundary: the entry points below are what the
+ * reference's Go packages bind over cgo in place of their Plan-9 assembler stubs and inner loops
+ * (INTEGRATION.md shows the cgo side).  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Reference seam each entry point replaces (paths relative to the wuwuz/Pacmann tree):
+ *   pm_expand_key      expandKeyAsm / GetLongKey          pianopir/util.go:117,167-171, aes_amd64.s:87-126
+ *   pm_prf_batch       PRFEvalWithLongKeyAndTag/aes128MMO pianopir/util.go:157-165,     aes_amd64.s:51-82
+ *   pm_xor_slices      xorSlices / EntryXor               pianopir/util.go:173, pir.go:258-265, aes_amd64.s:133-157
+ *   pm_hintgen*        PianoPIRClient.Preprocessing +     pianopir/pir.go:267-352 (hint parities),
+ *                      UpdatePreprocessing, batch fan-out  pianopir/batch-pir.go:119-155
+ *   pm_gather_rows     replacement values                 pianopir/pir.go:345-349
+ *   pm_answer_batch*   PianoPIRServer.PrivateQuery,       pianopir/pir.go:65-88,
+ *                      SimpleBatchPianoPIR.Query fan-out   pianopir/batch-pir.go:189-216
+ *   pm_l2_pairs/_batch L2Dist / L2DistanceSIMD            graphann/build_graph.go:119-134, l2_distance_amd64.s:4-36
+ *   pm_ip_u32_scan     InnerProduct + scan loop           graphann/l2_distance_amd64.s:39-68, graphann_test.go:268-273
+ *
+ * Conventions
+ *   - every function returns 0 (PM_OK) or a negative PM_ERR_* code; pm_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.  There is no CPU fallback:
+ *     without a usable CUDA device every compute entry point fails with PM_ERR_CUDA.
+ *   - functions without a `_dev` suffix take HOST pointers and include the host<->device copies;
+ *     `_dev` variants take DEVICE pointers (on the handle's device), enqueue on `stream`
+ *     (a cudaStream_t passed as void*, NULL = the handle's own stream) and do not synchronise.
+ *   - the library is re-entrant per handle; every entry point sets the CUDA device itself, so it may
+ *     be called from goroutines that migrate between OS threads.  C never retains a caller pointer
+ *     after the call returns; device-resident copies are owned by the opaque handle.
+ *   - bit-exactness: integer/byte results are bit-identical to the reference algorithm, including
+ *     xorSlices' "len%4 tail is not xored" behaviour; pm_l2_* reproduces the reference's 8-lane fp32
+ *     evaluation order (no FMA contraction), so distances are bit-identical as well.
+ */
+#ifndef PACMANN_CUDA_H
+#define PACMANN_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PM_OK 0
+#define PM_ERR_ARG (-1)         /* bad argument (null pointer, size mismatch, out-of-range index) */
+#define PM_ERR_CUDA (-2)        /* CUDA runtime failure, or no usable device */
+#define PM_ERR_UNSUPPORTED (-3) /* shape outside what the kernels implement */
+#define PM_ERR_NOMEM (-4)
+
+#define PM_NO_SKIP (-1)
+
+/* Device-resident flat row-major table of uint64: rows[n_rows][entry_u64].  The PIR database
+ * (rawDB, pianopir/pir.go:28-39) and, through its prefix of `dim` fp32 per row, the vector table
+ * used for distances (private-search.go:371-397 wire format).  A [N][D] uint32 matrix with even D
+ * is the same thing with entry_u64 = D/2. */
+typedef struct pm_db pm_db;
+
+const char *pm_version(void);
+const char *pm_last_error(void);
+int pm_device_count(int *count);
+/* number of kernel launches issued by this library in this process (for accounting) */
+uint64_t pm_launch_count(void);
+
+int pm_db_create(const uint64_t *rows_host, uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
+int pm_db_create_empty(uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
+int pm_db_upload(pm_db *db, uint64_t row0, uint64_t n_rows, const uint64_t *rows_host);
+int pm_db_info(const pm_db *db, uint64_t *n_rows, uint64_t *entry_u64, int *device, void **device_ptr);
+int pm_db_destroy(pm_db *db);
+/* blocks until everything enqueued on the handle's own streams has finished */
+int pm_db_sync(pm_db *db);
+
+/* A1: FIPS-197 AES-128 key schedule, 11 round keys as 44 little-endian uint32 (raw 16-byte blocks). */
+int pm_expand_key(const uint8_t key[16], uint32_t rk[44]);
+/* A2: out[i] = LE64((AES128_rk(B) xor B)[0:8]),  B = LE64((tags[i] << 35) + xs[i]) || 0^64. */
+int pm_prf_batch(const uint32_t rk[44], const uint64_t *tags, const uint64_t *xs, uint64_t n, uint64_t *out);
+/* A3: dst[0 : 4*(len_src/4)] ^= src[...] ; the len_src % 4 tail is left untouched (reference behaviour). */
+int pm_xor_slices(uint64_t *dst, const uint64_t *src, uint64_t len_src);
+
+/* A5/A7: one hint-generation job = (a range of) the hints of one PianoPIR instance over its DB slice.
+ *   parity[i] = XOR over chunks c in [0,set_size), c != skip_i, row = c*chunk_size + (PRF(rk,tag_i,c) & (chunk_size-1)),
+ *               row < n_rows  of  db[row0 + row]          (rows past n_rows are the reference's zero padding)
+ * Hints are numbered as PianoPIRClient.Initialization numbers them (pir.go:220-251): hint h has
+ *   tag_h  = tags ? tags[i] : h,                       h = hint_begin + i
+ *   skip_h = skip_chunk ? skip_chunk[i] : (h < n_primary ? PM_NO_SKIP : (h - n_primary) / backup_group)
+ * so the initial table needs no tag upload, while refreshed / custom tables pass explicit arrays.
+ * chunk_size must be a power of two; entry words beyond 4*(entry_u64/4) stay zero (A3 behaviour). */
+typedef struct pm_hint_job {
+    uint64_t row0, n_rows;         /* DB slice of this PianoPIR instance */
+    uint64_t chunk_size, set_size; /* pir.go:487-494 */
+    uint32_t rk[44];               /* longKey */
+    uint64_t hint_begin, n_hints;  /* hints [hint_begin, hint_begin + n_hints) */
+    uint64_t n_primary;            /* primaryHintNum */
+    uint64_t backup_group;         /* maxQueryPerChunk (0 = no backup hints) */
+    const uint64_t *tags;          /* [n_hints] or NULL */
+    const int32_t *skip_chunk;     /* [n_hints] or NULL */
+    uint64_t *parity_out;          /* [n_hints][entry_u64] */
+} pm_hint_job;
+
+int pm_hintgen(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs);
+int pm_hintgen_dev(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, void *stream);
+
+/* out[i] = db[row0 + idx[i]] if idx[i] < n_rows else zeros  (replacementVal, pir.go:345-349) */
+int pm_gather_rows(pm_db *db, uint64_t row0, uint64_t n_rows, const uint64_t *idx, uint64_t n, uint64_t *out);
+
+/* A6/A8: q server answers in one launch.  Sub-query i runs against the PianoPIR instance
+ * (row0[i], n_rows[i], chunk_size[i], set_size[i]) with offsets[i*offsets_stride + c], c < set_size[i]:
+ *   out[i] = XOR over c with idx = offsets[..c] + c*chunk_size < n_rows[i]  of  db[row0[i] + idx]. */
+int pm_answer_batch(pm_db *db, const uint64_t *row0, const uint64_t *n_rows, const uint32_t *chunk_size,
+                    const uint32_t *set_size, const uint32_t *offsets, uint64_t offsets_stride, uint64_t q,
+                    uint64_t *out);
+int pm_answer_batch_dev(pm_db *db, const uint64_t *row0, const uint64_t *n_rows, const uint32_t *chunk_size,
+                        const uint32_t *set_size, const uint32_t *offsets, uint64_t offsets_stride, uint64_t q,
+                        uint64_t *out, void *stream);
+
+/* A9: squared L2 in the reference's exact fp32 order.  out[i] = L2Dist(a[i], b[i]), rows of `dim` floats. */
+int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device);
+/* out[q*k + j] = L2Dist(first `dim` fp32 of db row ids[q*k + j], queries[q]);  ids outside [0, n_rows) give +inf. */
+int pm_l2_batch(pm_db *db, uint64_t dim, const float *queries, uint64_t n_queries, const int64_t *ids, uint64_t k,
+                float *out);
+int pm_l2_batch_dev(pm_db *db, uint64_t dim, const float *queries, uint64_t n_queries, const int64_t *ids, uint64_t k,
+                    float *out, void *stream);
+
+/* A11: db viewed as rows[n_rows][dim] uint32 (dim = 2*entry_u64, dim % 16 == 0 as the reference requires).
+ * checksum_out[t] = sum_i InnerProduct(row_i, queries[t]) mod 2^32.  If ip_out != NULL it also receives
+ * every per-row product, ip_out[t*n_rows + i]. */
+int pm_ip_u32_scan(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n_queries, uint32_t *checksum_out,
+                   uint32_t *ip_out);
+int pm_ip_u32_scan_dev(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n_queries, uint32_t *checksum_out,
+                       uint32_t *ip_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PACMANN_CUDA_H */

@@ -1,0 +1,273 @@
+// graphann distance kernels for sm_100a: bit-exact fp32 L2 (A9) and the uint32 inner-product linear
+// scan (A11).  See include/pacmann_cuda.h for the reference seams.
+#include <cmath>
+#include <cstring>
+
+#include "pm_common.cuh"
+
+namespace pm {
+
+// ---------------------------------------------------------------------------------------------
+// A9: L2Dist in the reference's evaluation order (graphann/l2_distance_amd64.s:4-36 and
+// build_graph.go:119-127):  8 strided partial sums  acc_l += fl(fl(a-b)^2)  (sub, mul, add rounded
+// separately, no FMA), then ((a0+a1)+(a2+a3)) + ((a4+a5)+(a6+a7)), then the dim%8 scalar tail.
+// Two lanes evaluate one distance: the even lane owns SIMD lanes 0-3, the odd lane 4-7, each
+// streaming its half of every 32-byte step as one 16-byte load; the halves meet in one shuffle.
+// ---------------------------------------------------------------------------------------------
+template <bool ALIGNED16>
+__device__ __forceinline__ float l2_half_pair(const float *__restrict__ a, const float *__restrict__ b, uint32_t dim,
+                                              int half) {
+    const uint32_t body = dim & ~7u;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    const float *pa = a + 4 * half, *pb = b + 4 * half;
+#pragma unroll 4
+    for (uint32_t i = 0; i < body; i += 8) {
+        float4 x, y;
+        if (ALIGNED16) {
+            x = *reinterpret_cast<const float4 *>(pa + i);
+            y = *reinterpret_cast<const float4 *>(pb + i);
+        } else {
+            x = make_float4(pa[i], pa[i + 1], pa[i + 2], pa[i + 3]);
+            y = make_float4(pb[i], pb[i + 1], pb[i + 2], pb[i + 3]);
+        }
+        float d0 = __fsub_rn(x.x, y.x), d1 = __fsub_rn(x.y, y.y), d2 = __fsub_rn(x.z, y.z), d3 = __fsub_rn(x.w, y.w);
+        a0 = __fadd_rn(a0, __fmul_rn(d0, d0));
+        a1 = __fadd_rn(a1, __fmul_rn(d1, d1));
+        a2 = __fadd_rn(a2, __fmul_rn(d2, d2));
+        a3 = __fadd_rn(a3, __fmul_rn(d3, d3));
+    }
+    return __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+}
+// full distance for the lane pair (both lanes return the same value)
+template <bool ALIGNED16>
+__device__ __forceinline__ float l2_pair(const float *a, const float *b, uint32_t dim, int half) {
+    float h = l2_half_pair<ALIGNED16>(a, b, dim, half);
+    float o = __shfl_xor_sync(0xffffffffu, h, 1);
+    float d = half ? __fadd_rn(o, h) : __fadd_rn(h, o);  // lo + hi on both lanes
+    for (uint32_t i = dim & ~7u; i < dim; i++) {
+        float x = __fsub_rn(a[i], b[i]);
+        d = __fadd_rn(d, __fmul_rn(x, x));
+    }
+    return d;
+}
+
+constexpr int L2_THREADS = 128;
+// grid.x = query, grid.y = candidate block; query vector staged in shared memory
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(L2_THREADS) l2_batch_kernel(const uint64_t *db, uint64_t n_rows, uint64_t entry_u64,
+                                                              uint32_t dim, const float *queries, const int64_t *ids,
+                                                              uint64_t k, float *out) {
+    extern __shared__ __align__(16) float s_q[];
+    const uint64_t q = blockIdx.x;
+    for (uint32_t i = threadIdx.x; i < dim; i += L2_THREADS) s_q[i] = queries[q * dim + i];
+    __syncthreads();
+    const int half = threadIdx.x & 1;
+    const uint64_t per_block = L2_THREADS / 2;
+    for (uint64_t j0 = (uint64_t)blockIdx.y * per_block; j0 < k; j0 += (uint64_t)gridDim.y * per_block) {
+        const uint64_t j = j0 + (threadIdx.x >> 1);
+        const bool in = j < k;
+        const int64_t id = in ? ids[q * k + j] : -1;
+        const bool ok = in && id >= 0 && (uint64_t)id < n_rows;
+        const float *row = reinterpret_cast<const float *>(db + (ok ? (uint64_t)id : 0) * entry_u64);
+        float d = l2_pair<ALIGNED16>(row, s_q, dim, half);
+        if (in && half == 0) out[q * k + j] = ok ? d : INFINITY;
+    }
+}
+__global__ void __launch_bounds__(L2_THREADS) l2_pairs_kernel(const float *a, const float *b, uint64_t n, uint32_t dim,
+                                                              float *out) {
+    const int half = threadIdx.x & 1;
+    const uint64_t stride = (uint64_t)gridDim.x * (L2_THREADS / 2);
+    const uint64_t n_up = (n + 15) & ~15ull;  // keep whole warps in the shuffle
+    for (uint64_t i = (uint64_t)blockIdx.x * (L2_THREADS / 2) + (threadIdx.x >> 1); i < n_up; i += stride) {
+        const bool ok = i < n;
+        const uint64_t r = ok ? i : 0;
+        float d = l2_pair<false>(a + r * dim, b + r * dim, dim, half);
+        if (ok && half == 0) out[i] = d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// A11: uint32 wrapping inner-product scan (graphann/l2_distance_amd64.s:39-68, graphann_test.go:268-273)
+// One thread per row, QT queries per pass held as accumulators; query words come from shared memory
+// as warp-wide broadcasts.  Integer arithmetic mod 2^32 is associative, so any summation order gives
+// the reference's result bit for bit.
+// ---------------------------------------------------------------------------------------------
+constexpr int IP_THREADS = 128;
+constexpr int IP_QT = 16;
+__global__ void __launch_bounds__(IP_THREADS) ip_scan_kernel(const uint4 *rows, uint64_t n_rows, uint32_t dim4,
+                                                             const uint32_t *queries, uint32_t n_queries, uint32_t q0,
+                                                             uint32_t *checksum, uint32_t *ip_out) {
+    extern __shared__ __align__(16) uint32_t s_qw[];  // [IP_QT][dim]
+    uint4 *s_q4 = reinterpret_cast<uint4 *>(s_qw);
+    const uint32_t nq = min((uint32_t)IP_QT, n_queries - q0);
+    for (uint32_t i = threadIdx.x; i < IP_QT * dim4; i += IP_THREADS) {
+        uint32_t t = i / dim4, c = i % dim4;
+        s_q4[i] = t < nq ? reinterpret_cast<const uint4 *>(queries)[(uint64_t)(q0 + t) * dim4 + c] : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    uint32_t total[IP_QT];
+#pragma unroll
+    for (int t = 0; t < IP_QT; t++) total[t] = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * IP_THREADS + threadIdx.x; r < n_rows; r += (uint64_t)gridDim.x * IP_THREADS) {
+        uint32_t acc[IP_QT];
+#pragma unroll
+        for (int t = 0; t < IP_QT; t++) acc[t] = 0;
+        const uint4 *row = rows + r * dim4;
+#pragma unroll 2
+        for (uint32_t c = 0; c < dim4; c++) {
+            const uint4 v = __ldg(row + c);
+#pragma unroll
+            for (int t = 0; t < IP_QT; t++) {
+                const uint4 qv = s_q4[t * dim4 + c];
+                acc[t] += v.x * qv.x + v.y * qv.y + v.z * qv.z + v.w * qv.w;
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < IP_QT; t++) {
+            total[t] += acc[t];
+            if (ip_out && (uint32_t)t < nq) ip_out[(uint64_t)(q0 + t) * n_rows + r] = acc[t];
+        }
+    }
+    // block reduction, then one atomic per query per block
+    __shared__ uint32_t s_red[IP_THREADS / 32][IP_QT];
+#pragma unroll
+    for (int t = 0; t < IP_QT; t++) {
+        uint32_t v = total[t];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nq) {
+        uint32_t v = 0;
+        for (int w = 0; w < IP_THREADS / 32; w++) v += s_red[w][threadIdx.x];
+        atomicAdd(checksum + q0 + threadIdx.x, v);
+    }
+}
+
+int l2_batch_enqueue(pm_db *db, uint64_t dim, const float *queries, uint64_t nq, const int64_t *ids, uint64_t k, float *out,
+                     cudaStream_t st) {
+    if (nq == 0 || k == 0) return PM_OK;
+    if (dim * 4 > db->entry_u64 * 8) return set_error(PM_ERR_ARG, "l2: dim %llu does not fit in a row", (unsigned long long)dim);
+    if (dim > 8192) return set_error(PM_ERR_UNSUPPORTED, "l2: dim too large");
+    if (nq > 0x7fffffffull) return set_error(PM_ERR_UNSUPPORTED, "l2: too many queries in one call");
+    uint64_t by = (k + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
+    if (by > 65535) by = 65535;
+    dim3 grid((unsigned)nq, (unsigned)by);
+    const size_t smem = ((dim + 3) & ~3ull) * 4;
+    if (db->entry_u64 % 2 == 0)
+        l2_batch_kernel<true><<<grid, L2_THREADS, smem, st>>>(db->d_rows, db->n_rows, db->entry_u64, (uint32_t)dim, queries, ids, k, out);
+    else
+        l2_batch_kernel<false><<<grid, L2_THREADS, smem, st>>>(db->d_rows, db->n_rows, db->entry_u64, (uint32_t)dim, queries, ids, k, out);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    return PM_OK;
+}
+
+int ip_scan_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq, uint32_t *checksum, uint32_t *ip_out,
+                    cudaStream_t st) {
+    if (nq == 0) return PM_OK;
+    if (dim == 0 || dim % 16) return set_error(PM_ERR_ARG, "ip scan: dim must be a positive multiple of 16 (reference loop)");
+    if (dim != db->entry_u64 * 2) return set_error(PM_ERR_ARG, "ip scan: dim must equal 2*entry_u64");
+    if (dim > 2048) return set_error(PM_ERR_UNSUPPORTED, "ip scan: dim too large");
+    if (nq > 0x7fffffffull) return set_error(PM_ERR_UNSUPPORTED, "ip scan: too many queries");
+    PM_CUDA(cudaMemsetAsync(checksum, 0, nq * 4, st));
+    const uint32_t dim4 = (uint32_t)(dim / 4);
+    const size_t smem = (size_t)IP_QT * dim * 4;
+    PM_CUDA(cudaFuncSetAttribute(ip_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint64_t blocks = (db->n_rows + IP_THREADS - 1) / IP_THREADS;
+    const uint64_t cap = (uint64_t)db->sm_count * 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks == 0) blocks = 1;
+    for (uint64_t q0 = 0; q0 < nq; q0 += IP_QT) {
+        ip_scan_kernel<<<(unsigned)blocks, IP_THREADS, smem, st>>>((const uint4 *)db->d_rows, db->n_rows, dim4, queries,
+                                                                  (uint32_t)nq, (uint32_t)q0, checksum, ip_out);
+        PM_CHECK_LAUNCH();
+        count_launch();
+    }
+    return PM_OK;
+}
+
+}  // namespace pm
+
+using namespace pm;
+
+PM_EXPORT int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device) {
+    if (n && (!a || !b || !out)) return set_error(PM_ERR_ARG, "pm_l2_pairs: null pointer");
+    if (n == 0) return PM_OK;
+    if (dim > 0xffffffffull) return set_error(PM_ERR_UNSUPPORTED, "pm_l2_pairs: dim too large");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    float *d = nullptr;
+    const size_t vb = n * dim * 4;
+    PM_CUDA(cudaMalloc(&d, 2 * vb + n * 4 + 256));
+    cudaError_t e = cudaMemcpy(d, a, vb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n * dim, b, vb, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS>>>(d, d + n * dim, n, (uint32_t)dim, d + 2 * n * dim);
+        count_launch();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2 * n * dim, n * 4, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return set_error(PM_ERR_CUDA, "pm_l2_pairs: %s", cudaGetErrorString(e));
+    return PM_OK;
+}
+
+PM_EXPORT int pm_l2_batch_dev(pm_db *db, uint64_t dim, const float *queries, uint64_t n_queries, const int64_t *ids, uint64_t k,
+                              float *out, void *stream) {
+    if (!db || (n_queries && k && (!queries || !ids || !out))) return set_error(PM_ERR_ARG, "pm_l2_batch_dev: null pointer");
+    int rc = ensure_device(db->device);
+    if (rc) return rc;
+    return l2_batch_enqueue(db, dim, queries, n_queries, ids, k, out, stream ? (cudaStream_t)stream : db->stream);
+}
+
+PM_EXPORT int pm_l2_batch(pm_db *db, uint64_t dim, const float *queries, uint64_t n_queries, const int64_t *ids, uint64_t k,
+                          float *out) {
+    if (!db || (n_queries && k && (!queries || !ids || !out))) return set_error(PM_ERR_ARG, "pm_l2_batch: null pointer");
+    if (n_queries == 0 || k == 0) return PM_OK;
+    int rc = ensure_device(db->device);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    const size_t qb = n_queries * dim * 4, ib = n_queries * k * 8, ob = n_queries * k * 4;
+    void *d_in = nullptr, *d_out = nullptr;
+    if ((rc = scratch(db, 1, ib + qb, &d_in))) return rc;
+    if ((rc = scratch(db, 0, ob, &d_out))) return rc;
+    int64_t *d_ids = (int64_t *)d_in;
+    float *d_q = (float *)((char *)d_in + ib);
+    PM_CUDA(cudaMemcpyAsync(d_ids, ids, ib, cudaMemcpyHostToDevice, db->stream));
+    PM_CUDA(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, db->stream));
+    if ((rc = l2_batch_enqueue(db, dim, d_q, n_queries, d_ids, k, (float *)d_out, db->stream))) return rc;
+    PM_CUDA(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, db->stream));
+    PM_CUDA(cudaStreamSynchronize(db->stream));
+    return PM_OK;
+}
+
+PM_EXPORT int pm_ip_u32_scan_dev(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n_queries, uint32_t *checksum_out,
+                                 uint32_t *ip_out, void *stream) {
+    if (!db || (n_queries && (!queries || !checksum_out))) return set_error(PM_ERR_ARG, "pm_ip_u32_scan_dev: null pointer");
+    int rc = ensure_device(db->device);
+    if (rc) return rc;
+    return ip_scan_enqueue(db, dim, queries, n_queries, checksum_out, ip_out, stream ? (cudaStream_t)stream : db->stream);
+}
+
+PM_EXPORT int pm_ip_u32_scan(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n_queries, uint32_t *checksum_out,
+                             uint32_t *ip_out) {
+    if (!db || (n_queries && (!queries || !checksum_out))) return set_error(PM_ERR_ARG, "pm_ip_u32_scan: null pointer");
+    if (n_queries == 0) return PM_OK;
+    int rc = ensure_device(db->device);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    const size_t qb = n_queries * dim * 4, cb = n_queries * 4, pb = ip_out ? n_queries * db->n_rows * 4 : 0;
+    void *d_in = nullptr, *d_out = nullptr;
+    if ((rc = scratch(db, 1, qb, &d_in))) return rc;
+    if ((rc = scratch(db, 0, ((cb + 255) & ~255ull) + pb, &d_out))) return rc;
+    uint32_t *d_ip = pb ? (uint32_t *)((char *)d_out + ((cb + 255) & ~255ull)) : nullptr;
+    PM_CUDA(cudaMemcpyAsync(d_in, queries, qb, cudaMemcpyHostToDevice, db->stream));
+    if ((rc = ip_scan_enqueue(db, dim, (const uint32_t *)d_in, n_queries, (uint32_t *)d_out, d_ip, db->stream))) return rc;
+    PM_CUDA(cudaMemcpyAsync(checksum_out, d_out, cb, cudaMemcpyDeviceToHost, db->stream));
+    if (pb) PM_CUDA(cudaMemcpyAsync(ip_out, d_ip, pb, cudaMemcpyDeviceToHost, db->stream));
+    PM_CUDA(cudaStreamSynchronize(db->stream));
+    return PM_OK;
+}

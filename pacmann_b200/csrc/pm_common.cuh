@@ -1,0 +1,72 @@
+// Internal helpers shared by the kernels of libpacmann_cuda.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <mutex>
+
+#include "../../include/pacmann_cuda.h"
+
+#define PM_EXPORT extern "C" __attribute__((visibility("default")))
+
+struct pm_db {
+    int device;
+    uint64_t n_rows, entry_u64;
+    uint64_t *d_rows;          // [n_rows][entry_u64], 256-byte aligned (cudaMalloc)
+    cudaStream_t stream;       // compute stream of this handle
+    cudaStream_t copy_stream;  // D2H / H2D overlap stream
+    cudaEvent_t ev[4];
+    // grow-only device scratch (per handle, so handles stay re-entrant with respect to each other)
+    void *scratch[4];
+    size_t scratch_bytes[4];
+    std::mutex mu;             // serialises calls on one handle
+    int sm_count;
+};
+
+namespace pm {
+
+int set_error(int code, const char *fmt, ...);
+void count_launch(uint64_t n = 1);
+int ensure_device(int device);  // cudaSetDevice + one-time table upload; returns PM_OK / error
+int sm_count(int device);
+// grow-only scratch slot on a handle
+int scratch(pm_db *db, int slot, size_t bytes, void **out);
+
+#define PM_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return pm::set_error(PM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                                 __FILE__, __LINE__);                                                   \
+    } while (0)
+
+#define PM_CHECK_LAUNCH()                                                                               \
+    do {                                                                                                \
+        cudaError_t _e = cudaGetLastError();                                                            \
+        if (_e != cudaSuccess)                                                                          \
+            return pm::set_error(PM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                                 __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// 128-bit streaming load that does not allocate in L1 (rows are touched once per SM)
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_stream(const uint2 *p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void vxor(uint4 &a, const uint4 &b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
+__device__ __forceinline__ void vxor(uint2 &a, const uint2 &b) { a.x ^= b.x; a.y ^= b.y; }
+__device__ __forceinline__ void vzero(uint4 &a) { a = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void vzero(uint2 &a) { a = make_uint2(0, 0); }
+
+}  // namespace pm

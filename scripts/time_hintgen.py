@@ -1,0 +1,81 @@
+"""Scratch timing of pm_hintgen_dev at a BASELINE.json shape (device-resident, CUDA events)."""
+import argparse
+import ctypes as C
+import math
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from pacmann_b200 import cabi
+
+
+def params(n, fail_log2):
+    target = int(2 * math.sqrt(n))
+    c = 1
+    while c < target:
+        c *= 2
+    s = (math.ceil(n / c) + 3) // 4 * 4
+    maxq = int(math.sqrt(n) * math.log(n))
+    p = math.ceil(math.log(2) * (fail_log2 + 1)) * c
+    p = (p + 7) // 8 * 8
+    mq = 3 * int(maxq / s)
+    mq = (mq + 7) // 8 * 8
+    return c, s, p, mq
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=3201821)
+    ap.add_argument("--entry-u64", type=int, default=112)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--fail", type=int, default=8)
+    ap.add_argument("--iters", type=int, default=5)
+    a = ap.parse_args()
+    torch.cuda.init()
+    E = a.entry_u64
+    parts = a.batch // 2 if a.batch else 1
+    ps = (a.n + parts - 1) // parts
+    db = cabi.DB(n_rows=a.n, entry_u64=E, device=0)
+    # fill on device with torch (timing only; parity is covered by tests)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    nbytes = a.n * E * 8
+    ptr = db.device_ptr()
+    t = torch.empty(0, dtype=torch.int64, device="cuda")
+    buf = torch.randint(-2**62, 2**62, (a.n * E,), dtype=torch.int64, device="cuda", generator=g)
+    cabi.check(0)
+    cudart = torch.cuda.cudart()
+    cudart.cudaMemcpy(ptr, buf.data_ptr(), nbytes, 3)
+    del buf
+    rk = np.arange(44, dtype=np.uint32) * 2654435761 % (2**32)
+    jobs, outs, total_h, prf = [], [], 0, 0
+    for i in range(parts):
+        n_i = min(ps, a.n - i * ps)
+        c, s, p, mq = params(n_i, a.fail)
+        H = p + s * mq
+        out = torch.empty(H * E, dtype=torch.int64, device="cuda")
+        outs.append(out)
+        jobs.append(cabi.make_job(i * ps, n_i, c, s, rk.astype(np.uint32), 0, H, p, mq, parity_out=out.data_ptr()))
+        total_h += H
+        prf += s * H
+    print(f"parts={parts} chunk={c} set={s} primary={p} mqpc={mq} hints/part={H} prf={prf} xor_bytes={prf*E*8/1e9:.3f} GB db={nbytes/1e9:.3f} GB")
+    st = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):
+        cabi.hintgen_dev(db, jobs, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(a.iters):
+        e0.record()
+        cabi.hintgen_dev(db, jobs, st)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = min(ts)
+    print(f"hintgen: {ms:.3f} ms (all {['%.3f' % x for x in ts]})  db-scan {nbytes/ms/1e6:.1f} GB/s  prf {prf/ms/1e6:.2f} G/s  xor-gather {prf*E*8/ms/1e6:.1f} GB/s")
+
+
+if __name__ == "__main__":
+    main()

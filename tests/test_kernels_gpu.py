@@ -1,0 +1,238 @@
+"""GPU parity tests: every C-ABI entry point against the CPU oracle on identical seeded inputs.
+Bar: bit-exact (integer / byte work, and fp32 L2 in the reference's evaluation order)."""
+import numpy as np
+import pytest
+
+from util import oracle_parities, splitmix_db
+
+pytestmark = pytest.mark.gpu
+
+KEY = bytes(range(16))
+
+
+def test_expand_key_matches_oracle(cabi, oracle):
+    rng = np.random.default_rng(3)
+    for key in [KEY, bytes(16), bytes([255] * 16)] + [bytes(rng.integers(0, 256, 16, dtype=np.uint8)) for _ in range(5)]:
+        assert (cabi.expand_key(key) == oracle.expand_key(key)).all()
+
+
+def test_prf_batch_matches_oracle(cabi, oracle):
+    rng = np.random.default_rng(4)
+    rk = oracle.expand_key(KEY)
+    n = 100_000
+    tags = rng.integers(0, 2**29, n, dtype=np.uint64)
+    xs = rng.integers(0, 2**35, n, dtype=np.uint64)
+    tags[:4] = [0, 1, 2**29 - 1, 2**64 - 1]
+    xs[:4] = [0, 2**35 - 1, 2**35 - 1, 2**64 - 1]
+    assert (cabi.prf_batch(rk, tags, xs) == oracle.prf_batch(rk, tags, xs)).all()
+
+
+def test_xor_slices_reference_constants(cabi, oracle):
+    # TestXORPerf (pianopir/pir_test.go:279-290)
+    p = np.full(8, 12312312, np.uint64)
+    q = np.full(8, 12312, np.uint64)
+    cabi.xor_slices(p, q)
+    assert (p == (12312312 ^ 12312)).all()
+    # tail len%4 is not xored (aes_amd64.s:139)
+    rng = np.random.default_rng(5)
+    for n in [0, 1, 3, 4, 6, 7, 112, 113]:
+        a = rng.integers(0, 2**64, n, dtype=np.uint64)
+        b = rng.integers(0, 2**64, n, dtype=np.uint64)
+        want = oracle.xor_slices(a.copy(), b)
+        got = cabi.xor_slices(a.copy(), b)
+        assert (got == want).all()
+        assert (got[n & ~3:] == a[n & ~3:]).all()
+
+
+def _hintgen_all(cabi, db, pir_o, rk, row0=0, split=None):
+    """Run pm_hintgen for every hint of one oracle PianoPIR; returns [H][E]."""
+    P, S, M, E = pir_o.primary_hint_num, pir_o.set_size, pir_o.max_query_per_chunk, pir_o.entry_u64
+    H = P + S * M
+    out = np.zeros((H, E), np.uint64)
+    bounds = [0, H] if not split else sorted(set([0, H] + [min(H, s) for s in split]))
+    jobs = []
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        jobs.append(cabi.make_job(row0, pir_o.db_size, pir_o.chunk_size, S, rk, a, b - a, P, M, parity_out=out[a:]))
+    cabi.hintgen(db, jobs)
+    return out
+
+
+@pytest.mark.parametrize("n_rows,entry_u64,fail_log2", [
+    (18750, 4, 40),      # TestPIRBasic shape (pir_test.go:13-25)
+    (5000, 16, 8),       # 128-byte rows, G=8 NV=1
+    (3000, 80, 8),       # SIFT-shaped 640-byte rows
+    (2500, 112, 8),      # MS-MARCO-shaped 896-byte rows
+    (1000, 6, 8),        # E%4 == 2: tail words stay zero
+    (1000, 7, 8),        # odd E: 8-byte path, tail not xored
+    (777, 2, 8),         # E < 4: nothing is xored at all (reference behaviour)
+    (900, 36, 8),        # E2x = 18 -> NV = 3
+    (600, 128, 8),       # 1 KiB rows, NV = 8
+])
+def test_hintgen_matches_oracle(cabi, oracle, n_rows, entry_u64, fail_log2):
+    rows = splitmix_db(n_rows, entry_u64, seed=n_rows)
+    pir_o = oracle.PianoPIR(n_rows, entry_u64 * 8, rows.reshape(-1), fail_log2)
+    pir_o.preprocessing(KEY, repl_seed=9)
+    want = oracle_parities(pir_o)
+    db = cabi.DB(rows)
+    got = _hintgen_all(cabi, db, pir_o, cabi.expand_key(KEY))
+    assert got.shape == want.shape
+    assert (got == want).all()
+    if entry_u64 % 4:
+        assert (got[:, entry_u64 & ~3:] == 0).all()
+    db.close()
+
+
+def test_hintgen_sharded_by_hint_set_and_explicit_tags(cabi, oracle):
+    n_rows, E = 20000, 16
+    rows = splitmix_db(n_rows, E, seed=11)
+    pir_o = oracle.PianoPIR(n_rows, E * 8, rows.reshape(-1), 8)
+    pir_o.preprocessing(KEY, repl_seed=1)
+    want = oracle_parities(pir_o)
+    db = cabi.DB(rows)
+    rk = cabi.expand_key(KEY)
+    H = want.shape[0]
+    # 8-way hint-set sharding (what 8 GPUs would each compute)
+    got = _hintgen_all(cabi, db, pir_o, rk, split=[H * i // 8 for i in range(1, 8)])
+    assert (got == want).all()
+    # explicit tag / skip arrays, in a shuffled order
+    P, S, M = pir_o.primary_hint_num, pir_o.set_size, pir_o.max_query_per_chunk
+    perm = np.random.default_rng(2).permutation(H)
+    tags = perm.astype(np.uint64)
+    skip = np.where(perm < P, -1, (perm - P) // M).astype(np.int32)
+    out = np.zeros((H, E), np.uint64)
+    job = cabi.make_job(0, n_rows, pir_o.chunk_size, S, rk, 0, H, 0, 0, tags=tags, skip_chunk=skip, parity_out=out)
+    cabi.hintgen(db, [job])
+    assert (out == want[perm]).all()
+    db.close()
+
+
+def test_hintgen_batch_partitions(cabi, oracle):
+    # SimpleBatchPianoPIR layout: 16 sub-PIRs over slices of one table, ragged last partition
+    n_rows, E, batch = 40003, 16, 32
+    rows = splitmix_db(n_rows, E, seed=12)
+    b_o = oracle.SimpleBatchPianoPIR(n_rows, E * 8, batch, rows.reshape(-1), 8)
+    b_o.preprocessing(key_seed=77, repl_seed=5, threads=4)
+    db = cabi.DB(rows)
+    jobs, outs = [], []
+    for i in range(b_o.partition_num):
+        sub = b_o.sub(i)
+        H = sub.primary_hint_num + sub.set_size * sub.max_query_per_chunk
+        out = np.zeros((H, E), np.uint64)
+        outs.append(out)
+        rk = cabi.expand_key(oracle.derive_key(77, 0, b_o.partition_num, i))
+        jobs.append(cabi.make_job(i * b_o.partition_size, sub.db_size, sub.chunk_size, sub.set_size, rk, 0, H,
+                                  sub.primary_hint_num, sub.max_query_per_chunk, parity_out=out))
+    cabi.hintgen(db, jobs)
+    for i in range(b_o.partition_num):
+        assert (outs[i] == oracle_parities(b_o.sub(i))).all(), f"partition {i}"
+    db.close()
+
+
+def test_gather_rows(cabi):
+    rows = splitmix_db(1000, 10, seed=13)
+    db = cabi.DB(rows)
+    idx = np.array([0, 5, 99, 100, 499, 500, 2**40], np.uint64)
+    got = cabi.gather_rows(db, 200, 500, idx)
+    for i, r in enumerate(idx):
+        want = rows[200 + int(r)] if r < 500 else np.zeros(10, np.uint64)
+        assert (got[i] == want).all()
+    db.close()
+
+
+@pytest.mark.parametrize("n_rows,entry_u64", [(18750, 4), (5000, 16), (3000, 80), (2500, 112), (1000, 6), (1000, 7), (400, 300)])
+def test_answer_matches_oracle(cabi, oracle, n_rows, entry_u64):
+    rows = splitmix_db(n_rows, entry_u64, seed=n_rows + 1)
+    pir_o = oracle.PianoPIR(n_rows, entry_u64 * 8, rows.reshape(-1), 8)
+    rng = np.random.default_rng(6)
+    q = 37
+    # offsets: only the low log2(C) bits are meaningful for in-range use, but the reference adds the
+    # raw value (pir.go:73), so exercise out-of-chunk values too
+    offs = rng.integers(0, pir_o.chunk_size, size=(q, pir_o.set_size), dtype=np.uint32)
+    offs[0, :] = pir_o.chunk_size - 1
+    offs[1, :] = 0
+    offs[2, -1] = 2**32 - 1
+    want = np.stack([pir_o.private_query(offs[i]) for i in range(q)])
+    db = cabi.DB(rows)
+    got = cabi.answer_batch(db, 0, n_rows, pir_o.chunk_size, pir_o.set_size, offs)
+    assert (got == want).all()
+    db.close()
+
+
+def test_answer_batch_mixed_partitions(cabi, oracle):
+    n_rows, E, batch = 40003, 16, 32
+    rows = splitmix_db(n_rows, E, seed=14)
+    b_o = oracle.SimpleBatchPianoPIR(n_rows, E * 8, batch, rows.reshape(-1), 8)
+    rng = np.random.default_rng(7)
+    subs = [b_o.sub(i) for i in range(b_o.partition_num)]
+    stride = max(s.set_size for s in subs)
+    q = 96
+    part = rng.integers(0, b_o.partition_num, q)
+    offs = np.zeros((q, stride), np.uint32)
+    want = np.zeros((q, E), np.uint64)
+    for i in range(q):
+        s = subs[part[i]]
+        offs[i, :s.set_size] = rng.integers(0, s.chunk_size, s.set_size, dtype=np.uint32)
+        want[i] = s.private_query(offs[i, :s.set_size])
+    db = cabi.DB(rows)
+    got = cabi.answer_batch(db, part * b_o.partition_size, [subs[p].db_size for p in part],
+                            [subs[p].chunk_size for p in part], [subs[p].set_size for p in part], offs)
+    assert (got == want).all()
+    db.close()
+
+
+@pytest.mark.parametrize("dim", [8, 128, 192, 100, 13, 5])
+def test_l2_pairs_bit_exact(cabi, oracle, dim):
+    rng = np.random.default_rng(8)
+    n = 1000
+    a = rng.standard_normal((n, dim)).astype(np.float32) * rng.uniform(0.1, 10, (n, 1)).astype(np.float32)
+    b = rng.standard_normal((n, dim)).astype(np.float32)
+    want = np.array([oracle.l2dist(a[i], b[i]) for i in range(n)], np.float32)
+    got = cabi.l2_pairs(a, b)
+    assert got.view(np.uint32).tolist() == want.view(np.uint32).tolist()   # bit-exact fp32, tolerance 0
+
+
+@pytest.mark.parametrize("dim,m", [(128, 32), (192, 32), (20, 5)])
+def test_l2_batch_over_packed_db(cabi, oracle, dim, m):
+    rng = np.random.default_rng(9)
+    n = 5000
+    vec = rng.standard_normal((n, dim)).astype(np.float32)
+    graph = rng.integers(0, n, (n, m), dtype=np.int32)
+    if (dim + m) % 2:
+        pytest.skip("entry must be a whole number of uint64")
+    raw = oracle.pack_db(vec, graph)
+    E = (dim + m) // 2
+    db = cabi.DB(raw.reshape(n, E))
+    nq, k = 17, 96
+    queries = rng.standard_normal((nq, dim)).astype(np.float32)
+    ids = rng.integers(0, n, (nq, k), dtype=np.int64)
+    ids[0, 0] = -1
+    ids[0, 1] = n
+    got = cabi.l2_batch(db, dim, queries, ids)
+    packed_f32 = raw.view(np.float32).reshape(n, 2 * E)
+    safe = np.where((ids >= 0) & (ids < n), ids, 0)
+    want = oracle.l2dist_batch(packed_f32, dim, queries, safe)
+    want[0, 0] = np.inf
+    want[0, 1] = np.inf
+    assert got.view(np.uint32).tolist() == want.view(np.uint32).tolist()
+    db.close()
+
+
+def test_ip_scan_matches_oracle_and_closed_form(cabi, oracle):
+    # TestInnerProduct (graphann_test.go:221-284): v[i][j] = i + j, q[j] = j
+    n, d = 20000, 192
+    rows = (np.arange(n, dtype=np.uint64)[:, None] + np.arange(d, dtype=np.uint64)[None, :]).astype(np.uint32)
+    qs = np.stack([(np.arange(d, dtype=np.uint64) + t).astype(np.uint32) for t in range(19)])
+    rng = np.random.default_rng(10)
+    qs[5:] = rng.integers(0, 2**32, (14, d), dtype=np.uint32)
+    db = cabi.DB(rows.view(np.uint64).reshape(n, d // 2))
+    cs, ip = cabi.ip_u32_scan(db, d, qs, want_products=True)
+    want = oracle.ip_scan(rows, qs)
+    assert (cs == want).all()
+    # closed form for t = 0: sum_i sum_j (i+j) j mod 2^32
+    j = np.arange(d, dtype=object)
+    closed = sum(int(((i + j) * j).sum()) for i in range(n)) % 2**32
+    assert int(cs[0]) == closed
+    for t in (0, 7):
+        for i in (0, 1, n - 1):
+            assert int(ip[t, i]) == oracle.inner_product(rows[i], qs[t])
+    db.close()
