@@ -61,6 +61,8 @@ uint64_t pm_launch_count(void);
 
 int pm_db_create(const uint64_t *rows_host, uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
 int pm_db_create_empty(uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
+/* borrow an existing device allocation (16-byte aligned, on `device`); the caller keeps ownership */
+int pm_db_wrap(void *device_rows, uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
 int pm_db_upload(pm_db *db, uint64_t row0, uint64_t n_rows, const uint64_t *rows_host);
 int pm_db_info(const pm_db *db, uint64_t *n_rows, uint64_t *entry_u64, int *device, void **device_ptr);
 int pm_db_destroy(pm_db *db);

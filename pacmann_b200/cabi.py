@@ -43,6 +43,7 @@ SIGNATURES = {
     "pm_launch_count": (C.c_uint64, []),
     "pm_db_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "pm_db_create_empty": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "pm_db_wrap": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "pm_db_upload": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "pm_db_info": (C.c_int, [C.c_void_p, u64p, u64p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "pm_db_destroy": (C.c_int, [C.c_void_p]),
@@ -125,9 +126,11 @@ def launch_count():
 class DB:
     """pm_db handle: device-resident rows[n_rows][entry_u64] (rawDB, pianopir/pir.go:28-39)."""
 
-    def __init__(self, rows=None, n_rows=None, entry_u64=None, device=0):
+    def __init__(self, rows=None, n_rows=None, entry_u64=None, device=0, device_ptr=None):
         self.h = C.c_void_p()
-        if rows is not None:
+        if device_ptr is not None:
+            check(lib().pm_db_wrap(device_ptr, n_rows, entry_u64, device, C.byref(self.h)))
+        elif rows is not None:
             rows = _arr(rows, np.uint64)
             if rows.ndim == 2:
                 n_rows, entry_u64 = rows.shape

@@ -24,6 +24,7 @@ struct pm_db {
     size_t scratch_bytes[4];
     std::mutex mu;             // serialises calls on one handle
     int sm_count;
+    bool owns_rows;            // false for pm_db_wrap handles
 };
 
 namespace pm {

@@ -96,7 +96,18 @@ PM_EXPORT int pm_device_count(int *count) {
     return PM_OK;
 }
 
+static int db_new(void *borrowed, uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
+
 PM_EXPORT int pm_db_create_empty(uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out) {
+    return db_new(nullptr, n_rows, entry_u64, device, out);
+}
+PM_EXPORT int pm_db_wrap(void *device_rows, uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out) {
+    if (!device_rows) return set_error(PM_ERR_ARG, "pm_db_wrap: null device pointer");
+    if ((uintptr_t)device_rows % 16) return set_error(PM_ERR_ARG, "pm_db_wrap: device pointer must be 16-byte aligned");
+    return db_new(device_rows, n_rows, entry_u64, device, out);
+}
+
+static int db_new(void *borrowed, uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out) {
     if (!out) return set_error(PM_ERR_ARG, "pm_db_create: null out pointer");
     *out = nullptr;
     if (entry_u64 == 0) return set_error(PM_ERR_ARG, "pm_db_create: entry_u64 must be > 0");
@@ -111,17 +122,23 @@ PM_EXPORT int pm_db_create_empty(uint64_t n_rows, uint64_t entry_u64, int device
     db->sm_count = sm_count(device);
     for (int i = 0; i < 4; i++) { db->scratch[i] = nullptr; db->scratch_bytes[i] = 0; }
     size_t bytes = n_rows * entry_u64 * 8;
-    cudaError_t e = cudaMalloc(&db->d_rows, bytes ? bytes : 256);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        delete db;
-        return set_error(PM_ERR_NOMEM, "cudaMalloc(%zu) for the table failed: %s", bytes, cudaGetErrorString(e));
+    cudaError_t e = cudaSuccess;
+    db->owns_rows = (borrowed == nullptr);
+    if (borrowed) {
+        db->d_rows = (uint64_t *)borrowed;
+    } else {
+        e = cudaMalloc(&db->d_rows, bytes ? bytes : 256);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            delete db;
+            return set_error(PM_ERR_NOMEM, "cudaMalloc(%zu) for the table failed: %s", bytes, cudaGetErrorString(e));
+        }
     }
     e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&db->ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
-        cudaFree(db->d_rows);
+        if (db->owns_rows) cudaFree(db->d_rows);
         delete db;
         return set_error(PM_ERR_CUDA, "stream/event creation failed: %s", cudaGetErrorString(e));
     }
@@ -180,7 +197,7 @@ PM_EXPORT int pm_db_destroy(pm_db *db) {
             if (db->scratch[i]) cudaFree(db->scratch[i]);
             cudaEventDestroy(db->ev[i]);
         }
-        cudaFree(db->d_rows);
+        if (db->owns_rows) cudaFree(db->d_rows);
         cudaStreamDestroy(db->stream);
         cudaStreamDestroy(db->copy_stream);
     }

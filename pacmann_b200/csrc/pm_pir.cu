@@ -201,6 +201,10 @@ __global__ void __launch_bounds__(HG_THREADS, 1) hintgen_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < NV; k++)
                 if ((uint32_t)(k * G + gl) < ev) o[k * G] = par[k];
+            // words past 4*(E/4) are never xored by the reference (A3): they stay zero
+            VT z;
+            vzero(z);
+            for (uint32_t col = NV * G + gl; col < ev; col += G) o[col - gl] = z;
         }
     }
 }

@@ -38,18 +38,11 @@ def main():
     E = a.entry_u64
     parts = a.batch // 2 if a.batch else 1
     ps = (a.n + parts - 1) // parts
-    db = cabi.DB(n_rows=a.n, entry_u64=E, device=0)
-    # fill on device with torch (timing only; parity is covered by tests)
     g = torch.Generator(device="cuda").manual_seed(1)
     nbytes = a.n * E * 8
-    ptr = db.device_ptr()
-    t = torch.empty(0, dtype=torch.int64, device="cuda")
     buf = torch.randint(-2**62, 2**62, (a.n * E,), dtype=torch.int64, device="cuda", generator=g)
-    cabi.check(0)
-    cudart = torch.cuda.cudart()
-    cudart.cudaMemcpy(ptr, buf.data_ptr(), nbytes, 3)
-    del buf
-    rk = np.arange(44, dtype=np.uint32) * 2654435761 % (2**32)
+    db = cabi.DB(n_rows=a.n, entry_u64=E, device=0, device_ptr=buf.data_ptr())
+    rk = (np.arange(44, dtype=np.uint64) * 2654435761 % (2**32)).astype(np.uint32)
     jobs, outs, total_h, prf = [], [], 0, 0
     for i in range(parts):
         n_i = min(ps, a.n - i * ps)
@@ -61,18 +54,20 @@ def main():
         total_h += H
         prf += s * H
     print(f"parts={parts} chunk={c} set={s} primary={p} mqpc={mq} hints/part={H} prf={prf} xor_bytes={prf*E*8/1e9:.3f} GB db={nbytes/1e9:.3f} GB")
-    st = torch.cuda.current_stream().cuda_stream
-    for _ in range(2):
-        cabi.hintgen_dev(db, jobs, st)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ts = []
-    for _ in range(a.iters):
-        e0.record()
-        cabi.hintgen_dev(db, jobs, st)
-        e1.record()
+    stream = torch.cuda.Stream()
+    st = stream.cuda_stream
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            cabi.hintgen_dev(db, jobs, st)
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(a.iters):
+            e0.record(stream)
+            cabi.hintgen_dev(db, jobs, st)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
     ms = min(ts)
     print(f"hintgen: {ms:.3f} ms (all {['%.3f' % x for x in ts]})  db-scan {nbytes/ms/1e6:.1f} GB/s  prf {prf/ms/1e6:.2f} G/s  xor-gather {prf*E*8/ms/1e6:.1f} GB/s")
 
