@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: PianoPIR hint-generation DB-scan GB/s on the MS-MARCO-shaped batch-PIR
+workload (BASELINE.json configs[3]: 3 201 821 entries x 896 B, batch 32 -> 16 sub-PIRs, FailureProbLog2 8).
+
+A "step" is one full SimpleBatchPianoPIR.Preprocessing() (pianopir/batch-pir.go:119-155): every primary and
+backup hint parity of all 16 sub-PIRs over the whole DB.  The DB is replicated per GPU and hints are sharded
+by hint set across ranks; with N > 1 the parities are gathered on rank 0 over NCCL inside the
+timed region, so the job is the same at every N ("strong" scaling: total work fixed).
+
+  value  = N*EB / t            DB-scan GB/s, DB resident in HBM, parities left in HBM (rank 0 after the gather)
+  e2e    = same metric through the host-buffer C-ABI call pm_hintgen(): job descriptors in, parities copied
+           back into pinned host memory inside the timed region (what the cgo bridge would do per Preprocessing)
+  roofline: algorithmic HBM bytes B_hbm = N*EB + sum_parts (P+B)*EB (DB read once + parities written once,
+           SURVEY.md 8d) / kernel time, against MEASURED_PEAKS.json hbm_gbs.  The kernel is NOT HBM-bound
+           (see DESIGN.md): xor_gather GB/s and PRF/s are reported next to it.
+  cpu_baseline: the C oracle (a port: the reference is Go and cannot be built here) on 1 thread, as the
+           reference runs (ThreadNum = 1), on a bounded sample (4 of the 16 sub-PIRs).
+  --impl reference: the same oracle with all host threads on the full workload (rank 0 only).
+
+Only the cpu_baseline / --impl reference legs import oracle/; the timed GPU path is the C-ABI library.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_ROWS = 3201821
+ENTRY_U64 = 112
+BATCH = 32
+FAIL_LOG2 = 8
+SEED = 20241600
+
+
+def pir_params(n, fail_log2):
+    """NewPianoPIR / NewPianoPIRClient parameter derivation (pianopir/pir.go:487-494, 138-142)."""
+    target = int(2 * math.sqrt(n))
+    c = 1
+    while c < target:
+        c *= 2
+    s = (math.ceil(n / c) + 3) // 4 * 4
+    maxq = int(math.sqrt(n) * math.log(n))
+    p = math.ceil(math.log(2) * (fail_log2 + 1)) * c
+    p = (p + 7) // 8 * 8
+    mq = 3 * int(maxq / s)
+    mq = (mq + 7) // 8 * 8
+    return c, s, p, mq
+
+
+def partitions(n, batch):
+    parts = batch // 2
+    ps = (n + parts - 1) // parts
+    out = []
+    for i in range(parts):
+        n_i = min(ps, n - i * ps)
+        c, s, p, mq = pir_params(n_i, FAIL_LOG2)
+        out.append(dict(row0=i * ps, n_rows=n_i, chunk=c, set=s, primary=p, mqpc=mq, hints=p + s * mq))
+    return out
+
+
+def gen_db(n_rows, entry_u64, row0=0, rows=None):
+    """Synthetic rawDB rows [row0, row0+rows): rng.Uint64() per word as TestBatchPIRPerf (pir_test.go:218-223),
+    from a seeded, block-indexed generator so any slice can be produced independently."""
+    rows = n_rows - row0 if rows is None else rows
+    out = np.empty((rows, entry_u64), np.uint64)
+    blk = 1 << 16
+    r = row0
+    while r < row0 + rows:
+        b = r // blk
+        lo, hi = b * blk, min((b + 1) * blk, n_rows)
+        data = np.random.Generator(np.random.PCG64(SEED + b)).integers(0, 2**64, size=(hi - lo, entry_u64), dtype=np.uint64)
+        a, z = max(r, lo), min(row0 + rows, hi)
+        out[a - row0:z - row0] = data[a - lo:z - lo]
+        r = z
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def result(self):
+        self.stop_flag = True
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU oracle port with all host threads on the full workload; rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import oracle as o
+    o.lib()
+    threads = os.cpu_count() or 1
+    parts = partitions(N_ROWS, BATCH)
+    db = gen_db(N_ROWS, ENTRY_U64)
+    pir = o.SimpleBatchPianoPIR(N_ROWS, ENTRY_U64 * 8, BATCH, db.reshape(-1), FAIL_LOG2)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        pir.preprocessing(key_seed=SEED + it, repl_seed=it, threads=threads)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    val = N_ROWS * ENTRY_U64 * 8 / t / 1e9
+    line = {
+        "impl": "reference", "metric": "pir_hintgen_db_scan_gbs", "value": val, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": workload_config(parts, 1),
+        "cpu_baseline": {"value": val, "unit": "GB/s", "cores": threads, "kind": "port",
+                         "sample": "full workload: all 16 sub-PIRs, OpenMP over sub-PIRs then hint ranges"},
+        "e2e": {"value": val, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Go + Plan-9 asm and cannot be built here (no Go toolchain): this is the C oracle port "
+                "(same AES-NI / AVX2 instructions), an upper bound on the Go code's speed",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(parts, n_gpus):
+    return {
+        "workload": "MS-MARCO-shaped batch-PIR hint preprocessing (BASELINE.json configs[3])",
+        "n_entries": N_ROWS, "entry_bytes": ENTRY_U64 * 8, "batch_size": BATCH, "sub_pirs": len(parts),
+        "fail_prob_log2": FAIL_LOG2, "chunk_size": parts[0]["chunk"], "set_size": parts[0]["set"],
+        "primary_hints": parts[0]["primary"], "backup_hints": parts[0]["set"] * parts[0]["mqpc"],
+        "sharding": f"hint-set x{n_gpus}, DB replicated per GPU",
+        "l2_policy": "inputs_exceed_l2 (2.87 GB table vs 126 MB L2)",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from pacmann_b200 import cabi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the b200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    cabi.lib()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    parts = partitions(N_ROWS, BATCH)
+    E = ENTRY_U64
+    db_bytes = N_ROWS * E * 8
+    total_hints = sum(p["hints"] for p in parts)
+    n_prf = sum(p["set"] * (p["hints"] - p["mqpc"]) for p in parts)     # S*H' : backup group c skips chunk c
+    b_hbm = db_bytes + total_hints * E * 8
+    b_xor = n_prf * E * 8
+
+    # ---- inputs: synthetic DB generated on the host, uploaded once (replicated per GPU) ----
+    host_db = gen_db(N_ROWS, E)
+    db = cabi.DB(host_db, device=local_rank)
+    rk_all = []
+    from pacmann_b200.keys import derive_key  # product-side key derivation (no oracle import here)
+    for i in range(len(parts)):
+        rk_all.append(cabi.expand_key(derive_key(SEED, 0, len(parts), i)))
+
+    # ---- hint-set sharding: rank r owns hints [H*r/N, H*(r+1)/N) of every sub-PIR ----
+    def shard(h):
+        return h * rank // world, h * (rank + 1) // world
+
+    my_hints = [shard(p["hints"]) for p in parts]
+    my_count = sum(b - a for a, b in my_hints)
+    max_count = max(sum(p["hints"] * (r + 1) // world - p["hints"] * r // world for p in parts) for r in range(world))
+    out_dev = torch.zeros(max_count * E, dtype=torch.int64, device=dev)      # this rank's parities (padded)
+    gather_list = [torch.empty_like(out_dev) for _ in range(world)] if (world > 1 and rank == 0) else None
+
+    def make_jobs(base_ptr):
+        jobs, off = [], 0
+        for p, (a, b), rk in zip(parts, my_hints, rk_all):
+            jobs.append(cabi.make_job(p["row0"], p["n_rows"], p["chunk"], p["set"], rk, a, b - a, p["primary"], p["mqpc"],
+                                      parity_out=base_ptr + off * E * 8))
+            off += b - a
+        return jobs
+
+    jobs_dev = make_jobs(out_dev.data_ptr())
+    stream = torch.cuda.Stream(device=dev)
+
+    def step_device():
+        cabi.hintgen_dev(db, jobs_dev, stream.cuda_stream)
+        if world > 1:
+            dist.gather(out_dev, gather_list, dst=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step_device()
+        barrier()
+        l0 = cabi.launch_count()
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ek0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        ek1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        e0.record(stream)
+        for i in range(args.steps):
+            ek0[i].record(stream)
+            cabi.hintgen_dev(db, jobs_dev, stream.cuda_stream)
+            ek1[i].record(stream)
+            if world > 1:
+                dist.gather(out_dev, gather_list, dst=0)
+        e1.record(stream)
+        barrier()
+        clocks = sampler.result()
+        launches = cabi.launch_count() - l0
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(ek0, ek1)]))
+    t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t[0]) / args.steps
+    kern_ms = float(t[1])
+    value = db_bytes / (ms_step * 1e-3) / 1e9
+
+    # ---- end-to-end through the host-buffer C-ABI (pinned host outputs, D2H inside the timed region) ----
+    out_host = torch.empty(my_count * E, dtype=torch.int64).pin_memory()
+    jobs_host = make_jobs(out_host.data_ptr())
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        cabi.hintgen(db, jobs_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        cabi.hintgen(db, jobs_host)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0])
+    h2d_bytes = len(parts) * 256 * world
+    d2h_bytes = total_hints * E * 8
+
+    # ---- spot check (outside every timed region): a few parities recomputed from the PRF definition ----
+    verified = None
+    if rank == 0:
+        verified = spot_check(cabi, host_db, parts, rk_all, my_hints, out_host.numpy().view(np.uint64).reshape(-1, E))
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        b_hbm_rank = db_bytes + max_count * E * 8      # per GPU: whole DB read once + its share of the parities
+        achieved = b_hbm_rank / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "pir_hintgen_db_scan_gbs", "value": value, "unit": "GB/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(parts, world),
+            "clocks": clocks, "gpu_launches": int(launches) * world,
+            "e2e": {"value": db_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
+                    "timer": "host perf_counter around the synchronous pm_hintgen() call, max over ranks",
+                    "note": "DB is uploaded once at pm_db_create (as rawDB is built once in NewSimpleBatchPianoPIR); "
+                            "per step only job descriptors go in and all parities come back to pinned host memory"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "hintgen_kernel<uint4,8,7,...>",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": b_hbm_rank,
+                         "binding_term": "not HBM: L1 data-pipe wavefronts (row gather + AES T-table LDS) and ALU; see DESIGN.md",
+                         "xor_gather_gbs": b_xor / world / (kern_ms * 1e-3) / 1e9,
+                         "prf_per_s": n_prf / world / (kern_ms * 1e-3)},
+            "verified_vs_prf_definition": verified,
+            "reference_published": {"msmarco_prep_s": "9-10 (1 thread, reproduction/msmarco/README.md:26)"},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(parts)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def spot_check(cabi, host_db, parts, rk_all, my_hints, got):
+    """Recompute a handful of parities on the host from pm_prf_batch offsets + numpy XOR (no oracle)."""
+    ok, off = True, 0
+    rng = np.random.default_rng(1)
+    for p, (a, b), rk in zip(parts, my_hints, rk_all):
+        if b > a:
+            for h in {a, b - 1, int(rng.integers(a, b))}:
+                cs = np.arange(p["set"], dtype=np.uint64)
+                offs = cabi.prf_batch(rk, np.full(p["set"], h, np.uint64), cs) & np.uint64(p["chunk"] - 1)
+                rows = cs * np.uint64(p["chunk"]) + offs
+                skip = -1 if h < p["primary"] else (h - p["primary"]) // p["mqpc"]
+                sel = rows[(rows < p["n_rows"]) & (cs != skip if skip >= 0 else True)]
+                want = np.bitwise_xor.reduce(host_db[p["row0"] + sel.astype(np.int64)], axis=0)
+                ok = ok and bool((got[off + h - a] == want).all())
+        off += b - a
+    return ok
+
+
+def cpu_baseline(parts):
+    """1-thread C oracle (as the reference runs: ThreadNum = 1, pianopir/batch-pir.go:16) on 4 of the 16 sub-PIRs."""
+    from oracle import oracle as o
+    o.lib()
+    n_sample = 4
+    rows = sum(p["n_rows"] for p in parts[:n_sample])
+    t = 0.0
+    for i in range(n_sample):
+        p = parts[i]
+        sub = gen_db(N_ROWS, ENTRY_U64, p["row0"], p["n_rows"])
+        pir = o.PianoPIR(p["n_rows"], ENTRY_U64 * 8, sub.reshape(-1), FAIL_LOG2)
+        t0 = time.perf_counter()
+        pir.preprocessing(o.derive_key(SEED, 0, len(parts), i), repl_seed=i, threads=1)
+        t += time.perf_counter() - t0
+    return {"value": rows * ENTRY_U64 * 8 / t / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": f"sub-PIRs 0..{n_sample - 1} of 16 ({rows} rows, {rows * ENTRY_U64 * 8 / 1e9:.2f} GB), "
+                      f"{t:.1f} s of single-thread CPU work", "seconds": t}
+
+
+if __name__ == "__main__":
+    main()
