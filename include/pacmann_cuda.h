@@ -114,6 +114,8 @@ int pm_answer_batch_dev(pm_db *db, const uint64_t *row0, const uint64_t *n_rows,
 
 /* A9: squared L2 in the reference's exact fp32 order.  out[i] = L2Dist(a[i], b[i]), rows of `dim` floats. */
 int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device);
+/* out[i] = L2Dist(vecs[i], query): one query against n host vectors (SearchKNN's per-step and re-rank call sites) */
+int pm_l2_query(const float *vecs, uint64_t n, uint64_t dim, const float *query, float *out, int device);
 /* out[q*k + j] = L2Dist(first `dim` fp32 of db row ids[q*k + j], queries[q]);  ids outside [0, n_rows) give +inf. */
 int pm_l2_batch(pm_db *db, uint64_t dim, const float *queries, uint64_t n_queries, const int64_t *ids, uint64_t k,
                 float *out);

@@ -57,6 +57,7 @@ SIGNATURES = {
     "pm_answer_batch": (C.c_int, [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64, C.c_void_p]),
     "pm_answer_batch_dev": (C.c_int, [C.c_void_p] * 6 + [C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pm_l2_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]),
+    "pm_l2_query": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
     "pm_l2_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_l2_batch_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pm_ip_u32_scan": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
@@ -233,6 +234,14 @@ def l2_pairs(a, b, device=0):
     assert a.shape == b.shape and a.ndim == 2
     out = np.zeros(a.shape[0], np.float32)
     check(lib().pm_l2_pairs(_ptr(a), _ptr(b), a.shape[0], a.shape[1], _ptr(out), device))
+    return out
+
+
+def l2_query(vecs, query, device=0):
+    vecs, query = _arr(vecs, np.float32), _arr(query, np.float32)
+    assert vecs.ndim == 2 and query.size == vecs.shape[1]
+    out = np.zeros(vecs.shape[0], np.float32)
+    check(lib().pm_l2_query(_ptr(vecs), vecs.shape[0], vecs.shape[1], _ptr(query), _ptr(out), device))
     return out
 
 

@@ -1,0 +1,280 @@
+// Host-side mirror of the reference's `graphann` package and PIRGraphInfo adapter.  See graphann.hpp.
+#include "graphann.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+#include <unordered_map>
+
+namespace graphann {
+
+using pianopir::Mix64;
+
+static void check(int rc, const char *what) {
+    if (rc != PM_OK) throw std::runtime_error(std::string(what) + ": " + pm_last_error());
+}
+
+float L2Dist(const std::vector<float> &v1, const std::vector<float> &v2, int device) {
+    float d = 0;
+    check(pm_l2_query(v1.data(), 1, v1.size(), v2.data(), &d, device), "pm_l2_query");
+    return d;
+}
+// distances of many host vectors to one query: one launch (the batched form of the L2Dist call sites)
+static void dist_many(const std::vector<const float *> &vecs, int64_t dim, const float *query, int device,
+                      std::vector<float> *out) {
+    out->assign(vecs.size(), 0.f);
+    if (vecs.empty()) return;
+    std::vector<float> flat(vecs.size() * (size_t)dim);
+    for (size_t i = 0; i < vecs.size(); i++) memcpy(&flat[i * dim], vecs[i], (size_t)dim * 4);
+    check(pm_l2_query(flat.data(), vecs.size(), (uint64_t)dim, query, out->data(), device), "pm_l2_query");
+}
+
+// ---------------------------------------------------------------------------------------------
+int BasicGraphInfo::GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) {
+    out->resize(ids.size());
+    for (size_t i = 0; i < ids.size(); i++) {
+        Vertex &v = (*out)[i];
+        v.Id = ids[i];
+        v.Neighbors.assign(Graph + ids[i] * M, Graph + (ids[i] + 1) * M);
+        v.Vector.assign(Vectors + ids[i] * Dim, Vectors + (ids[i] + 1) * Dim);
+    }
+    return 0;
+}
+int BasicGraphInfo::GetStartVertex(std::vector<Vertex> *out) {
+    int64_t targetNum = (int64_t)std::sqrt((double)N);
+    std::vector<int64_t> batch(targetNum);
+    for (int64_t i = 0; i < targetNum; i++) batch[i] = i;
+    return GetVertexInfo(batch, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+void PackEntry(int64_t dim, int64_t m, const float *vector, const int32_t *neighbors, uint64_t *entry) {
+    uint8_t *o = (uint8_t *)entry;  // little-endian host: LE f32 bit patterns then LE u32 ids
+    memcpy(o, vector, (size_t)dim * 4);
+    for (int64_t j = 0; j < m; j++) {
+        uint32_t v = (uint32_t)neighbors[j];
+        memcpy(o + dim * 4 + j * 4, &v, 4);
+    }
+}
+void Entry2VectorAndNeighbors(int64_t dim, int64_t m, const uint64_t *entry, std::vector<float> *vector,
+                              std::vector<int64_t> *neighbors) {
+    const uint8_t *e = (const uint8_t *)entry;
+    vector->resize(dim);
+    memcpy(vector->data(), e, (size_t)dim * 4);
+    neighbors->resize(m);
+    for (int64_t j = 0; j < m; j++) {
+        uint32_t v;
+        memcpy(&v, e + dim * 4 + j * 4, 4);
+        (*neighbors)[j] = (int64_t)v;
+    }
+}
+
+PIRGraphInfo::PIRGraphInfo(int64_t N, int64_t Dim, int64_t M, const int32_t *graph, const float *vectors, bool skipPrep,
+                           bool nonPrivate, uint64_t seed, int device)
+    : N(N), Dim(Dim), M(M), graph(graph), vectors(vectors), skipPrep(skipPrep), NonPrivateMode(nonPrivate), seed(seed),
+      device(device) {}
+PIRGraphInfo::~PIRGraphInfo() { delete PIR; }
+
+void PIRGraphInfo::Preprocess() {
+    DBEntryByteNum = (uint64_t)(Dim * 4 + M * 4);
+    const uint64_t E = DBEntryByteNum / 8;
+    rawDB.assign((uint64_t)N * E, 0);
+    for (int64_t i = 0; i < N; i++) PackEntry(Dim, M, vectors + i * Dim, graph + i * M, &rawDB[(uint64_t)i * E]);
+    DBTotalSize = (uint64_t)N * DBEntryByteNum;
+    PIR = new pianopir::SimpleBatchPianoPIR((uint64_t)N, DBEntryByteNum, (uint64_t)M, rawDB.data(), rawDB.size(), 8, device);
+    PIR->SetSeeds(Mix64(seed, 1), Mix64(seed, 2));
+    if (skipPrep) PIR->DummyPreprocessing();
+    else PIR->Preprocessing();
+}
+
+int PIRGraphInfo::GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) {
+    totalQueryNum += (int64_t)ids.size();
+    out->resize(ids.size());
+    if (NonPrivateMode) {
+        for (size_t i = 0; i < ids.size(); i++) {
+            Vertex &v = (*out)[i];
+            v.Id = ids[i];
+            v.Vector.assign(vectors + ids[i] * Dim, vectors + (ids[i] + 1) * Dim);
+            v.Neighbors.assign(graph + ids[i] * M, graph + (ids[i] + 1) * M);
+        }
+        return 0;
+    }
+    std::vector<uint64_t> indices(ids.begin(), ids.end());
+    std::vector<std::vector<uint64_t>> responses;
+    if (PIR->Query(indices, &responses) != 0) return -1;
+    for (size_t i = 0; i < ids.size(); i++) {
+        Vertex &v = (*out)[i];
+        v.Id = ids[i];
+        Entry2VectorAndNeighbors(Dim, M, responses[i].data(), &v.Vector, &v.Neighbors);
+        bool correctQ = true;
+        for (int64_t j = 0; j < M; j++)
+            if (v.Neighbors[j] != (int64_t)(uint32_t)graph[ids[i] * M + j]) { correctQ = false; break; }
+        if (correctQ) succQueryNum++;
+    }
+    return 0;
+}
+
+int PIRGraphInfo::GetStartVertex(std::vector<Vertex> *out) {
+    int64_t targetNum = (int64_t)std::sqrt((double)N);
+    std::vector<uint8_t> added((size_t)N, 0);
+    out->resize(targetNum);
+    uint64_t ctr = 0;
+    const uint64_t s = Mix64(seed, 3);
+    for (int64_t i = 0; i < targetNum; i++) {
+        int64_t x = (int64_t)(Mix64(s, ctr++) % (uint64_t)N);
+        while (added[x]) x = (int64_t)(Mix64(s, ctr++) % (uint64_t)N);
+        added[x] = 1;
+        Vertex &v = (*out)[i];
+        v.Id = x;
+        v.Vector.assign(vectors + x * Dim, vectors + (x + 1) * Dim);
+        v.Neighbors.assign(graph + x * M, graph + (x + 1) * M);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+void GraphANNFrontend::Preprocess() {
+    Graph->Preprocess();
+    if (Graph->GetStartVertex(&StartVertices) != 0) throw std::runtime_error("GetStartVertex failed");
+}
+
+namespace {
+struct VD { float dist; int64_t id; };
+// container/heap's up/down/Push/Pop with Less = dist < dist (search.go:92-111)
+struct ExploreQueue {
+    std::vector<VD> a;
+    void up(int64_t j) {
+        for (;;) {
+            int64_t i = (j - 1) / 2;
+            if (i == j || j <= 0 || !(a[j].dist < a[i].dist)) break;
+            std::swap(a[i], a[j]);
+            j = i;
+        }
+    }
+    void down(int64_t i0, int64_t n) {
+        int64_t i = i0;
+        for (;;) {
+            int64_t j1 = 2 * i + 1;
+            if (j1 >= n || j1 < 0) break;
+            int64_t j = j1, j2 = j1 + 1;
+            if (j2 < n && a[j2].dist < a[j1].dist) j = j2;
+            if (!(a[j].dist < a[i].dist)) break;
+            std::swap(a[i], a[j]);
+            i = j;
+        }
+    }
+    void Push(VD v) { a.push_back(v); up((int64_t)a.size() - 1); }
+    VD Pop() {
+        int64_t n = (int64_t)a.size() - 1;
+        std::swap(a[0], a[n]);
+        down(0, n);
+        VD v = a.back();
+        a.pop_back();
+        return v;
+    }
+    size_t Len() const { return a.size(); }
+};
+}  // namespace
+
+int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking,
+                                std::vector<int64_t> *ret, std::vector<int64_t> *stepRet) {
+    int64_t n, dim, m;
+    Graph->GetMetadata(&n, &dim, &m);
+    const int device = Graph->Device();
+    std::unordered_map<int64_t, int64_t> reachStep;
+    std::unordered_map<int64_t, Vertex> knownVertices;
+    std::vector<int64_t> knownOrder;  // insertion order, only to make iteration deterministic
+    ExploreQueue toBeExplored;
+    const uint64_t rseed = Mix64(randSeed, queryCounter++);
+    uint64_t rctr = 0;
+    std::vector<float> dists;
+
+    if (!benchmarking) {  // search.go:129-148
+        std::vector<const float *> ptrs;
+        for (auto &v : StartVertices) ptrs.push_back(v.Vector.data());
+        dist_many(ptrs, dim, queryVector, device, &dists);
+        std::vector<size_t> order(StartVertices.size());
+        for (size_t i = 0; i < order.size(); i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dists[a] < dists[b]; });
+        for (size_t i = 0; (int64_t)toBeExplored.Len() < parallel && i < order.size(); i++) {
+            const Vertex &v = StartVertices[order[i]];
+            if (knownVertices.count(v.Id)) continue;
+            knownVertices[v.Id] = v;
+            knownOrder.push_back(v.Id);
+            toBeExplored.Push({dists[order[i]], v.Id});
+            reachStep[v.Id] = 0;
+        }
+    }
+
+    std::vector<Vertex> queryResults;
+    for (int64_t step = 0; step < maxStep; step++) {  // search.go:150-208
+        std::vector<int64_t> batchQ;
+        batchQ.reserve((size_t)(parallel * m));
+        for (int64_t rept = 0; rept < parallel; rept++) {
+            if (toBeExplored.Len() == 0 || benchmarking) {
+                for (int64_t i = 0; i < m; i++) batchQ.push_back((int64_t)(Mix64(rseed, rctr++) % (uint64_t)n));
+            } else {
+                VD item = toBeExplored.Pop();
+                const Vertex &v = knownVertices[item.id];
+                batchQ.insert(batchQ.end(), v.Neighbors.begin(), v.Neighbors.end());
+            }
+        }
+        if (Graph->GetVertexInfo(batchQ, &queryResults) != 0) return -1;
+        if (benchmarking) continue;
+        // newly discovered vertices of this step: one distance launch for all of them
+        std::vector<size_t> fresh;
+        for (size_t i = 0; i < queryResults.size(); i++) {
+            const Vertex &v = queryResults[i];
+            if (knownVertices.count(v.Id)) continue;
+            bool dup = false;  // a duplicate id inside this batch is "already known" by the time the loop reaches it
+            for (size_t f : fresh) dup = dup || queryResults[f].Id == v.Id;
+            if (dup) continue;
+            bool ok = false;
+            for (int64_t nb : v.Neighbors) if (nb != 0) { ok = true; break; }
+            if (ok) fresh.push_back(i);
+        }
+        std::vector<const float *> ptrs;
+        for (size_t i : fresh) ptrs.push_back(queryResults[i].Vector.data());
+        dist_many(ptrs, dim, queryVector, device, &dists);
+        for (size_t t = 0; t < fresh.size(); t++) {
+            const Vertex &v = queryResults[fresh[t]];
+            knownVertices[v.Id] = v;
+            knownOrder.push_back(v.Id);
+            reachStep[v.Id] = step;
+            toBeExplored.Push({dists[t], v.Id});
+        }
+    }
+
+    // search.go:210-233
+    std::vector<const float *> ptrs;
+    for (int64_t id : knownOrder) ptrs.push_back(knownVertices[id].Vector.data());
+    dist_many(ptrs, dim, queryVector, device, &dists);
+    std::vector<VD> all(knownOrder.size());
+    for (size_t i = 0; i < all.size(); i++) all[i] = {dists[i], knownOrder[i]};
+    std::sort(all.begin(), all.end(), [](const VD &a, const VD &b) { return a.dist < b.dist || (a.dist == b.dist && a.id < b.id); });
+    ret->assign(k, -1);
+    stepRet->assign(k, -1);
+    for (int64_t i = 0; i < k && i < (int64_t)all.size(); i++) {
+        (*ret)[i] = all[i].id;
+        (*stepRet)[i] = reachStep[all[i].id];
+    }
+    return 0;
+}
+
+int GraphANNFrontend::SearchKNNBatch(const float *queryVectors, int64_t nq, int64_t k, int64_t maxStep, int64_t parallel,
+                                     bool benchmarking, std::vector<int64_t> *ret, std::vector<int64_t> *stepRet) {
+    int64_t n, dim, m;
+    Graph->GetMetadata(&n, &dim, &m);
+    ret->assign((size_t)(nq * k), -1);
+    stepRet->assign((size_t)(nq * k), -1);
+    std::vector<int64_t> r, s;
+    for (int64_t i = 0; i < nq; i++) {  // search.go:236-245: a plain loop
+        if (SearchKNN(queryVectors + i * dim, k, maxStep, parallel, benchmarking, &r, &s) != 0) return -1;
+        memcpy(&(*ret)[i * k], r.data(), (size_t)k * 8);
+        memcpy(&(*stepRet)[i * k], s.data(), (size_t)k * 8);
+    }
+    return 0;
+}
+
+}  // namespace graphann

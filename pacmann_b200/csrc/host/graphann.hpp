@@ -1,0 +1,91 @@
+// Host-side mirror of the reference's `graphann` package (graphann/search.go, build_graph.go:119-134)
+// and of the PIRGraphInfo adapter in private-search.go:334-531, in C++ (no Go toolchain here).
+// Distance evaluation goes through the C-ABI (pm_l2_query / pm_l2_batch); traversal control stays on
+// the host as it stays in Go.  Tie rules where Go leaves the order unspecified:
+// start-vertex ranking is stable in input order, the explore queue is container/heap's binary heap,
+// the final ranking orders by (distance, id).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "pianopir.hpp"
+
+namespace graphann {
+
+struct Vertex {  // search.go:12-16
+    int64_t Id = 0;
+    std::vector<int64_t> Neighbors;
+    std::vector<float> Vector;
+};
+
+class GetGraphInfo {  // search.go:20-25
+public:
+    virtual ~GetGraphInfo() {}
+    virtual void Preprocess() = 0;
+    virtual void GetMetadata(int64_t *n, int64_t *dim, int64_t *m) const = 0;
+    virtual int GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) = 0;
+    virtual int GetStartVertex(std::vector<Vertex> *out) = 0;
+    virtual int Device() const { return 0; }
+};
+
+// L2Dist (build_graph.go:119-127) for one pair: a single-distance launch, kept for API parity
+float L2Dist(const std::vector<float> &v1, const std::vector<float> &v2, int device = 0);
+
+class BasicGraphInfo : public GetGraphInfo {  // search.go:29-65
+public:
+    BasicGraphInfo(int64_t N, int64_t Dim, int64_t M, const int32_t *graph, const float *vectors)
+        : N(N), Dim(Dim), M(M), Graph(graph), Vectors(vectors) {}
+    void Preprocess() override {}
+    void GetMetadata(int64_t *n, int64_t *dim, int64_t *m) const override { *n = N; *dim = Dim; *m = M; }
+    int GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) override;
+    int GetStartVertex(std::vector<Vertex> *out) override;
+    int64_t N, Dim, M;
+    const int32_t *Graph;   // [N][M]
+    const float *Vectors;   // [N][Dim]
+};
+
+// PIRGraphInfo (private-search.go:334-531): the graph behind a SimpleBatchPianoPIR.
+class PIRGraphInfo : public GetGraphInfo {
+public:
+    PIRGraphInfo(int64_t N, int64_t Dim, int64_t M, const int32_t *graph, const float *vectors, bool skipPrep,
+                 bool nonPrivate, uint64_t seed, int device = 0);
+    ~PIRGraphInfo() override;
+    void Preprocess() override;                                                        // :355-412
+    void GetMetadata(int64_t *n, int64_t *dim, int64_t *m) const override { *n = N; *dim = Dim; *m = M; }
+    int GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) override;  // :441-506
+    int GetStartVertex(std::vector<Vertex> *out) override;                             // :508-531
+    int Device() const override { return device; }
+    int64_t N, Dim, M;
+    const int32_t *graph;
+    const float *vectors;
+    bool skipPrep, NonPrivateMode;
+    uint64_t DBEntryByteNum = 0, DBTotalSize = 0;
+    std::vector<uint64_t> rawDB;
+    pianopir::SimpleBatchPianoPIR *PIR = nullptr;
+    int64_t totalQueryNum = 0, succQueryNum = 0;
+    uint64_t seed;
+    int device;
+};
+
+// Entry2VectorAndNeighbors (private-search.go:418-439) and its inverse (the packing loop :371-397)
+void Entry2VectorAndNeighbors(int64_t dim, int64_t m, const uint64_t *entry, std::vector<float> *vector,
+                              std::vector<int64_t> *neighbors);
+void PackEntry(int64_t dim, int64_t m, const float *vector, const int32_t *neighbors, uint64_t *entry);
+
+class GraphANNFrontend {  // search.go:69-245
+public:
+    explicit GraphANNFrontend(GetGraphInfo *g) : Graph(g) {}
+    void Preprocess();
+    void GetMetadata(int64_t *n, int64_t *dim, int64_t *m) const { Graph->GetMetadata(n, dim, m); }
+    // returns the k nearest ids and the step at which each was reached (-1 padding), search.go:114-234
+    int SearchKNN(const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking,
+                  std::vector<int64_t> *ret, std::vector<int64_t> *stepRet);
+    int SearchKNNBatch(const float *queryVectors, int64_t nq, int64_t k, int64_t maxStep, int64_t parallel,
+                       bool benchmarking, std::vector<int64_t> *ret, std::vector<int64_t> *stepRet);
+    GetGraphInfo *Graph;
+    std::vector<Vertex> StartVertices;
+    uint64_t randSeed = 0;   // stands in for Go's global math/rand in the "random query" branch (search.go:155-159)
+    uint64_t queryCounter = 0;
+};
+
+}  // namespace graphann

@@ -1,0 +1,276 @@
+// Flat C handles over the C++ host mirror (pianopir:: / graphann::) so the Python tests and benchmarks
+// can drive it through ctypes.  Not part of the drop-in boundary (that is include/pacmann_cuda.h).
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "graphann.hpp"
+#include "pianopir.hpp"
+
+#define PMH extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string t_err;
+#define PMH_TRY try {
+#define PMH_CATCH(rv)                  \
+    }                                  \
+    catch (const std::exception &e) {  \
+        t_err = e.what();              \
+        return rv;                     \
+    }
+
+using pianopir::PianoPIR;
+using pianopir::SimpleBatchPianoPIR;
+
+PMH const char *pmh_last_error() { return t_err.c_str(); }
+PMH uint64_t pmh_mix64(uint64_t seed, uint64_t ctr) { return pianopir::Mix64(seed, ctr); }
+PMH void pmh_derive_key(uint64_t seed, uint64_t epoch, uint64_t parts, uint64_t i, uint8_t out[16]) {
+    auto k = pianopir::DeriveKey(seed, epoch, parts, i);
+    memcpy(out, k.b, 16);
+}
+PMH uint64_t pmh_prf(const uint32_t *rk, uint64_t tag, uint64_t x) {
+    std::vector<uint32_t> v(rk, rk + 44);
+    return pianopir::PRFEvalWithLongKeyAndTag(v, tag, x);
+}
+
+// ---- standalone PianoPIR (owns its DeviceDB) ----
+struct PirBox {
+    pianopir::DeviceDB *db;
+    PianoPIR *pir;
+};
+PMH void *pmh_pir_new(uint64_t n, uint64_t entry_bytes, const uint64_t *rawDB, uint64_t fail_log2, int device) {
+    PMH_TRY
+    auto *b = new PirBox();
+    b->db = new pianopir::DeviceDB(rawDB, n, entry_bytes / 8, device);
+    b->pir = new PianoPIR(n, entry_bytes, b->db, 0, fail_log2);
+    return b;
+    PMH_CATCH(nullptr)
+}
+PMH void pmh_pir_free(void *h) {
+    auto *b = (PirBox *)h;
+    if (!b) return;
+    delete b->pir;
+    delete b->db;
+    delete b;
+}
+static PianoPIR *as_pir(void *h, int boxed) { return boxed ? ((PirBox *)h)->pir : (PianoPIR *)h; }
+PMH void pmh_pir_set_seeds(void *h, int boxed, uint64_t key_seed, uint64_t epoch, uint64_t repl_seed) {
+    auto &c = as_pir(h, boxed)->client;
+    c.keySeed = key_seed;
+    c.keyEpoch = epoch;
+    c.replSeed = repl_seed;
+}
+PMH int pmh_pir_preprocessing(void *h, int boxed) {
+    PMH_TRY
+    as_pir(h, boxed)->Preprocessing();
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH int pmh_pir_dummy_preprocessing(void *h, int boxed) {
+    PMH_TRY
+    as_pir(h, boxed)->DummyPreprocessing();
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH int pmh_pir_query(void *h, int boxed, uint64_t idx, int real, uint64_t *out) {
+    PMH_TRY
+    std::vector<uint64_t> ret;
+    int rc = as_pir(h, boxed)->Query(idx, real != 0, &ret);
+    memcpy(out, ret.data(), ret.size() * 8);
+    return rc;
+    PMH_CATCH(-100)
+}
+PMH int pmh_pir_private_query(void *h, int boxed, const uint32_t *offsets, uint64_t *out) {
+    PMH_TRY
+    PianoPIR *p = as_pir(h, boxed);
+    std::vector<uint32_t> o(offsets, offsets + p->config.SetSize);
+    std::vector<uint64_t> ret;
+    p->server.PrivateQuery(o, &ret);
+    memcpy(out, ret.data(), ret.size() * 8);
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH int pmh_pir_nonprivate_query(void *h, int boxed, uint64_t idx, uint64_t *out) {
+    PMH_TRY
+    std::vector<uint64_t> ret;
+    int rc = as_pir(h, boxed)->server.NonePrivateQuery(idx, &ret);
+    memcpy(out, ret.data(), ret.size() * 8);
+    return rc;
+    PMH_CATCH(-100)
+}
+PMH uint64_t pmh_pir_get(void *h, int boxed, int what) {
+    PianoPIR *p = as_pir(h, boxed);
+    switch (what) {
+    case 0: return p->config.DBEntrySize;
+    case 1: return p->config.DBSize;
+    case 2: return p->config.ChunkSize;
+    case 3: return p->config.SetSize;
+    case 4: return p->client.MaxQueryNum;
+    case 5: return p->client.primaryHintNum;
+    case 6: return p->client.maxQueryPerChunk;
+    case 7: return p->client.FinishedQueryNum;
+    case 8: return p->config.ThreadNum;
+    case 9: return p->config.FailureProbLog2;
+    }
+    return 0;
+}
+PMH const uint64_t *pmh_pir_table(void *h, int boxed, int what) {
+    auto &c = as_pir(h, boxed)->client;
+    switch (what) {
+    case 0: return c.primaryShortTag.data();
+    case 1: return c.primaryParity.data();
+    case 2: return c.primaryProgramPoint.data();
+    case 3: return c.replacementIdx.data();
+    case 4: return c.replacementVal.data();
+    case 5: return c.backupShortTag.data();
+    case 6: return c.backupParity.data();
+    case 7: return c.QueryHistogram.data();
+    }
+    return nullptr;
+}
+PMH const uint32_t *pmh_pir_long_key(void *h, int boxed) { return as_pir(h, boxed)->client.longKey.data(); }
+PMH double pmh_pir_local_storage(void *h, int boxed) { return as_pir(h, boxed)->LocalStorageSize(); }
+PMH double pmh_pir_comm_cost(void *h, int boxed) { return as_pir(h, boxed)->CommCostPerQuery(); }
+
+// ---- SimpleBatchPianoPIR ----
+PMH void *pmh_batch_new(uint64_t n, uint64_t entry_bytes, uint64_t batch, const uint64_t *rawDB, uint64_t len,
+                        uint64_t fail_log2, int device) {
+    PMH_TRY
+    return new SimpleBatchPianoPIR(n, entry_bytes, batch, rawDB, len, fail_log2, device);
+    PMH_CATCH(nullptr)
+}
+PMH void pmh_batch_free(void *h) { delete (SimpleBatchPianoPIR *)h; }
+PMH void pmh_batch_set_seeds(void *h, uint64_t key_seed, uint64_t repl_seed) { ((SimpleBatchPianoPIR *)h)->SetSeeds(key_seed, repl_seed); }
+PMH int pmh_batch_preprocessing(void *h) {
+    PMH_TRY
+    ((SimpleBatchPianoPIR *)h)->Preprocessing();
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH int pmh_batch_dummy_preprocessing(void *h) {
+    PMH_TRY
+    ((SimpleBatchPianoPIR *)h)->DummyPreprocessing();
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH int pmh_batch_query(void *h, const uint64_t *idx, uint64_t n, uint64_t *out) {
+    PMH_TRY
+    auto *b = (SimpleBatchPianoPIR *)h;
+    std::vector<uint64_t> v(idx, idx + n);
+    std::vector<std::vector<uint64_t>> ret;
+    int rc = b->Query(v, &ret);
+    if (rc != 0) {
+        t_err = "index out of range";
+        return rc;
+    }
+    const uint64_t E = b->config.DBEntrySize;
+    for (uint64_t i = 0; i < n; i++) memcpy(out + i * E, ret[i].data(), E * 8);
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH void *pmh_batch_sub(void *h, uint64_t i) { return ((SimpleBatchPianoPIR *)h)->subPIR[i]; }
+PMH uint64_t pmh_batch_get(void *h, int what) {
+    auto *b = (SimpleBatchPianoPIR *)h;
+    switch (what) {
+    case 0: return b->config.PartitionNum;
+    case 1: return b->config.PartitionSize;
+    case 2: return b->FinishedBatchNum;
+    case 3: return b->QueriesMadeInPartition;
+    case 4: return b->SupportBatchNum;
+    case 5: return b->serverQueries;
+    case 6: return b->serverLaunches;
+    case 7: return b->CommCostPerBatchOnline();
+    case 8: return b->CommCostPerBatchOffline();
+    }
+    return 0;
+}
+PMH double pmh_batch_local_storage(void *h) { return ((SimpleBatchPianoPIR *)h)->LocalStorageSize(); }
+PMH double pmh_batch_prep_time(void *h) { return ((SimpleBatchPianoPIR *)h)->PreprocessingTime(); }
+
+// ---- graphann ----
+PMH float pmh_l2dist(const float *a, const float *b, uint64_t dim, int device) {
+    PMH_TRY
+    std::vector<float> x(a, a + dim), y(b, b + dim);
+    return graphann::L2Dist(x, y, device);
+    PMH_CATCH(-1.0f)
+}
+struct FrontBox {
+    graphann::GetGraphInfo *g;
+    graphann::GraphANNFrontend *f;
+};
+PMH void *pmh_frontend_basic(int64_t n, int64_t dim, int64_t m, const int32_t *graph, const float *vectors) {
+    PMH_TRY
+    auto *b = new FrontBox();
+    b->g = new graphann::BasicGraphInfo(n, dim, m, graph, vectors);
+    b->f = new graphann::GraphANNFrontend(b->g);
+    return b;
+    PMH_CATCH(nullptr)
+}
+PMH void *pmh_frontend_pir(int64_t n, int64_t dim, int64_t m, const int32_t *graph, const float *vectors, int skip_prep,
+                           int non_private, uint64_t seed, int device) {
+    PMH_TRY
+    auto *b = new FrontBox();
+    b->g = new graphann::PIRGraphInfo(n, dim, m, graph, vectors, skip_prep != 0, non_private != 0, seed, device);
+    b->f = new graphann::GraphANNFrontend(b->g);
+    return b;
+    PMH_CATCH(nullptr)
+}
+PMH void pmh_frontend_free(void *h) {
+    auto *b = (FrontBox *)h;
+    if (!b) return;
+    delete b->f;
+    delete b->g;
+    delete b;
+}
+PMH int pmh_frontend_preprocess(void *h) {
+    PMH_TRY
+    ((FrontBox *)h)->f->Preprocess();
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH int64_t pmh_frontend_start_ids(void *h, int64_t *out, int64_t cap) {
+    auto &sv = ((FrontBox *)h)->f->StartVertices;
+    for (int64_t i = 0; i < (int64_t)sv.size() && i < cap; i++) out[i] = sv[i].Id;
+    return (int64_t)sv.size();
+}
+PMH void pmh_frontend_set_start_ids(void *h, const int64_t *ids, int64_t n) {
+    auto *b = (FrontBox *)h;
+    std::vector<int64_t> v(ids, ids + n);
+    // start vertices are plaintext copies of dataset rows (private-search.go:508-531), whichever ids are chosen
+    int64_t N, D, M;
+    b->g->GetMetadata(&N, &D, &M);
+    if (auto *pg = dynamic_cast<graphann::PIRGraphInfo *>(b->g)) {
+        b->f->StartVertices.resize(n);
+        for (int64_t i = 0; i < n; i++) {
+            auto &vx = b->f->StartVertices[i];
+            vx.Id = ids[i];
+            vx.Vector.assign(pg->vectors + ids[i] * D, pg->vectors + (ids[i] + 1) * D);
+            vx.Neighbors.assign(pg->graph + ids[i] * M, pg->graph + (ids[i] + 1) * M);
+        }
+    } else {
+        b->g->GetVertexInfo(v, &b->f->StartVertices);
+    }
+}
+PMH void pmh_frontend_set_rand_seed(void *h, uint64_t seed) {
+    ((FrontBox *)h)->f->randSeed = seed;
+    ((FrontBox *)h)->f->queryCounter = 0;
+}
+PMH int pmh_frontend_search_knn(void *h, const float *queries, int64_t nq, int64_t k, int64_t max_step, int64_t parallel,
+                                int benchmarking, int64_t *ret, int64_t *step_ret) {
+    PMH_TRY
+    std::vector<int64_t> r, s;
+    int rc = ((FrontBox *)h)->f->SearchKNNBatch(queries, nq, k, max_step, parallel, benchmarking != 0, &r, &s);
+    if (rc != 0) return rc;
+    memcpy(ret, r.data(), r.size() * 8);
+    memcpy(step_ret, s.data(), s.size() * 8);
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH void *pmh_frontend_pir_handle(void *h) {
+    auto *pg = dynamic_cast<graphann::PIRGraphInfo *>(((FrontBox *)h)->g);
+    return pg ? pg->PIR : nullptr;
+}
+PMH int64_t pmh_frontend_stat(void *h, int what) {
+    auto *pg = dynamic_cast<graphann::PIRGraphInfo *>(((FrontBox *)h)->g);
+    if (!pg) return 0;
+    return what == 0 ? pg->totalQueryNum : pg->succQueryNum;
+}

