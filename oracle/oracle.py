@@ -52,6 +52,7 @@ def lib():
             "orc_pir_free": (None, [C.c_void_p]),
             "orc_pir_initialization": (None, [C.c_void_p, u8p]),
             "orc_pir_preprocessing": (None, [C.c_void_p, u8p, C.c_uint64, C.c_int]),
+            "orc_pir_preprocessing_range": (None, [C.c_void_p, u8p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]),
             "orc_pir_dummy_preprocessing": (None, [C.c_void_p, u8p]),
             "orc_pir_private_query": (None, [C.c_void_p, u32p, u64p]),
             "orc_pir_nonprivate_query": (C.c_int, [C.c_void_p, C.c_uint64, u64p]),
@@ -209,6 +210,9 @@ class PianoPIR:
 
     def preprocessing(self, key, repl_seed=0, threads=1):
         lib().orc_pir_preprocessing(self.h, _p(key_bytes(key), u8p), repl_seed, threads)
+
+    def preprocessing_range(self, key, h0, h1, repl_seed=0, do_repl=False):
+        lib().orc_pir_preprocessing_range(self.h, _p(key_bytes(key), u8p), repl_seed, h0, h1, int(do_repl))
 
     def dummy_preprocessing(self, key):
         lib().orc_pir_dummy_preprocessing(self.h, _p(key_bytes(key), u8p))

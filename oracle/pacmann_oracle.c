@@ -517,6 +517,13 @@ ORC_API void orc_pir_preprocessing(orc_pir *p, const uint8_t key[16], uint64_t r
         preprocessing_range(p, a, b, repl_seed, t == 0);
     }
 }
+/* hint-set shard of Preprocessing: only hints [h0,h1) are computed (the others stay zero) -- what one GPU of an
+ * N-GPU run owns.  Replacement values are produced only when do_repl != 0. */
+ORC_API void orc_pir_preprocessing_range(orc_pir *p, const uint8_t key[16], uint64_t repl_seed, uint64_t h0, uint64_t h1,
+                                         int do_repl) {
+    orc_pir_initialization(p, key);
+    preprocessing_range(p, h0, h1, repl_seed, do_repl);
+}
 /* DummyPreprocessing : pir.go:520-523 */
 ORC_API void orc_pir_dummy_preprocessing(orc_pir *p, const uint8_t key[16]) {
     orc_pir_initialization(p, key);

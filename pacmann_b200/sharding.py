@@ -1,0 +1,34 @@
+"""Hint-set sharding of PianoPIR preprocessing across GPUs: every hint's parity depends only on
+(key, tag, DB), so rank r of N computes hints [H*r/N, H*(r+1)/N) of every sub-PIR over its own replica of the DB,
+with no data-path exchange; the parities are then gathered on the consumer.  Pure index arithmetic, shared by
+bench.py and the multi-process tests."""
+
+
+def shard_range(n_hints, rank, world):
+    """half-open hint range owned by `rank`"""
+    return n_hints * rank // world, n_hints * (rank + 1) // world
+
+
+def shard_sizes(hints_per_part, world):
+    """per-rank total hint counts over all sub-PIRs"""
+    return [sum(shard_range(h, r, world)[1] - shard_range(h, r, world)[0] for h in hints_per_part) for r in range(world)]
+
+
+def padded_shard_len(hints_per_part, world):
+    """every rank's buffer is padded to the largest shard so a fixed-size gather works"""
+    return max(shard_sizes(hints_per_part, world))
+
+
+def assemble(gathered, hints_per_part, world, entry_u64):
+    """gathered[r] = rank r's flat buffer (its shard of sub-PIR 0, then of sub-PIR 1, ...; padded).
+    Returns one [n_hints][entry_u64] array per sub-PIR in hint-number order."""
+    import numpy as np
+    out = [np.zeros((h, entry_u64), np.uint64) for h in hints_per_part]
+    for r in range(world):
+        buf = np.asarray(gathered[r]).reshape(-1, entry_u64)
+        off = 0
+        for i, h in enumerate(hints_per_part):
+            a, b = shard_range(h, r, world)
+            out[i][a:b] = buf[off:off + (b - a)]
+            off += b - a
+    return out

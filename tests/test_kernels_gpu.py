@@ -236,3 +236,53 @@ def test_ip_scan_matches_oracle_and_closed_form(cabi, oracle):
         for i in (0, 1, n - 1):
             assert int(ip[t, i]) == oracle.inner_product(rows[i], qs[t])
     db.close()
+
+
+# ---- committed golden vectors (tests/golden/, generated with an independent AES / a scalar fp32 emulation) ----
+def _gold(name):
+    import json, os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+
+
+def test_golden_key_schedule_and_prf(cabi):
+    kat = _gold("aes_prf_kat.json")
+    for v in kat["schedule"]:
+        assert cabi.expand_key(bytes.fromhex(v["key"])).tolist() == v["words"]
+    by_key = {}
+    for v in kat["prf"]:
+        by_key.setdefault(v["key"], []).append(v)
+    for key, vs in by_key.items():
+        rk = cabi.expand_key(bytes.fromhex(key))
+        got = cabi.prf_batch(rk, [v["tag"] for v in vs], [v["x"] for v in vs])
+        assert got.tolist() == [v["out"] for v in vs]
+
+
+def test_golden_l2_and_inner_product(cabi):
+    kat = _gold("distance_kat.json")
+    for v in kat["l2"]:
+        a = np.array(v["a"], np.uint32).view(np.float32)[None, :]
+        b = np.array(v["b"], np.uint32).view(np.float32)[None, :]
+        assert int(cabi.l2_pairs(a, b).view(np.uint32)[0]) == v["out_bits"], v["dim"]
+        assert int(cabi.l2_query(a, b[0]).view(np.uint32)[0]) == v["out_bits"], v["dim"]
+    for v in kat["ip"]:
+        a = np.array(v["a"], np.uint32)
+        db = cabi.DB(a.view(np.uint64).reshape(1, -1))
+        assert int(cabi.ip_u32_scan(db, a.size, np.array(v["b"], np.uint32))[0]) == v["out"]
+        db.close()
+
+
+def test_hintgen_low_bits_path_equals_full_prf(cabi, oracle):
+    """The hint kernel evaluates only the low bytes of the PRF (pm_aes.cuh prf_low); check it against the
+    full-width generic kernel for a chunk size that needs more than 16 bits is impossible at test sizes, so pin
+    the 16-bit path on every (tag, chunk) of one instance instead: offsets recovered from single-row parities."""
+    n, E = 4096, 4
+    rows = np.zeros((n, E), np.uint64)
+    rows[:, 0] = np.arange(n)                       # row r holds r: a one-chunk parity reveals the offset
+    db = cabi.DB(rows)
+    rk = cabi.expand_key(KEY)
+    C, S, H = 4096, 1, 5000
+    out = np.zeros((H, E), np.uint64)
+    cabi.hintgen(db, [cabi.make_job(0, n, C, S, rk, 0, H, H, 0, parity_out=out)])
+    want = oracle.prf_batch(rk, np.arange(H, dtype=np.uint64), np.zeros(H, np.uint64)) & np.uint64(C - 1)
+    assert (out[:, 0] == want).all()
+    db.close()

@@ -1,0 +1,75 @@
+"""Multi-process (gloo, world_size 2 and 3) test of the hint-set sharding used by bench.py --gpus N: each rank
+computes only its hint range of every sub-PIR, the shards are gathered on rank 0 and assembled, and the result must
+equal the unsharded tables.  The per-shard compute is the CPU oracle here (no GPU in this container); on the GPU box
+the same index arithmetic (pacmann_b200/sharding.py) drives pm_hintgen_dev + an NCCL gather."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, result_file):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as o
+    from pacmann_b200 import sharding
+    from util import splitmix_db
+
+    n, E, batch = 9001, 6, 8
+    rows = splitmix_db(n, E, seed=99)
+    full = o.SimpleBatchPianoPIR(n, E * 8, batch, rows.reshape(-1), 8)
+    parts = full.partition_num
+    subs = [full.sub(i) for i in range(parts)]
+    hints = [s.primary_hint_num + s.set_size * s.max_query_per_chunk for s in subs]
+    pad = sharding.padded_shard_len(hints, world)
+    mine = np.zeros((pad, E), np.uint64)
+    off = 0
+    for i, s in enumerate(subs):
+        a, b = sharding.shard_range(hints[i], rank, world)
+        key = o.derive_key(7, 0, parts, i)
+        s.preprocessing_range(key, a, b)
+        tab = np.concatenate([s.table("primary_parity"), s.table("backup_parity").reshape(-1, E)])
+        mine[off:off + b - a] = tab[a:b]
+        off += b - a
+    t = torch.from_numpy(mine.view(np.int64))
+    gathered = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+    dist.gather(t, gathered, dst=0)
+    ok = True
+    if rank == 0:
+        tables = sharding.assemble([g.numpy().view(np.uint64) for g in gathered], hints, world, E)
+        full.preprocessing(key_seed=7, repl_seed=0, threads=2)
+        for i in range(parts):
+            s = full.sub(i)
+            want = np.concatenate([s.table("primary_parity"), s.table("backup_parity").reshape(-1, E)])
+            ok = ok and bool((tables[i] == want).all())
+        open(result_file, "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_hint_set_sharding_gathers_to_the_unsharded_tables(world, tmp_path):
+    port = 29500 + os.getpid() % 2000 + world
+    result = tmp_path / "result.txt"
+    mp.spawn(_worker, args=(world, port, str(result)), nprocs=world, join=True)
+    assert result.read_text() == "ok"
+
+
+def test_shard_ranges_partition_the_hints():
+    from pacmann_b200 import sharding
+    for h in (0, 1, 7, 24416, 104448):
+        for world in (1, 2, 3, 4, 8):
+            r = [sharding.shard_range(h, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == h
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
