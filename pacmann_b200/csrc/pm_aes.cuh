@@ -129,4 +129,44 @@ __device__ __forceinline__ uint32_t prf_low(const AesTab<NTAB> &T, const RK &rk,
     return out ^ rk[40] ^ x;  // final AddRoundKey, then the MMO feed-forward (xor with input word 0)
 }
 
+// ---- the same PRF as a resumable computation -----------------------------------------------------
+// prf_rounds<.., RA, RB> runs AES rounds RA..RB (1-based; 10 = final round + feed-forward) on `st`, so the hint
+// kernel can interleave slices of the next group's PRF with the row loads of the current group.  After round 10
+// st.s0 holds what prf_low() returns.  Identical arithmetic, different schedule.
+struct PrfState { uint32_t s0, s1, s2, s3; };
+
+template <int NTAB, int NB, int RA, int RB, typename RK>
+__device__ __forceinline__ void prf_rounds(const AesTab<NTAB> &T, const RK &rk, const PrfTagPart &g, uint32_t x, PrfState &st) {
+#pragma unroll
+    for (int r = RA; r <= RB; r++) {
+        if (r == 1) {
+            uint32_t w0 = x ^ rk[0];
+            st.s0 = g.g0 ^ T.t0(byte_of(w0, 0));
+            st.s1 = g.g1 ^ T.t3(byte_of(w0, 3));
+            st.s2 = g.g2 ^ T.t2(byte_of(w0, 2));
+            st.s3 = g.g3 ^ T.t1(byte_of(w0, 1));
+        } else if (r < 9) {
+            aes_round(T, st.s0, st.s1, st.s2, st.s3, rk[4 * r], rk[4 * r + 1], rk[4 * r + 2], rk[4 * r + 3]);
+        } else if (r == 9) {
+            uint32_t s0 = st.s0, s1 = st.s1, s2 = st.s2, s3 = st.s3;
+            st.s0 = T.t0(byte_of(s0, 0)) ^ T.t1(byte_of(s1, 1)) ^ T.t2(byte_of(s2, 2)) ^ T.t3(byte_of(s3, 3)) ^ rk[36];
+            st.s1 = T.t0(byte_of(s1, 0)) ^ T.t1(byte_of(s2, 1)) ^ T.t2(byte_of(s3, 2)) ^ T.t3(byte_of(s0, 3)) ^ rk[37];
+            if (NB == 4) {
+                st.s2 = T.t0(byte_of(s2, 0)) ^ T.t1(byte_of(s3, 1)) ^ T.t2(byte_of(s0, 2)) ^ T.t3(byte_of(s1, 3)) ^ rk[38];
+                st.s3 = T.t0(byte_of(s3, 0)) ^ T.t1(byte_of(s0, 1)) ^ T.t2(byte_of(s1, 2)) ^ T.t3(byte_of(s2, 3)) ^ rk[39];
+            }
+        } else {
+            uint32_t out = T.sbox(byte_of(st.s0, 0)) | (T.sbox(byte_of(st.s1, 1)) << 8);
+            if (NB == 4) out |= (T.sbox(byte_of(st.s2, 2)) << 16) | (T.sbox(byte_of(st.s3, 3)) << 24);
+            st.s0 = out ^ rk[40] ^ x;
+        }
+    }
+}
+// rounds of phase PH when the 10 rounds are cut into NPH slices
+template <int PH, int NPH>
+struct PrfPhase {
+    static constexpr int first = PH * 10 / NPH + 1;
+    static constexpr int last = (PH + 1) * 10 / NPH;
+};
+
 }  // namespace pm

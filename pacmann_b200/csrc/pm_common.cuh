@@ -33,6 +33,7 @@ int set_error(int code, const char *fmt, ...);
 void count_launch(uint64_t n = 1);
 int ensure_device(int device);  // cudaSetDevice + one-time table upload; returns PM_OK / error
 int sm_count(int device);
+const void *zero_page(int device);  // 4 KB of device zeros, allocated once per device
 // grow-only scratch slot on a handle
 int scratch(pm_db *db, int slot, size_t bytes, void **out);
 

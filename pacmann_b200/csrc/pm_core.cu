@@ -24,6 +24,7 @@ constexpr int MAX_DEV = 64;
 static std::mutex g_dev_mu;
 static bool g_dev_ready[MAX_DEV] = {};
 static int g_sm_count[MAX_DEV] = {};
+static void *g_zero[MAX_DEV] = {};
 
 // device < 0: keep the calling thread's current device
 int ensure_device(int device) {
@@ -48,11 +49,14 @@ int ensure_device(int device) {
         g_sm_count[device] = prop.multiProcessorCount;
         int rc = upload_tables();
         if (rc) return rc;
+        PM_CUDA(cudaMalloc(&g_zero[device], 4096));
+        PM_CUDA(cudaMemset(g_zero[device], 0, 4096));
         g_dev_ready[device] = true;
     }
     return PM_OK;
 }
 int sm_count(int device) { return g_sm_count[device]; }
+const void *zero_page(int device) { return g_zero[device]; }
 
 int scratch(pm_db *db, int slot, size_t bytes, void **out) {
     if (bytes == 0) bytes = 256;

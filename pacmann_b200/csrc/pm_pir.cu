@@ -1,5 +1,6 @@
 // PianoPIR kernels for sm_100a: AES-PRF, key schedule, hint generation (A5/A7), server answer
 // (A6/A8), row gather, xorSlices.  See include/pacmann_cuda.h for the reference seams.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -138,14 +139,59 @@ __device__ __forceinline__ uint2 ldg_row(const uint2 *p, bool pred) {
     return v;
 }
 
-template <typename VT, int G, int NV, int NTAB, int NB, int U>
+// ---- software pipelining and load policy ------------------------------------------------------------
+// Details of the inner loop, all about keeping the pipes busy:
+//  * the PRF of the NEXT group of G chunks is evaluated in NPH = G/U slices interleaved with the U-row load
+//    batches of the CURRENT group, so each warp hides its own row-load latency behind its own AES work;
+//  * no per-load predicates: a (hint, chunk) pair that must not contribute (zero padding past n_rows, the
+//    skipped chunk, inactive lanes, chunks past S in the last group) still loads a real, harmless row -- a
+//    different one per pair, so no L2 line becomes a hot spot -- and bit 31 of the exchanged row word says
+//    whether to XOR it.  The common case (every pair of the warp's batch contributes) is one warp-uniform
+//    vote and the unmasked 3-input XOR;
+//  * FULL = the row is an exact multiple of G vectors (896 B, 640 B, 128 B rows): no column predicates either.
+constexpr uint32_t ROW_CONTRIB = 0x80000000u;
+template <typename VT, int G, int NV, int NTAB, int NB, int U, bool FULL, int PH, int NPH, typename RK>
+__device__ __forceinline__ void hg_phase(const AesTab<NTAB> &T, const RK &R, const PrfTagPart &g, uint32_t c_next,
+                                         PrfState &st, uint32_t row_cur, int gbase, int gl, const VT *base,
+                                         uint32_t ev, uint32_t evx, VT (&par)[NV]) {
+    VT buf[U][NV];
+    uint32_t rr[U];
+    bool all_in = true;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        rr[u] = __shfl_sync(0xffffffffu, row_cur, gbase + PH * U + u);
+        all_in = all_in && (rr[u] & ROW_CONTRIB);
+        const VT *rp = base + (uint64_t)(rr[u] & ~ROW_CONTRIB) * ev;
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+            if (FULL) buf[u][k] = ldg_stream(rp + k * G);
+            else buf[u][k] = ldg_row(rp + k * G, (uint32_t)(k * G + gl) < evx);
+        }
+    }
+    prf_rounds<NTAB, NB, PrfPhase<PH, NPH>::first, PrfPhase<PH, NPH>::last>(T, R, g, c_next, st);
+    if (__all_sync(0xffffffffu, all_in)) {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int k = 0; k < NV; k++) vxor(par[k], buf[u][k]);
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (rr[u] & ROW_CONTRIB) {
+#pragma unroll
+                for (int k = 0; k < NV; k++) vxor(par[k], buf[u][k]);
+            }
+    }
+}
+
+template <typename VT, int G, int NV, int NTAB, int NB, int U, bool FULL>
 __global__ void __launch_bounds__(HG_THREADS, 1) hintgen_kernel(const __grid_constant__ HintParams P) {
     extern __shared__ uint32_t smem[];
     aes_tab_fill<NTAB>(smem, c_te0);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const AesTab<NTAB> T{smem + lane};
-    constexpr int GPW = 32 / G;
+    constexpr int GPW = 32 / G, NPH = G / U;
     const int gl = lane & (G - 1), gbase = lane & ~(G - 1), gw = lane / G;
     const uint32_t hints_per_tile = (HG_THREADS / 32) * GPW;
     const uint32_t ev = P.ev, evx = P.evx;
@@ -174,34 +220,31 @@ __global__ void __launch_bounds__(HG_THREADS, 1) hintgen_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < NV; k++) vzero(par[k]);
 
+        // row word exchanged inside the group: bits 0..30 = a row that is always safe to read, bit 31 = contributes
+        auto to_row = [&](uint32_t c, uint32_t prf) -> uint32_t {
+            const uint32_t off = prf & cmask, row = (c << cshift) + off;
+            const bool in = c < S && row < n_rows;
+            const uint32_t safe = in ? row : (off < n_rows ? off : 0);
+            return safe | ((in && active && (int32_t)c != skip) ? ROW_CONTRIB : 0u);
+        };
+        PrfState st;
+        prf_rounds<NTAB, NB, 1, 10>(T, R, g, (uint32_t)gl, st);  // prologue: rows of the first group
+        uint32_t row_next = to_row(gl, st.s0);
         for (uint32_t c0 = 0; c0 < S; c0 += G) {
-            const uint32_t c = c0 + gl;
-            const uint32_t off = prf_low<NTAB, NB>(T, R, g, c) & cmask;
-            uint32_t row = (c << cshift) + off;
-            if (!(active && c < S && (int32_t)c != skip && row < n_rows)) row = ROW_INVALID;
-#pragma unroll
-            for (int i0 = 0; i0 < G; i0 += U) {
-                VT buf[U][NV];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const uint32_t r = __shfl_sync(0xffffffffu, row, gbase + i0 + u);
-                    const VT *rp = base + (uint64_t)r * ev;
-#pragma unroll
-                    for (int k = 0; k < NV; k++)
-                        buf[u][k] = ldg_row(rp + k * G, r != ROW_INVALID && (uint32_t)(k * G + gl) < evx);
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++)
-#pragma unroll
-                    for (int k = 0; k < NV; k++) vxor(par[k], buf[u][k]);
+            const uint32_t row_cur = row_next, c_next = c0 + G + gl;
+            hg_phase<VT, G, NV, NTAB, NB, U, FULL, 0, NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
+            if (NPH > 1) hg_phase<VT, G, NV, NTAB, NB, U, FULL, (NPH > 1 ? 1 : 0), NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
+            if (NPH > 2) {
+                hg_phase<VT, G, NV, NTAB, NB, U, FULL, (NPH > 2 ? 2 : 0), NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
+                hg_phase<VT, G, NV, NTAB, NB, U, FULL, (NPH > 2 ? 3 : 0), NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
             }
+            row_next = to_row(c_next, st.s0);
         }
         if (active) {
             VT *o = reinterpret_cast<VT *>(J.out) + i * ev + gl;
 #pragma unroll
             for (int k = 0; k < NV; k++)
                 if ((uint32_t)(k * G + gl) < ev) o[k * G] = par[k];
-            // words past 4*(E/4) are never xored by the reference (A3): they stay zero
             VT z;
             vzero(z);
             for (uint32_t col = NV * G + gl; col < ev; col += G) o[col - gl] = z;
@@ -285,18 +328,34 @@ __global__ void xor_slices_kernel(uint64_t *dst, const uint64_t *src, uint64_t n
 // ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
-template <typename VT, int G, int NV, int NB>
-static int launch_hintgen_t(const HintParams &P, int sm, cudaStream_t st) {
-    constexpr int NTAB = 1;
-    constexpr int U = (G >= 2) ? 2 : 1;
-    auto kern = hintgen_kernel<VT, G, NV, NTAB, NB, U>;
-    const int smem = aes_tab_words<NTAB>() * 4;
+// tuning knob (read once): PM_HG_NTAB=1|4 forces the number of T-tables; default by row width (measured on B200:
+// four tables win while the PRF dominates, i.e. rows up to 640 B; one table + PRMT rotations wins for 896 B rows)
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+template <typename KERN>
+static int launch_hg(KERN kern, int smem, const HintParams &P, int sm, cudaStream_t st) {
     PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const uint32_t grid = P.n_tiles < (uint32_t)sm ? P.n_tiles : (uint32_t)sm;
     kern<<<grid, HG_THREADS, smem, st>>>(P);
     PM_CHECK_LAUNCH();
     count_launch();
     return PM_OK;
+}
+template <typename VT, int G, int NV, int NB>
+static int launch_hintgen_t(const HintParams &P, int sm, cudaStream_t st) {
+    constexpr int U = (G >= 2) ? 2 : 1;
+    constexpr bool kFourTables = sizeof(VT) == 16 && NB == 2;  // instantiated only where it is ever selected
+    static const int forced = env_int("PM_HG_NTAB", 0);
+    const int ntab = forced ? forced : (NV * G <= 40 ? 4 : 1);
+    const bool full = (P.evx == (uint32_t)(NV * G));
+    if (kFourTables && ntab == 4) {
+        if (full) return launch_hg(hintgen_kernel<VT, G, NV, kFourTables ? 4 : 1, NB, U, true>, aes_tab_words<4>() * 4, P, sm, st);
+        return launch_hg(hintgen_kernel<VT, G, NV, kFourTables ? 4 : 1, NB, U, false>, aes_tab_words<4>() * 4, P, sm, st);
+    }
+    if (full) return launch_hg(hintgen_kernel<VT, G, NV, 1, NB, U, true>, aes_tab_words<1>() * 4, P, sm, st);
+    return launch_hg(hintgen_kernel<VT, G, NV, 1, NB, U, false>, aes_tab_words<1>() * 4, P, sm, st);
 }
 template <typename VT, int G, int NB>
 static int launch_hintgen_nv(int nv, const HintParams &P, int sm, cudaStream_t st) {
@@ -339,7 +398,7 @@ int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStr
         if (J.chunk_size == 0 || (J.chunk_size & (J.chunk_size - 1)))
             return set_error(PM_ERR_ARG, "hintgen: chunk_size %llu is not a power of two", (unsigned long long)J.chunk_size);
         if (J.row0 + J.n_rows > db->n_rows) return set_error(PM_ERR_ARG, "hintgen: job %llu exceeds the table", (unsigned long long)a);
-        if (J.n_rows >= 0xffffffffull || J.set_size >= 0x7fffffffull || J.chunk_size > 0x80000000ull ||
+        if (J.n_rows >= 0x7fffffffull || J.set_size >= 0x7fffffffull || J.chunk_size > 0x80000000ull ||
             J.chunk_size * J.set_size > 0xffffffffull)
             return set_error(PM_ERR_UNSUPPORTED, "hintgen: instance too large for 32-bit row offsets");
         if (J.n_hints && !J.parity_out) return set_error(PM_ERR_ARG, "hintgen: parity_out is null");
@@ -360,6 +419,10 @@ int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStr
         for (; a < n_jobs && nj < HG_MAX_JOBS; a++) {
             const pm_hint_job &J = jobs[a];
             if (J.n_hints == 0) continue;
+            if (J.n_rows == 0) {  // an empty instance has all-zero parities
+                PM_CUDA(cudaMemsetAsync(J.parity_out, 0, J.n_hints * E * 8, st));
+                continue;
+            }
             HintJobDev &D = P.jobs[nj++];
             memcpy(D.rk, J.rk, sizeof(D.rk));
             D.row0 = J.row0; D.n_rows = J.n_rows;
@@ -376,8 +439,8 @@ int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStr
         P.n_tiles = tiles;
         if (wide) rc = need4 ? launch_hintgen_g<uint4, 4>(evx, P, db->sm_count, st, &hpt, false)
                              : launch_hintgen_g<uint4, 2>(evx, P, db->sm_count, st, &hpt, false);
-        else rc = need4 ? launch_hintgen_g<uint2, 4>(evx, P, db->sm_count, st, &hpt, false)
-                        : launch_hintgen_g<uint2, 2>(evx, P, db->sm_count, st, &hpt, false);
+        else if (need4) rc = set_error(PM_ERR_UNSUPPORTED, "hintgen: odd entry_u64 with chunk_size > 65536 is not built");
+        else rc = launch_hintgen_g<uint2, 2>(evx, P, db->sm_count, st, &hpt, false);
         if (rc != PM_OK) return rc;
     }
     return PM_OK;

@@ -1,0 +1,79 @@
+"""Private-ANN queries/s: private graph search (graphann.SearchKNN over PIRGraphInfo) on synthetic data of the SIFT
+or MS-MARCO shape, B200 path vs the CPU oracle on the same host.  Parameters follow run-private-search.sh:16-18
+(step 20, parallel 3) and reproduction/msmarco/reproduce.sh:226-230."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+
+
+def gen(n, dim, m, shape, seed):
+    rng = np.random.default_rng(seed)
+    if shape == "sift":      # integers 0..255 stored as f32 (graphann/loader.go:47-51)
+        vec = rng.integers(0, 256, (n, dim), dtype=np.uint8).astype(np.float32)
+    else:                    # MS-MARCO-shaped: per-dimension sigma decaying 0.82 -> 0.29
+        vec = rng.standard_normal((n, dim), dtype=np.float32) * np.linspace(0.82, 0.29, dim, dtype=np.float32)
+    graph = rng.integers(0, n, (n, m), dtype=np.int32)          # genRandomGraph (private-search.go:54-69)
+    self_loop = graph == np.arange(n, dtype=np.int32)[:, None]
+    graph[self_loop] = (graph[self_loop] + 1) % n
+    return vec, graph
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="sift", choices=["sift", "msmarco"])
+    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--q", type=int, default=200)
+    ap.add_argument("--cpu-q", type=int, default=20)
+    ap.add_argument("--k", type=int, default=0)
+    ap.add_argument("--step", type=int, default=20)
+    ap.add_argument("--parallel", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    n = a.n or (1000000 if a.shape == "sift" else 3201821)
+    dim = 128 if a.shape == "sift" else 192
+    k = a.k or (10 if a.shape == "sift" else 100)
+    m = 32
+    vec, graph = gen(n, dim, m, a.shape, 1)
+    queries = vec[np.random.default_rng(2).integers(0, n, a.q)] + np.float32(0.5)
+
+    from pacmann_b200 import cabi, graphann
+    from pacmann_b200.keys import mix64
+    seed = 7
+    f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed)
+    t0 = time.perf_counter()
+    f.Preprocess()
+    prep_s = time.perf_counter() - t0
+    pir = f.PIR
+    f.SearchKNNBatch(queries[:2], k, a.step, a.parallel)          # warm-up
+    l0, s0 = cabi.launch_count(), pir.serverQueries
+    t0 = time.perf_counter()
+    ret, _ = f.SearchKNNBatch(queries, k, a.step, a.parallel)
+    dt = time.perf_counter() - t0
+    res = dict(shape=a.shape, n=n, dim=dim, m=m, k=k, step=a.step, parallel=a.parallel, queries=a.q,
+               gpu_prep_s=prep_s, gpu_pir_prep_s=pir.PreprocessingTime(), gpu_s_per_query=dt / a.q, gpu_qps=a.q / dt,
+               gpu_launches=cabi.launch_count() - l0, server_subqueries=pir.serverQueries - s0,
+               success_rate=f.succQueryNum / max(1, f.totalQueryNum))
+    if not a.no_cpu:
+        from oracle import oracle as o
+        raw = o.pack_db(vec, graph)
+        o_pir = o.SimpleBatchPianoPIR(n, (dim + m) * 4, m, raw, 8)
+        t0 = time.perf_counter()
+        o_pir.preprocessing(key_seed=mix64(seed, 1), repl_seed=mix64(seed, 2), threads=os.cpu_count())
+        res["cpu_prep_s_all_threads"] = time.perf_counter() - t0
+        start = f.StartVertexIds()
+        o.search_knn_private(o_pir, vec, graph, start, queries[:2], k, a.step, a.parallel)
+        t0 = time.perf_counter()
+        o_ret, _, _ = o.search_knn_private(o_pir, vec, graph, start, queries[2:2 + a.cpu_q], k, a.step, a.parallel)
+        cdt = time.perf_counter() - t0
+        res.update(cpu_s_per_query=cdt / a.cpu_q, cpu_qps=a.cpu_q / cdt, cpu_threads_online=1,
+                   reference_published_s_per_query="0.0559 / 0.0640 (SIFT1M, private-search-report.txt:19,44)")
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
