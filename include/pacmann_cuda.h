@@ -13,6 +13,8 @@
  *   pm_gather_rows     replacement values                 pianopir/pir.go:345-349
  *   pm_answer_batch*   PianoPIRServer.PrivateQuery,       pianopir/pir.go:65-88,
  *                      SimpleBatchPianoPIR.Query fan-out   pianopir/batch-pir.go:189-216
+ *   pm_client_*        PianoPIRClient.{Initialization,    pianopir/pir.go:203-255, 267-352, 354-471
+ *                      Preprocessing,Query} resident form
  *   pm_l2_pairs/_batch L2Dist / L2DistanceSIMD            graphann/build_graph.go:119-134, l2_distance_amd64.s:4-36
  *   pm_ip_u32_scan     InnerProduct + scan loop           graphann/l2_distance_amd64.s:39-68, graphann_test.go:268-273
  *
@@ -111,6 +113,41 @@ int pm_answer_batch(pm_db *db, const uint64_t *row0, const uint64_t *n_rows, con
 int pm_answer_batch_dev(pm_db *db, const uint64_t *row0, const uint64_t *n_rows, const uint32_t *chunk_size,
                         const uint32_t *set_size, const uint32_t *offsets, uint64_t offsets_stride, uint64_t q,
                         uint64_t *out, void *stream);
+
+/* ---- GPU-resident client ------------------------------------------------------------
+ * The hint tables of every sub-PIR of one SimpleBatchPianoPIR stay in HBM: Preprocessing ships no parities to
+ * the host, and the online Query's hint search / set expansion / refresh (pianopir/pir.go:354-471) run on the
+ * GPU around the server answer.  Results and the client state are bit-identical to the sequential reference. */
+typedef struct pm_client pm_client;
+typedef struct pm_client_part {
+    uint64_t row0, n_rows, chunk_size, set_size;
+    uint64_t n_primary;     /* primaryHintNum */
+    uint64_t backup_group;  /* maxQueryPerChunk */
+    uint64_t max_query_num; /* MaxQueryNum */
+} pm_client_part;
+typedef struct pm_client_query {
+    uint32_t part;                  /* sub-PIR index */
+    uint32_t kind;                  /* 0 = dummy query (pir.go:363-371), 1 = real query */
+    uint64_t idx;                   /* index inside the sub-PIR (real queries) */
+    uint64_t dummy_seed, dummy_ctr; /* dummy: offsets[c] = mix64(dummy_seed, dummy_ctr + c) & (chunk_size-1) */
+} pm_client_query;
+
+int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t n_parts, pm_client **out);
+int pm_client_destroy(pm_client *c);
+/* Initialization (pir.go:203-255) + Preprocessing (pir.go:267-352) of the listed parts, entirely on the device.
+ * rk = [n][44] long keys; replacement offset of (chunk c, slot j) = mix64(repl_seed[i], c*mqpc + j) & (chunk_size-1).
+ * skip_prep != 0 is DummyPreprocessing (pir.go:520-523). */
+int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint64_t n, const uint32_t *rk, const uint64_t *repl_seed,
+                         int skip_prep);
+/* q client queries in one call.  Queries of the same part are processed in array order (each real query consumes
+ * and refreshes a hint).  out[i] = the entry (zeros for dummy / failed queries); status[i] = 0 ok, 2 query budget
+ * exceeded, 3 too many queries in the chunk, 4 no hit hint (pir.go:386-419).  The caller keeps the local cache
+ * (pir.go:381-383) and therefore never sends an index twice between two preprocessings. */
+int pm_client_query_batch(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status);
+/* copy one table of one part to the host (tests / checkpointing): 0 primaryShortTag, 1 primaryParity,
+ * 2 primaryProgramPoint, 3 replacementIdx, 4 replacementVal, 5 backupShortTag, 6 backupParity, 7 QueryHistogram,
+ * 8 FinishedQueryNum */
+int pm_client_download(pm_client *c, uint32_t part, int table, uint64_t *out, uint64_t cap_words);
 
 /* A9: squared L2 in the reference's exact fp32 order.  out[i] = L2Dist(a[i], b[i]), rows of `dim` floats. */
 int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device);

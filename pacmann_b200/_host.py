@@ -36,11 +36,12 @@ SIG = {
     "pmh_batch_query": (C.c_int, [vp, vp, u64, vp]),
     "pmh_batch_sub": (vp, [vp, u64]),
     "pmh_batch_get": (u64, [vp, C.c_int]),
+    "pmh_batch_enable_resident": (C.c_int, [vp]),
     "pmh_batch_local_storage": (C.c_double, [vp]),
     "pmh_batch_prep_time": (C.c_double, [vp]),
     "pmh_l2dist": (C.c_float, [vp, vp, u64, C.c_int]),
     "pmh_frontend_basic": (vp, [i64, i64, i64, vp, vp]),
-    "pmh_frontend_pir": (vp, [i64, i64, i64, vp, vp, C.c_int, C.c_int, u64, C.c_int]),
+    "pmh_frontend_pir": (vp, [i64, i64, i64, vp, vp, C.c_int, C.c_int, u64, C.c_int, C.c_int]),
     "pmh_frontend_free": (None, [vp]),
     "pmh_frontend_preprocess": (C.c_int, [vp]),
     "pmh_frontend_start_ids": (i64, [vp, vp, i64]),

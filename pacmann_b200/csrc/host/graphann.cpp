@@ -84,6 +84,7 @@ void PIRGraphInfo::Preprocess() {
     DBTotalSize = (uint64_t)N * DBEntryByteNum;
     PIR = new pianopir::SimpleBatchPianoPIR((uint64_t)N, DBEntryByteNum, (uint64_t)M, rawDB.data(), rawDB.size(), 8, device);
     PIR->SetSeeds(Mix64(seed, 1), Mix64(seed, 2));
+    if (residentClient && !NonPrivateMode) PIR->EnableResidentClient();
     if (skipPrep) PIR->DummyPreprocessing();
     else PIR->Preprocessing();
 }

@@ -59,6 +59,7 @@ public:
     const int32_t *graph;
     const float *vectors;
     bool skipPrep, NonPrivateMode;
+    bool residentClient = true;  // keep the hint tables on the GPU (pm_client_*)
     uint64_t DBEntryByteNum = 0, DBTotalSize = 0;
     std::vector<uint64_t> rawDB;
     pianopir::SimpleBatchPianoPIR *PIR = nullptr;

@@ -167,7 +167,22 @@ PMH int pmh_batch_query(void *h, const uint64_t *idx, uint64_t n, uint64_t *out)
     return 0;
     PMH_CATCH(-100)
 }
-PMH void *pmh_batch_sub(void *h, uint64_t i) { return ((SimpleBatchPianoPIR *)h)->subPIR[i]; }
+PMH void *pmh_batch_sub(void *h, uint64_t i) {
+    auto *b = (SimpleBatchPianoPIR *)h;
+    try {
+        b->SyncTablesFromDevice(i);  // resident mode: refresh the host copy of the tables for inspection
+    } catch (const std::exception &e) {
+        t_err = e.what();
+        return nullptr;
+    }
+    return b->subPIR[i];
+}
+PMH int pmh_batch_enable_resident(void *h) {
+    PMH_TRY
+    ((SimpleBatchPianoPIR *)h)->EnableResidentClient();
+    return 0;
+    PMH_CATCH(-100)
+}
 PMH uint64_t pmh_batch_get(void *h, int what) {
     auto *b = (SimpleBatchPianoPIR *)h;
     switch (what) {
@@ -206,10 +221,12 @@ PMH void *pmh_frontend_basic(int64_t n, int64_t dim, int64_t m, const int32_t *g
     PMH_CATCH(nullptr)
 }
 PMH void *pmh_frontend_pir(int64_t n, int64_t dim, int64_t m, const int32_t *graph, const float *vectors, int skip_prep,
-                           int non_private, uint64_t seed, int device) {
+                           int non_private, uint64_t seed, int device, int resident) {
     PMH_TRY
     auto *b = new FrontBox();
-    b->g = new graphann::PIRGraphInfo(n, dim, m, graph, vectors, skip_prep != 0, non_private != 0, seed, device);
+    auto *pg = new graphann::PIRGraphInfo(n, dim, m, graph, vectors, skip_prep != 0, non_private != 0, seed, device);
+    pg->residentClient = resident != 0;
+    b->g = pg;
     b->f = new graphann::GraphANNFrontend(b->g);
     return b;
     PMH_CATCH(nullptr)

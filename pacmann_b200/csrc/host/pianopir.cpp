@@ -404,6 +404,7 @@ SimpleBatchPianoPIR::SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNu
     }
 }
 SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
+    if (rclient) pm_client_destroy(rclient);
     for (auto *p : subPIR) delete p;
     delete db;
 }
@@ -446,6 +447,14 @@ void SimpleBatchPianoPIR::Preprocessing() {
     QueriesMadeInPartition = 0;
     auto t0 = std::chrono::steady_clock::now();
     const uint64_t E = config.DBEntrySize, PN = config.PartitionNum;
+    if (resident) {
+        std::vector<uint32_t> ids(PN);
+        for (uint64_t i = 0; i < PN; i++) ids[i] = (uint32_t)i;
+        PreprocessResident(ids, false);
+        for (auto *p : subPIR) p->client.keyEpoch += 1;
+        RecordStats(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        return;
+    }
     std::vector<pm_hint_job> jobs(PN);
     std::vector<std::vector<uint64_t>> outs(PN);
     for (uint64_t i = 0; i < PN; i++) {
@@ -478,6 +487,14 @@ void SimpleBatchPianoPIR::Preprocessing() {
 }
 
 void SimpleBatchPianoPIR::DummyPreprocessing() {  // batch-pir.go:157-166
+    if (resident) {
+        std::vector<uint32_t> ids(config.PartitionNum);
+        for (uint64_t i = 0; i < config.PartitionNum; i++) ids[i] = (uint32_t)i;
+        PreprocessResident(ids, true);
+        for (auto *p : subPIR) { p->client.skipPrep = true; p->client.keyEpoch += 1; }
+        RecordStats(0);
+        return;
+    }
     for (auto *p : subPIR) {
         p->DummyPreprocessing();
         p->client.keyEpoch += 1;
@@ -529,6 +546,7 @@ void SimpleBatchPianoPIR::Flush(std::vector<PendingQuery> &pend, std::vector<uin
 }
 
 int SimpleBatchPianoPIR::Query(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret) {
+    if (resident) return QueryResident(idx, ret);
     const uint64_t PN = config.PartitionNum, PS = config.PartitionSize, E = config.DBEntrySize;
     const uint64_t queryNumToMake = idx.size() / PN;
     std::vector<std::vector<uint64_t>> partitionQueries(PN);
@@ -568,6 +586,145 @@ int SimpleBatchPianoPIR::Query(const std::vector<uint64_t> &idx, std::vector<std
         else (*ret)[i].assign(E, 0);
     }
     if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) {  // batch-pir.go:239-245
+        Preprocessing();
+    } else {
+        FinishedBatchNum += idx.size() / config.BatchSize;
+        QueriesMadeInPartition += queryNumToMake;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GPU-resident client
+// ---------------------------------------------------------------------------------------------
+void SimpleBatchPianoPIR::EnableResidentClient() {
+    if (resident) return;
+    std::vector<pm_client_part> parts(config.PartitionNum);
+    for (uint64_t i = 0; i < config.PartitionNum; i++) {
+        PianoPIR *p = subPIR[i];
+        parts[i] = pm_client_part{p->server.row0, p->config.DBSize, p->config.ChunkSize, p->config.SetSize,
+                                  p->client.primaryHintNum, p->client.maxQueryPerChunk, p->client.MaxQueryNum};
+    }
+    check(pm_client_create(db->h, parts.data(), parts.size(), &rclient), "pm_client_create");
+    resident = true;
+}
+
+// Initialization + Preprocessing of the listed sub-PIRs on the device (keys and seeds derived as in the host path)
+void SimpleBatchPianoPIR::PreprocessResident(const std::vector<uint32_t> &ids, bool skipPrep) {
+    std::vector<uint32_t> rk(ids.size() * 44);
+    std::vector<uint64_t> seeds(ids.size());
+    for (size_t a = 0; a < ids.size(); a++) {
+        PianoPIRClient &c = subPIR[ids[a]]->client;
+        c.FinishedQueryNum = 0;
+        c.masterKey = DeriveKey(c.keySeed, c.keyEpoch, c.keyParts, c.keyIndex);
+        c.longKey = GetLongKey(c.masterKey);
+        c.localCache.clear();
+        c.pendingCached.clear();
+        memcpy(&rk[a * 44], c.longKey.data(), 176);
+        seeds[a] = Mix64(c.replSeed, c.keyEpoch * c.keyParts + c.keyIndex);
+    }
+    check(pm_client_preprocess(rclient, ids.data(), ids.size(), rk.data(), seeds.data(), skipPrep ? 1 : 0), "pm_client_preprocess");
+}
+
+void SimpleBatchPianoPIR::SyncTablesFromDevice(uint64_t i) {
+    if (!resident) return;
+    PianoPIRClient &c = subPIR[i]->client;
+    const uint64_t E = config.DBEntrySize, P = c.primaryHintNum, B = subPIR[i]->config.SetSize * c.maxQueryPerChunk;
+    c.primaryShortTag.resize(P); c.primaryParity.resize(P * E); c.primaryProgramPoint.resize(P);
+    c.replacementIdx.resize(B); c.replacementVal.resize(B * E); c.backupShortTag.resize(B); c.backupParity.resize(B * E);
+    c.QueryHistogram.resize(subPIR[i]->config.SetSize);
+    std::vector<uint64_t> *tabs[8] = {&c.primaryShortTag, &c.primaryParity, &c.primaryProgramPoint, &c.replacementIdx,
+                                      &c.replacementVal, &c.backupShortTag, &c.backupParity, &c.QueryHistogram};
+    for (int t = 0; t < 8; t++) check(pm_client_download(rclient, (uint32_t)i, t, tabs[t]->data(), tabs[t]->size()), "pm_client_download");
+    uint64_t fin = 0;
+    check(pm_client_download(rclient, (uint32_t)i, 8, &fin, 1), "pm_client_download");
+    c.FinishedQueryNum = fin;
+}
+
+int SimpleBatchPianoPIR::QueryResident(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret) {
+    const uint64_t PN = config.PartitionNum, PS = config.PartitionSize, E = config.DBEntrySize;
+    const uint64_t queryNumToMake = idx.size() / PN;
+    std::vector<std::vector<uint64_t>> partitionQueries(PN);
+    for (uint64_t v : idx) {
+        uint64_t pi = v / PS;
+        if (pi >= PN) return -1;
+        partitionQueries[pi].push_back(v);
+    }
+    struct Pend { uint64_t part, global, local; int kind; /* 0 dummy, 1 real, 2 cached */ int64_t qpos; };
+    std::unordered_map<uint64_t, std::vector<uint64_t>> responses;
+    std::vector<Pend> pend;
+    std::vector<pm_client_query> ql;
+    std::vector<uint64_t> pendingReal(PN, 0);
+
+    auto flush = [&]() {
+        std::vector<uint64_t> out(ql.size() * E);
+        std::vector<int32_t> status(ql.size());
+        if (!ql.empty()) {
+            check(pm_client_query_batch(rclient, ql.data(), ql.size(), out.data(), status.data()), "pm_client_query_batch");
+            serverLaunches += 1;
+        }
+        std::vector<uint64_t> zero(E, 0);
+        for (const Pend &pd : pend) {
+            PianoPIRClient &c = subPIR[pd.part]->client;
+            if (pd.kind == 0) { serverQueries += 1; continue; }
+            if (pd.kind == 2) {  // served from the local cache (pir.go:381-383); an earlier failure of the same index repeats as zeros
+                auto it = c.localCache.find(pd.local);
+                responses[pd.global] = it != c.localCache.end() ? it->second : zero;
+                continue;
+            }
+            std::vector<uint64_t> r(out.begin() + pd.qpos * (int64_t)E, out.begin() + (pd.qpos + 1) * (int64_t)E);
+            if (status[pd.qpos] == 0) {
+                serverQueries += 1;
+                c.FinishedQueryNum += 1;
+                c.localCache[pd.local] = r;
+            }
+            for (size_t k = 0; k < c.pendingCached.size(); k++)
+                if (c.pendingCached[k] == pd.local) { c.pendingCached.erase(c.pendingCached.begin() + (long)k); break; }
+            responses[pd.global] = r;
+        }
+        pend.clear();
+        ql.clear();
+        std::fill(pendingReal.begin(), pendingReal.end(), 0);
+    };
+
+    for (uint64_t i = 0; i < PN; i++) {
+        auto &lst = partitionQueries[i];
+        while (lst.size() < queryNumToMake) lst.push_back(DefaultValue);
+        PianoPIR *p = subPIR[i];
+        PianoPIRClient &c = p->client;
+        for (uint64_t j = 0; j < queryNumToMake; j++) {
+            // pir.go:527-530 needs the exact FinishedQueryNum, which is only known after the pending queries ran
+            if (c.FinishedQueryNum + pendingReal[i] >= c.MaxQueryNum) {
+                flush();
+                if (c.FinishedQueryNum == c.MaxQueryNum) PreprocessResident({(uint32_t)i}, c.skipPrep);
+            }
+            if (lst[j] == DefaultValue) {
+                ql.push_back(pm_client_query{(uint32_t)i, 0, 0, c.dummySeed, c.dummyCtr});
+                c.dummyCtr += p->config.SetSize;
+                pend.push_back(Pend{i, DefaultValue, 0, 0, (int64_t)ql.size() - 1});
+                continue;
+            }
+            const uint64_t local = lst[j] - i * PS;
+            bool cached = c.localCache.count(local) != 0;
+            for (size_t k = 0; !cached && k < c.pendingCached.size(); k++) cached = c.pendingCached[k] == local;
+            if (cached) {
+                pend.push_back(Pend{i, lst[j], local, 2, -1});
+            } else {
+                ql.push_back(pm_client_query{(uint32_t)i, 1, local, 0, 0});
+                c.pendingCached.push_back(local);
+                pendingReal[i] += 1;
+                pend.push_back(Pend{i, lst[j], local, 1, (int64_t)ql.size() - 1});
+            }
+        }
+    }
+    flush();
+    ret->resize(idx.size());
+    for (size_t i = 0; i < idx.size(); i++) {
+        auto it = responses.find(idx[i]);
+        if (it != responses.end()) (*ret)[i] = it->second;
+        else (*ret)[i].assign(E, 0);
+    }
+    if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) {
         Preprocessing();
     } else {
         FinishedBatchNum += idx.size() / config.BatchSize;

@@ -154,7 +154,17 @@ public:
     double preprocessingTime = 0;
     uint64_t serverQueries = 0, serverLaunches = 0;  // accounting: sub-queries answered / pm_answer_batch calls
 
+    // GPU-resident client (pm_client_*): hint tables stay in HBM, hint search / refresh run on the GPU.
+    // Must be enabled before Preprocessing(); the host-side tables of the sub-PIRs are then only refreshed on
+    // request (SyncTablesFromDevice), counters and the local cache stay on the host.
+    void EnableResidentClient();
+    void SyncTablesFromDevice(uint64_t i);
+    bool resident = false;
+    pm_client *rclient = nullptr;
+
 private:
+    void PreprocessResident(const std::vector<uint32_t> &ids, bool skipPrep);
+    int QueryResident(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret);
     void Flush(std::vector<PendingQuery> &pend, std::vector<uint64_t> &pend_part, std::vector<uint64_t> &pend_global,
                std::unordered_map<uint64_t, std::vector<uint64_t>> &responses);
 };

@@ -1,0 +1,403 @@
+// GPU-resident PianoPIR client: the hint tables of every sub-PIR of one
+// SimpleBatchPianoPIR live in HBM, so Preprocessing() never ships parities to the host and the online
+// Query's first-match hint search (pianopir/pir.go:405-414, up to primaryHintNum PRF evaluations per
+// query on the CPU) runs as a block-wide parallel search.  Included at the end of pm_pir.cu (same
+// translation unit as the AES table in constant memory).
+//
+// One query call = three launches on one stream:
+//   client_prepare_kernel   one CTA per sub-PIR walks its queries IN ORDER: budget checks, hint search,
+//                           set expansion, programmed-point and replacement patching (pir.go:386-447) and
+//                           the response-independent half of the refresh (tags, program point, counters)
+//   answer_kernel           the server's PrivateQuery for every sub-query of the call (pir.go:65-88)
+//   client_finish_kernel    response xor replacement xor parity, parity refresh from the backup hint
+//                           (pir.go:451-463), again in order per sub-PIR
+// The split at the server call is legal because nothing the prepare step reads depends on a response
+// value; results and the final client state are bit-identical to the sequential reference
+// (tests/test_resident_client_gpu.py compares every table with the oracle's).
+#pragma once
+
+namespace pm {
+
+constexpr uint64_t kDefaultProgramPoint = 0x7fffffffull;  // pir.go:15
+constexpr int CL_THREADS = 512;
+
+struct ClientPartDev {
+    uint32_t rk[44];
+    uint64_t row0, n_rows, chunk_size, set_size, n_primary, backup_group, max_query_num;
+    uint32_t chunk_mask, chunk_shift;
+    uint64_t *tags, *pp, *parity;              // [P], [P], [P][E]
+    uint64_t *btags, *bparity, *ridx, *rval;   // [S*M], [S*M][E], [S*M], [S*M][E]
+    uint64_t *hist;                            // [S]
+    uint64_t *finished;                        // [1]
+};
+
+__device__ __forceinline__ uint64_t mix64_dev(uint64_t seed, uint64_t ctr) {
+    uint64_t z = seed + (ctr + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+// Initialization (pir.go:203-255) + replacement index draw (pir.go:345-347), one CTA column per part
+__global__ void client_init_kernel(const ClientPartDev *parts, const uint32_t *part_ids, const uint64_t *repl_seed, int skip_prep) {
+    const ClientPartDev &D = parts[part_ids[blockIdx.y]];
+    const uint64_t P = D.n_primary, B = D.set_size * D.backup_group, M = D.backup_group, seed = repl_seed[blockIdx.y];
+    const uint64_t n = P > B ? P : B;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (i < P) {
+            D.tags[i] = i;
+            D.pp[i] = kDefaultProgramPoint;
+        }
+        if (i < B) {
+            D.btags[i] = P + i;
+            const uint64_t c = i / M;
+            // i == c*M + j; DummyPreprocessing leaves the Initialization value (pir.go:245)
+            D.ridx[i] = skip_prep ? kDefaultProgramPoint : (mix64_dev(seed, i) & (D.chunk_size - 1)) + c * D.chunk_size;
+        }
+        if (i < D.set_size) D.hist[i] = 0;
+        if (i == 0) *D.finished = 0;
+    }
+}
+
+struct RkOfPtr {
+    const uint32_t *p;
+    __device__ __forceinline__ uint32_t operator[](int i) const { return p[i]; }
+};
+
+struct ClientQueryDev {  // mirrors pm_client_query
+    uint32_t part, kind;
+    uint64_t idx, dummy_seed, dummy_ctr;
+};
+struct ClientMeta {
+    uint64_t hit, slot;
+    int32_t status;  // 0 ok, 2 budget, 3 too many in chunk, 4 no hit; -1 dummy
+    int32_t pad;
+};
+
+__global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const ClientPartDev *parts, const ClientQueryDev *queries,
+                                                                    uint32_t q, uint32_t stride, uint32_t *offsets,
+                                                                    ClientMeta *meta, uint64_t *a_row0, uint64_t *a_nrows,
+                                                                    uint32_t *a_chunk, uint32_t *a_set) {
+    extern __shared__ uint32_t smem[];
+    uint32_t *s_tab = smem;                           // replicated Te0
+    uint32_t *s_rk = smem + aes_tab_words<1>();       // 44 round-key words
+    uint32_t *s_offs = s_rk + 64;                     // [stride]
+    __shared__ uint32_t s_hit;
+    __shared__ int s_status;
+    const uint32_t part = blockIdx.x;
+    const ClientPartDev &D = parts[part];
+    aes_tab_fill<1>(s_tab, c_te0);
+    if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
+    __syncthreads();
+    const AesTab<1> T{s_tab + (threadIdx.x & 31)};
+    const RkOfPtr R{s_rk};
+    const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
+    const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
+
+    for (uint32_t t = 0; t < q; t++) {
+        if (queries[t].part != part) continue;   // block-uniform
+        const ClientQueryDev Q = queries[t];
+        if (threadIdx.x == 0) {
+            a_row0[t] = D.row0; a_nrows[t] = D.n_rows; a_chunk[t] = (uint32_t)C; a_set[t] = S;
+        }
+        if (Q.kind == 0) {  // dummy query: SetSize random offsets (pir.go:363-371)
+            for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS)
+                offsets[(uint64_t)t * stride + c] = (uint32_t)(mix64_dev(Q.dummy_seed, Q.dummy_ctr + c) & cmask);
+            if (threadIdx.x == 0) meta[t] = ClientMeta{0, 0, -1, 0};
+            continue;
+        }
+        const uint64_t chunkId = Q.idx / C, offset = Q.idx % C;
+        if (threadIdx.x == 0) {
+            int st = 0;
+            if (*D.finished >= D.max_query_num) st = 2;             // pir.go:386-391
+            else if (D.hist[chunkId] >= M) st = 3;                  // pir.go:396-400
+            s_status = st;
+            s_hit = 0xffffffffu;
+        }
+        __syncthreads();
+        if (s_status != 0) {
+            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, s_status, 0}; a_set[t] = 0; }
+            __syncthreads();
+            continue;
+        }
+        // first primary hint whose PRF lands on `offset` and is not programmed inside this chunk (pir.go:405-414)
+        uint32_t hit = 0xffffffffu;
+        for (uint64_t base = 0; base < P; base += CL_THREADS) {
+            const uint64_t i = base + threadIdx.x;
+            if (i < P) {
+                const PrfTagPart g = prf_tag_part(T, R, D.tags[i]);
+                const uint32_t ho = prf_low<1, 4>(T, R, g, (uint32_t)chunkId) & cmask;
+                if (ho == (uint32_t)offset) {
+                    const uint64_t pp = D.pp[i];
+                    if (pp == kDefaultProgramPoint || pp / C != chunkId) atomicMin(&s_hit, (uint32_t)i);
+                }
+            }
+            __syncthreads();
+            hit = s_hit;
+            __syncthreads();
+            if (hit != 0xffffffffu) break;
+        }
+        if (hit == 0xffffffffu) {  // pir.go:416-419
+            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, 4, 0}; a_set[t] = 0; }
+            continue;
+        }
+        // expand the hit hint to a full set (pir.go:424-427)
+        {
+            const PrfTagPart g = prf_tag_part(T, R, D.tags[hit]);
+            for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) s_offs[c] = prf_low<1, 4>(T, R, g, c) & cmask;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint64_t pp = D.pp[hit];
+            if (pp != kDefaultProgramPoint) s_offs[pp / C] = (uint32_t)(pp & cmask);      // pir.go:430-433
+            const uint64_t inGroup = D.hist[chunkId], slot = chunkId * M + inGroup;
+            s_offs[chunkId] = (uint32_t)(D.ridx[slot] & cmask);                           // pir.go:436-439
+            meta[t] = ClientMeta{hit, slot, 0, 0};
+            // response-independent half of the refresh (pir.go:460-467)
+            D.tags[hit] = D.btags[slot];
+            D.pp[hit] = Q.idx;
+            *D.finished += 1;
+            D.hist[chunkId] += 1;
+        }
+        __syncthreads();
+        for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) offsets[(uint64_t)t * stride + c] = s_offs[c];
+        __threadfence_block();
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev *parts, const ClientQueryDev *queries,
+                                                            const ClientMeta *meta, uint32_t q, uint32_t E,
+                                                            const uint64_t *answers, uint64_t *out) {
+    const uint32_t part = blockIdx.x;
+    const ClientPartDev &D = parts[part];
+    const uint32_t E4 = E & ~3u;  // EntryXor granularity (xorSlices leaves the len%4 tail untouched)
+    for (uint32_t t = 0; t < q; t++) {
+        if (queries[t].part != part) continue;
+        const ClientMeta m = meta[t];
+        if (m.status != 0) {  // dummy or failed: zero entry (pir.go:356-360)
+            for (uint32_t w = threadIdx.x; w < E; w += blockDim.x) out[(uint64_t)t * E + w] = 0;
+            continue;
+        }
+        uint64_t *par = D.parity + m.hit * E;
+        const uint64_t *bpar = D.bparity + m.slot * E, *rv = D.rval + m.slot * E;
+        for (uint32_t w = threadIdx.x; w < E; w += blockDim.x) {
+            uint64_t r = answers[(uint64_t)t * E + w];
+            uint64_t np = bpar[w];                       // copy(primaryParity[hit], backupParity[slot])  pir.go:461
+            if (w < E4) {
+                r ^= rv[w] ^ par[w];                     // pir.go:451,453
+                np ^= r;                                 // pir.go:463
+            }
+            par[w] = np;
+            out[(uint64_t)t * E + w] = r;
+        }
+        __syncthreads();  // a later query of this part may hit the hint refreshed here
+    }
+}
+
+}  // namespace pm
+
+// =============================================================================================
+// C-ABI: pm_client_*
+// =============================================================================================
+struct pm_client {
+    pm_db *db;
+    uint64_t n_parts, E;
+    std::vector<pm::ClientPartDev> host_parts;  // device pointers inside
+    pm::ClientPartDev *d_parts;
+    void *arena;
+    uint64_t max_set;
+    std::mutex mu;
+};
+
+PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t n_parts, pm_client **out) {
+    using namespace pm;
+    if (!db || !parts || !out || n_parts == 0) return set_error(PM_ERR_ARG, "pm_client_create: null pointer / no parts");
+    *out = nullptr;
+    int rc = ensure_device(db->device);
+    if (rc) return rc;
+    const uint64_t E = db->entry_u64;
+    uint64_t words = 0, max_set = 0;
+    for (uint64_t i = 0; i < n_parts; i++) {
+        const pm_client_part &p = parts[i];
+        if (p.chunk_size == 0 || (p.chunk_size & (p.chunk_size - 1)) || p.row0 + p.n_rows > db->n_rows || p.set_size == 0 ||
+            p.set_size > 16384 || p.chunk_size * p.set_size > 0x7fffffffull || p.n_primary >= 0xffffffffull)
+            return set_error(PM_ERR_ARG, "pm_client_create: bad geometry for part %llu", (unsigned long long)i);
+        const uint64_t P = p.n_primary, B = p.set_size * p.backup_group;
+        words += 2 * P + P * E + 2 * B + 2 * B * E + p.set_size + 2;
+        words = (words + 1) & ~1ull;
+        if (p.set_size > max_set) max_set = p.set_size;
+    }
+    pm_client *c = new (std::nothrow) pm_client();
+    if (!c) return set_error(PM_ERR_NOMEM, "out of host memory");
+    c->db = db; c->n_parts = n_parts; c->E = E; c->max_set = max_set;
+    cudaError_t e = cudaMalloc(&c->arena, words * 8 + 256);
+    if (e != cudaSuccess) { cudaGetLastError(); delete c; return set_error(PM_ERR_NOMEM, "pm_client_create: cudaMalloc(%llu) failed", (unsigned long long)(words * 8)); }
+    e = cudaMalloc(&c->d_parts, n_parts * sizeof(ClientPartDev));
+    if (e != cudaSuccess) { cudaGetLastError(); cudaFree(c->arena); delete c; return set_error(PM_ERR_NOMEM, "pm_client_create: cudaMalloc failed"); }
+    uint64_t *cur = (uint64_t *)c->arena;
+    c->host_parts.resize(n_parts);
+    for (uint64_t i = 0; i < n_parts; i++) {
+        const pm_client_part &p = parts[i];
+        ClientPartDev &D = c->host_parts[i];
+        memset(&D, 0, sizeof(D));
+        const uint64_t P = p.n_primary, B = p.set_size * p.backup_group;
+        D.row0 = p.row0; D.n_rows = p.n_rows; D.chunk_size = p.chunk_size; D.set_size = p.set_size;
+        D.n_primary = P; D.backup_group = p.backup_group; D.max_query_num = p.max_query_num;
+        D.chunk_mask = (uint32_t)(p.chunk_size - 1); D.chunk_shift = (uint32_t)__builtin_ctzll(p.chunk_size);
+        D.parity = cur; cur += P * E;      // primary then backup parities contiguous in hint-number order
+        D.bparity = cur; cur += B * E;
+        D.rval = cur; cur += B * E;
+        D.tags = cur; cur += P;
+        D.pp = cur; cur += P;
+        D.btags = cur; cur += B;
+        D.ridx = cur; cur += B;
+        D.hist = cur; cur += p.set_size;
+        D.finished = cur; cur += 2;
+        if ((uintptr_t)cur & 15) cur += 1;
+    }
+    *out = c;
+    return PM_OK;
+}
+
+PM_EXPORT int pm_client_destroy(pm_client *c) {
+    if (!c) return PM_OK;
+    if (pm::ensure_device(c->db->device) == PM_OK) {
+        cudaStreamSynchronize(c->db->stream);
+        cudaFree(c->arena);
+        cudaFree(c->d_parts);
+    }
+    delete c;
+    return PM_OK;
+}
+
+PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint64_t n, const uint32_t *rk, const uint64_t *repl_seed,
+                                   int skip_prep) {
+    using namespace pm;
+    if (!c || (n && (!part_ids || !rk || !repl_seed))) return set_error(PM_ERR_ARG, "pm_client_preprocess: null pointer");
+    if (n == 0) return PM_OK;
+    int rc = ensure_device(c->db->device);
+    if (rc) return rc;
+    pm_db *db = c->db;
+    std::lock_guard<std::mutex> lock(db->mu);
+    const uint64_t E = c->E;
+    uint64_t max_n = 0;
+    for (uint64_t a = 0; a < n; a++) {
+        if (part_ids[a] >= c->n_parts) return set_error(PM_ERR_ARG, "pm_client_preprocess: part id out of range");
+        ClientPartDev &D = c->host_parts[part_ids[a]];
+        memcpy(D.rk, rk + a * 44, sizeof(D.rk));
+        const uint64_t P = D.n_primary, B = D.set_size * D.backup_group;
+        max_n = std::max(max_n, std::max(P, B));
+    }
+    PM_CUDA(cudaMemcpyAsync(c->d_parts, c->host_parts.data(), c->n_parts * sizeof(ClientPartDev), cudaMemcpyHostToDevice, db->stream));
+    void *d_tmp = nullptr;
+    if ((rc = scratch(db, 1, n * 16, &d_tmp))) return rc;
+    uint32_t *d_ids = (uint32_t *)d_tmp;
+    uint64_t *d_seed = (uint64_t *)((char *)d_tmp + ((n * 4 + 7) & ~7ull));
+    PM_CUDA(cudaMemcpyAsync(d_ids, part_ids, n * 4, cudaMemcpyHostToDevice, db->stream));
+    PM_CUDA(cudaMemcpyAsync(d_seed, repl_seed, n * 8, cudaMemcpyHostToDevice, db->stream));
+    dim3 grid((unsigned)std::min<uint64_t>((max_n + 255) / 256, 64), (unsigned)n);
+    client_init_kernel<<<grid, 256, 0, db->stream>>>(c->d_parts, d_ids, d_seed, skip_prep);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    std::vector<pm_hint_job> jobs;
+    for (uint64_t a = 0; a < n; a++) {
+        const ClientPartDev &D = c->host_parts[part_ids[a]];
+        const uint64_t P = D.n_primary, B = D.set_size * D.backup_group;
+        if (skip_prep) {  // DummyPreprocessing (pir.go:520-523): Initialization only, parities and replacement values zero
+            PM_CUDA(cudaMemsetAsync(D.parity, 0, (P + 2 * B) * E * 8, db->stream));
+            continue;
+        }
+        pm_hint_job j;
+        memset(&j, 0, sizeof(j));
+        j.row0 = D.row0; j.n_rows = D.n_rows; j.chunk_size = D.chunk_size; j.set_size = D.set_size;
+        memcpy(j.rk, D.rk, sizeof(j.rk));
+        j.hint_begin = 0; j.n_hints = P + B; j.n_primary = P; j.backup_group = D.backup_group;
+        j.parity_out = D.parity;
+        jobs.push_back(j);
+    }
+    if (!jobs.empty()) {
+        if ((rc = hintgen_enqueue(db, jobs.data(), jobs.size(), db->stream))) return rc;
+        for (uint64_t a = 0; a < n; a++) {  // replacement values (pir.go:348)
+            const ClientPartDev &D = c->host_parts[part_ids[a]];
+            if ((rc = gather_enqueue(db, D.row0, D.n_rows, D.ridx, D.set_size * D.backup_group, D.rval, db->stream))) return rc;
+        }
+    }
+    PM_CUDA(cudaStreamSynchronize(db->stream));
+    return PM_OK;
+}
+
+PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status) {
+    using namespace pm;
+    if (!c || (q && (!queries || !out || !status))) return set_error(PM_ERR_ARG, "pm_client_query_batch: null pointer");
+    if (q == 0) return PM_OK;
+    if (q > 1u << 20) return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: too many queries in one call");
+    static_assert(sizeof(pm_client_query) == sizeof(ClientQueryDev), "pm_client_query layout");
+    for (uint64_t t = 0; t < q; t++) {
+        if (queries[t].part >= c->n_parts) return set_error(PM_ERR_ARG, "pm_client_query_batch: part id out of range");
+        if (queries[t].kind == 1 && queries[t].idx >= c->host_parts[queries[t].part].n_rows)
+            return set_error(PM_ERR_ARG, "pm_client_query_batch: idx %llu is out of range", (unsigned long long)queries[t].idx);  // pir.go:373-378
+    }
+    int rc = ensure_device(c->db->device);
+    if (rc) return rc;
+    pm_db *db = c->db;
+    std::lock_guard<std::mutex> lock(db->mu);
+    const uint64_t E = c->E, stride = (c->max_set + 3) & ~3ull;
+    // staging: queries | meta | offsets | answer descriptors   and   answers | out
+    const size_t b_q = q * sizeof(ClientQueryDev), b_meta = q * sizeof(ClientMeta), b_off = q * stride * 4, b_desc = q * 24;
+    void *d_in = nullptr, *d_out = nullptr;
+    if ((rc = scratch(db, 1, b_q + b_meta + b_off + b_desc + 64, &d_in))) return rc;
+    if ((rc = scratch(db, 0, 2 * q * E * 8, &d_out))) return rc;
+    ClientQueryDev *d_q = (ClientQueryDev *)d_in;
+    ClientMeta *d_meta = (ClientMeta *)((char *)d_in + b_q);
+    uint32_t *d_off = (uint32_t *)((char *)d_meta + b_meta);
+    uint64_t *d_row0 = (uint64_t *)((char *)d_off + b_off), *d_nrows = d_row0 + q;
+    uint32_t *d_chunk = (uint32_t *)(d_nrows + q), *d_set = d_chunk + q;
+    uint64_t *d_ans = (uint64_t *)d_out, *d_res = d_ans + q * E;
+    PM_CUDA(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, db->stream));
+    const size_t smem = (aes_tab_words<1>() + 64 + stride) * 4;
+    PM_CUDA(cudaFuncSetAttribute(client_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    client_prepare_kernel<<<(unsigned)c->n_parts, CL_THREADS, smem, db->stream>>>(c->d_parts, d_q, (uint32_t)q, (uint32_t)stride, d_off,
+                                                                                  d_meta, d_row0, d_nrows, d_chunk, d_set);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    if ((rc = answer_enqueue(db, d_row0, d_nrows, d_chunk, d_set, d_off, stride, q, (uint32_t)stride, d_ans, db->stream))) return rc;
+    client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, db->stream>>>(c->d_parts, d_q, d_meta, (uint32_t)q, (uint32_t)E, d_ans, d_res);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    PM_CUDA(cudaMemcpyAsync(out, d_res, q * E * 8, cudaMemcpyDeviceToHost, db->stream));
+    std::vector<ClientMeta> meta(q);
+    PM_CUDA(cudaMemcpyAsync(meta.data(), d_meta, b_meta, cudaMemcpyDeviceToHost, db->stream));
+    PM_CUDA(cudaStreamSynchronize(db->stream));
+    for (uint64_t t = 0; t < q; t++) status[t] = meta[t].status < 0 ? 0 : meta[t].status;
+    return PM_OK;
+}
+
+PM_EXPORT int pm_client_download(pm_client *c, uint32_t part, int table, uint64_t *out, uint64_t cap_words) {
+    using namespace pm;
+    if (!c || !out || part >= c->n_parts) return set_error(PM_ERR_ARG, "pm_client_download: bad argument");
+    int rc = ensure_device(c->db->device);
+    if (rc) return rc;
+    const ClientPartDev &D = c->host_parts[part];
+    const uint64_t P = D.n_primary, B = D.set_size * D.backup_group, E = c->E;
+    const uint64_t *src = nullptr;
+    uint64_t words = 0;
+    switch (table) {
+    case 0: src = D.tags; words = P; break;
+    case 1: src = D.parity; words = P * E; break;
+    case 2: src = D.pp; words = P; break;
+    case 3: src = D.ridx; words = B; break;
+    case 4: src = D.rval; words = B * E; break;
+    case 5: src = D.btags; words = B; break;
+    case 6: src = D.bparity; words = B * E; break;
+    case 7: src = D.hist; words = D.set_size; break;
+    case 8: src = D.finished; words = 1; break;
+    default: return set_error(PM_ERR_ARG, "pm_client_download: unknown table %d", table);
+    }
+    if (cap_words < words) return set_error(PM_ERR_ARG, "pm_client_download: buffer too small (%llu < %llu words)",
+                                            (unsigned long long)cap_words, (unsigned long long)words);
+    std::lock_guard<std::mutex> lock(c->db->mu);
+    PM_CUDA(cudaMemcpyAsync(out, src, words * 8, cudaMemcpyDeviceToHost, c->db->stream));
+    PM_CUDA(cudaStreamSynchronize(c->db->stream));
+    return PM_OK;
+}

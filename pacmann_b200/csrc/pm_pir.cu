@@ -698,3 +698,5 @@ PM_EXPORT int pm_answer_batch(pm_db *db, const uint64_t *row0, const uint64_t *n
     PM_CUDA(cudaStreamSynchronize(db->stream));
     return PM_OK;
 }
+
+#include "pm_client.cuh"

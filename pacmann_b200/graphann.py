@@ -23,14 +23,14 @@ def L2Dist(v1, v2, device=0):
 class GraphANNFrontend:
     """graphann.GraphANNFrontend over BasicGraphInfo (non-private) or PIRGraphInfo (private, private-search.go)."""
 
-    def __init__(self, vectors, graph, private=False, skipPrep=False, nonPrivateMode=False, seed=1, device=0):
+    def __init__(self, vectors, graph, private=False, skipPrep=False, nonPrivateMode=False, seed=1, device=0, resident=True):
         self.vectors = np.ascontiguousarray(vectors, np.float32)
         self.graph = np.ascontiguousarray(graph, np.int32)
         self.n, self.dim = self.vectors.shape
         self.m = self.graph.shape[1]
         L = _host.lib()
         if private:
-            h = L.pmh_frontend_pir(self.n, self.dim, self.m, _p(self.graph), _p(self.vectors), int(skipPrep), int(nonPrivateMode), seed, device)
+            h = L.pmh_frontend_pir(self.n, self.dim, self.m, _p(self.graph), _p(self.vectors), int(skipPrep), int(nonPrivateMode), seed, device, int(resident))
         else:
             h = L.pmh_frontend_basic(self.n, self.dim, self.m, _p(self.graph), _p(self.vectors))
         if not h:

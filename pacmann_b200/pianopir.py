@@ -155,6 +155,10 @@ class SimpleBatchPianoPIR:
     def SetSeeds(self, key_seed, repl_seed=0):
         _host.lib().pmh_batch_set_seeds(self.h, key_seed, repl_seed)
 
+    def EnableResidentClient(self):
+        """keep the hint tables in HBM and run the online client on the GPU (pm_client_*)"""
+        _host.check(_host.lib().pmh_batch_enable_resident(self.h))
+
     def Preprocessing(self):
         _host.check(_host.lib().pmh_batch_preprocessing(self.h))
 
@@ -171,7 +175,10 @@ class SimpleBatchPianoPIR:
         return out, None
 
     def subPIR(self, i):
-        return PianoPIR(0, 0, None, 0, _borrow=_host.lib().pmh_batch_sub(self.h, i), _keep=self)
+        h = _host.lib().pmh_batch_sub(self.h, i)
+        if not h:
+            raise _host.HostError(_host.lib().pmh_last_error().decode())
+        return PianoPIR(0, 0, None, 0, _borrow=h, _keep=self)
 
     FinishedBatchNum = property(lambda s: s._get(2))
     QueriesMadeInPartition = property(lambda s: s._get(3))
