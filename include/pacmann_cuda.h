@@ -73,6 +73,7 @@ int pm_db_sync(pm_db *db);
 
 /* A1: FIPS-197 AES-128 key schedule, 11 round keys as 44 little-endian uint32 (raw 16-byte blocks). */
 int pm_expand_key(const uint8_t key[16], uint32_t rk[44]);
+int pm_expand_key_batch(const uint8_t *keys /* [n][16] */, uint64_t n, uint32_t *rk /* [n][44] */);
 /* A2: out[i] = LE64((AES128_rk(B) xor B)[0:8]),  B = LE64((tags[i] << 35) + xs[i]) || 0^64. */
 int pm_prf_batch(const uint32_t rk[44], const uint64_t *tags, const uint64_t *xs, uint64_t n, uint64_t *out);
 /* A3: dst[0 : 4*(len_src/4)] ^= src[...] ; the len_src % 4 tail is left untouched (reference behaviour). */

@@ -49,6 +49,7 @@ SIGNATURES = {
     "pm_db_destroy": (C.c_int, [C.c_void_p]),
     "pm_db_sync": (C.c_int, [C.c_void_p]),
     "pm_expand_key": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pm_expand_key_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_prf_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_xor_slices": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "pm_hintgen": (C.c_int, [C.c_void_p, C.POINTER(HintJob), C.c_uint64]),

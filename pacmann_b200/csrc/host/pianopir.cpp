@@ -613,16 +613,18 @@ void SimpleBatchPianoPIR::EnableResidentClient() {
 void SimpleBatchPianoPIR::PreprocessResident(const std::vector<uint32_t> &ids, bool skipPrep) {
     std::vector<uint32_t> rk(ids.size() * 44);
     std::vector<uint64_t> seeds(ids.size());
+    std::vector<uint8_t> keys(ids.size() * 16);
     for (size_t a = 0; a < ids.size(); a++) {
         PianoPIRClient &c = subPIR[ids[a]]->client;
         c.FinishedQueryNum = 0;
         c.masterKey = DeriveKey(c.keySeed, c.keyEpoch, c.keyParts, c.keyIndex);
-        c.longKey = GetLongKey(c.masterKey);
+        memcpy(&keys[a * 16], c.masterKey.b, 16);
         c.localCache.clear();
         c.pendingCached.clear();
-        memcpy(&rk[a * 44], c.longKey.data(), 176);
         seeds[a] = Mix64(c.replSeed, c.keyEpoch * c.keyParts + c.keyIndex);
     }
+    check(pm_expand_key_batch(keys.data(), ids.size(), rk.data()), "pm_expand_key_batch");  // GetLongKey for every sub-PIR
+    for (size_t a = 0; a < ids.size(); a++) subPIR[ids[a]]->client.longKey.assign(rk.begin() + a * 44, rk.begin() + (a + 1) * 44);
     check(pm_client_preprocess(rclient, ids.data(), ids.size(), rk.data(), seeds.data(), skipPrep ? 1 : 0), "pm_client_preprocess");
 }
 

@@ -198,22 +198,21 @@ static int l2_host(const float *a, const float *b, uint64_t b_rows, uint64_t n, 
     if (dim > 0xffffffffull) return set_error(PM_ERR_UNSUPPORTED, "pm_l2: dim too large");
     int rc = ensure_device(device);
     if (rc) return rc;
-    float *d = nullptr;
     const size_t ab = n * dim * 4, bb = b_rows * dim * 4;
-    PM_CUDA(cudaMalloc(&d, ab + bb + n * 4 + 256));
-    float *d_b = d + n * dim, *d_out = d_b + b_rows * dim;
-    cudaError_t e = cudaMemcpy(d, a, ab, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMemcpy(d_b, b, bb, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
-        if (blocks > 148 * 16) blocks = 148 * 16;
-        l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS>>>(d, d_b, b_rows == 1 ? 0 : dim, n, (uint32_t)dim, d_out);
-        count_launch();
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, n * 4, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) return set_error(PM_ERR_CUDA, "pm_l2: %s", cudaGetErrorString(e));
+    void *w = nullptr;
+    cudaStream_t st;
+    std::unique_lock<std::mutex> lock;
+    if ((rc = dev_work(device, ab + bb + n * 4 + 256, &w, &st, &lock))) return rc;
+    float *d = (float *)w, *d_b = d + n * dim, *d_out = d_b + b_rows * dim;
+    PM_CUDA(cudaMemcpyAsync(d, a, ab, cudaMemcpyHostToDevice, st));
+    PM_CUDA(cudaMemcpyAsync(d_b, b, bb, cudaMemcpyHostToDevice, st));
+    uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS, 0, st>>>(d, d_b, b_rows == 1 ? 0 : dim, n, (uint32_t)dim, d_out);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    PM_CUDA(cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, st));
+    PM_CUDA(cudaStreamSynchronize(st));
     return PM_OK;
 }
 PM_EXPORT int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device) {

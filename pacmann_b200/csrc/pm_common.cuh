@@ -25,6 +25,8 @@ struct pm_db {
     std::mutex mu;             // serialises calls on one handle
     int sm_count;
     bool owns_rows;            // false for pm_db_wrap handles
+    unsigned int *sync_pool;   // 64 barrier counters (one 128-byte line each), handed out round-robin
+    std::atomic<unsigned> sync_next;
 };
 
 namespace pm {
@@ -36,6 +38,10 @@ int sm_count(int device);
 const void *zero_page(int device);  // 4 KB of device zeros, allocated once per device
 // grow-only scratch slot on a handle
 int scratch(pm_db *db, int slot, size_t bytes, void **out);
+unsigned int *sync_counter(pm_db *db);  // next barrier counter of the handle's pool
+// per-device grow-only workspace + stream for the handle-less entry points (pm_l2_*, pm_prf_batch, ...); the returned
+// lock serialises those calls on one device and must be held until the stream has been synchronised
+int dev_work(int device, size_t bytes, void **ptr, cudaStream_t *stream, std::unique_lock<std::mutex> *lock);
 
 #define PM_CUDA(expr)                                                                                   \
     do {                                                                                                \

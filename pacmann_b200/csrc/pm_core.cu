@@ -56,6 +56,39 @@ int ensure_device(int device) {
     return PM_OK;
 }
 int sm_count(int device) { return g_sm_count[device]; }
+unsigned int *sync_counter(pm_db *db) { return db->sync_pool + 32 * (db->sync_next.fetch_add(1) % 64); }
+
+struct DevWork {
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    void *buf = nullptr;
+    size_t bytes = 0;
+};
+static DevWork g_work[MAX_DEV];
+int dev_work(int device, size_t bytes, void **ptr, cudaStream_t *stream, std::unique_lock<std::mutex> *lock) {
+    if (device < 0) PM_CUDA(cudaGetDevice(&device));
+    DevWork &w = g_work[device];
+    *lock = std::unique_lock<std::mutex>(w.mu);
+    if (!w.stream) PM_CUDA(cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking));
+    if (w.bytes < bytes) {
+        if (w.buf) {
+            PM_CUDA(cudaStreamSynchronize(w.stream));
+            PM_CUDA(cudaFree(w.buf));
+            w.buf = nullptr;
+            w.bytes = 0;
+        }
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMalloc(&w.buf, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return set_error(PM_ERR_NOMEM, "cudaMalloc(%zu) for the device workspace failed: %s", want, cudaGetErrorString(e));
+        }
+        w.bytes = want;
+    }
+    *ptr = w.buf;
+    *stream = w.stream;
+    return PM_OK;
+}
 const void *zero_page(int device) { return g_zero[device]; }
 
 int scratch(pm_db *db, int slot, size_t bytes, void **out) {
@@ -138,7 +171,9 @@ static int db_new(void *borrowed, uint64_t n_rows, uint64_t entry_u64, int devic
             return set_error(PM_ERR_NOMEM, "cudaMalloc(%zu) for the table failed: %s", bytes, cudaGetErrorString(e));
         }
     }
-    e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
+    db->sync_next = 0;
+    e = cudaMalloc(&db->sync_pool, 64 * 128);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&db->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&db->ev[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -202,6 +237,7 @@ PM_EXPORT int pm_db_destroy(pm_db *db) {
             cudaEventDestroy(db->ev[i]);
         }
         if (db->owns_rows) cudaFree(db->d_rows);
+        cudaFree(db->sync_pool);
         cudaStreamDestroy(db->stream);
         cudaStreamDestroy(db->copy_stream);
     }

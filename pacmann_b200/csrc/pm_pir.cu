@@ -1,5 +1,6 @@
 // PianoPIR kernels for sm_100a: AES-PRF, key schedule, hint generation (A5/A7), server answer
 // (A6/A8), row gather, xorSlices.  See include/pacmann_cuda.h for the reference seams.
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -52,10 +53,13 @@ struct RkOfArray {
     __device__ __forceinline__ uint32_t operator[](int i) const { return a.w[i]; }
 };
 
-__global__ void expand_key_kernel(const uint32_t *key_words, uint32_t *rk) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void expand_key_kernel(const uint32_t *key_words, uint32_t *rk_out, uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const uint32_t *key = key_words + 4 * t;
+    uint32_t *rk = rk_out + 44 * t;
     uint32_t w[44];
-    for (int i = 0; i < 4; i++) w[i] = key_words[i];
+    for (int i = 0; i < 4; i++) w[i] = key[i];
     uint32_t rcon = 1;
     for (int i = 4; i < 44; i++) {
         uint32_t t = w[i - 1];
@@ -115,6 +119,7 @@ struct HintParams {
     const void *db;
     uint32_t n_jobs, n_tiles;
     uint32_t ev, evx;  // vectors per row (incl. un-xored tail), vectors that are xored
+    unsigned int *sync;  // round barrier counter (cooperative launch) or nullptr
 };
 struct RkOfJob {
     const HintParams &P;
@@ -196,7 +201,28 @@ __global__ void __launch_bounds__(HG_THREADS, 1) hintgen_kernel(const __grid_con
     const uint32_t hints_per_tile = (HG_THREADS / 32) * GPW;
     const uint32_t ev = P.ev, evx = P.evx;
 
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+    // Rounds: in round r the CTAs process tiles r*grid .. r*grid+grid-1, i.e. one contiguous range of hints of
+    // (nearly always) one sub-PIR, and all of them sweep that sub-PIR's DB slice from chunk 0.  With the round
+    // barrier the CTAs start every sweep together, so a chunk is fetched from HBM once per round and re-hit in L2
+    // by the other CTAs; without it they drift apart until the sweeps are uncorrelated.
+    const uint32_t rounds = (P.n_tiles + gridDim.x - 1) / gridDim.x;
+    for (uint32_t round = 0; round < rounds; round++) {
+        const uint32_t tile = round * gridDim.x + blockIdx.x;
+        if (P.sync && round > 0) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(P.sync, 1u);
+                const unsigned int target = round * gridDim.x;
+                unsigned int seen;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.sync));
+                    if (seen < target) __nanosleep(100);
+                } while (seen < target);
+            }
+            __syncthreads();
+        }
+        if (tile >= P.n_tiles) continue;
         int j = 0;
         while (j + 1 < (int)P.n_jobs && tile >= P.jobs[j + 1].tile_begin) j++;
         const HintJobDev &J = P.jobs[j];
@@ -338,7 +364,16 @@ template <typename KERN>
 static int launch_hg(KERN kern, int smem, const HintParams &P, int sm, cudaStream_t st) {
     PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     const uint32_t grid = P.n_tiles < (uint32_t)sm ? P.n_tiles : (uint32_t)sm;
-    kern<<<grid, HG_THREADS, smem, st>>>(P);
+    if (P.sync && P.n_tiles > grid) {
+        // round barrier needs every CTA resident: cooperative launch (one 512-thread CTA per SM always fits)
+        PM_CUDA(cudaMemsetAsync(P.sync, 0, sizeof(unsigned int), st));
+        void *args[] = {(void *)&P};
+        PM_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(HG_THREADS), args, (size_t)smem, st));
+    } else {
+        HintParams Q = P;
+        Q.sync = nullptr;
+        kern<<<grid, HG_THREADS, smem, st>>>(Q);
+    }
     PM_CHECK_LAUNCH();
     count_launch();
     return PM_OK;
@@ -409,6 +444,13 @@ int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStr
         HintParams P;
         memset(&P, 0, sizeof(P));
         P.db = db->d_rows;
+        // The round barrier pays when a sub-PIR's slice does not fit in L2 (measured: 896 B x 200 k rows = 179 MB,
+        // -12 % time); for slices that stay L2-resident anyway (SIFT-shaped: 40 MB) it only costs.  PM_HG_SYNC=0|1 forces.
+        static const int force_sync = env_int("PM_HG_SYNC", -1);
+        uint64_t max_slice = 0;
+        for (uint64_t b = a; b < n_jobs && b < a + HG_MAX_JOBS; b++) max_slice = std::max<uint64_t>(max_slice, jobs[b].n_rows * E * 8);
+        const bool use_sync = force_sync >= 0 ? force_sync != 0 : max_slice > (64ull << 20);
+        P.sync = use_sync ? sync_counter(db) : nullptr;
         P.ev = ev;
         P.evx = evx;
         uint32_t hpt = 0;
@@ -509,23 +551,26 @@ using namespace pm;
 // =============================================================================================
 // C-ABI
 // =============================================================================================
-PM_EXPORT int pm_expand_key(const uint8_t key[16], uint32_t rk[44]) {
-    if (!key || !rk) return set_error(PM_ERR_ARG, "pm_expand_key: null pointer");
+PM_EXPORT int pm_expand_key_batch(const uint8_t *keys, uint64_t n, uint32_t *rk) {
+    if (n && (!keys || !rk)) return set_error(PM_ERR_ARG, "pm_expand_key: null pointer");
+    if (n == 0) return PM_OK;
+    if (n > 1u << 24) return set_error(PM_ERR_UNSUPPORTED, "pm_expand_key_batch: too many keys");
     int rc = ensure_device(-1);
     if (rc) return rc;
-    uint32_t *d = nullptr;
-    PM_CUDA(cudaMalloc(&d, (4 + 44) * 4));
-    cudaError_t e = cudaMemcpy(d, key, 16, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) {
-        expand_key_kernel<<<1, 32>>>(d, d + 4);
-        count_launch();
-        e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaMemcpy(rk, d + 4, 44 * 4, cudaMemcpyDeviceToHost);
-    cudaFree(d);
-    if (e != cudaSuccess) return set_error(PM_ERR_CUDA, "pm_expand_key: %s", cudaGetErrorString(e));
+    void *w = nullptr;
+    cudaStream_t st;
+    std::unique_lock<std::mutex> lock;
+    if ((rc = dev_work(-1, n * (16 + 176), &w, &st, &lock))) return rc;
+    uint32_t *d_key = (uint32_t *)w, *d_rk = d_key + 4 * n;
+    PM_CUDA(cudaMemcpyAsync(d_key, keys, n * 16, cudaMemcpyHostToDevice, st));
+    expand_key_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(d_key, d_rk, (uint32_t)n);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    PM_CUDA(cudaMemcpyAsync(rk, d_rk, n * 176, cudaMemcpyDeviceToHost, st));
+    PM_CUDA(cudaStreamSynchronize(st));
     return PM_OK;
 }
+PM_EXPORT int pm_expand_key(const uint8_t key[16], uint32_t rk[44]) { return pm_expand_key_batch(key, 1, rk); }
 
 PM_EXPORT int pm_prf_batch(const uint32_t rk[44], const uint64_t *tags, const uint64_t *xs, uint64_t n, uint64_t *out) {
     if (!rk || (n && (!tags || !xs || !out))) return set_error(PM_ERR_ARG, "pm_prf_batch: null pointer");
