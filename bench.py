@@ -187,6 +187,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-search", action="store_true", help="skip the private-ANN queries/s part")
+    ap.add_argument("--search-queries", type=int, default=96, help="private ANN queries per GPU")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -312,6 +314,14 @@ def main():
     if rank == 0:
         verified = spot_check(cabi, host_db, parts, rk_all, my_hints, out_host.numpy().view(np.uint64).reshape(-1, E))
 
+    # ---- second half of the metric: end-to-end private-ANN queries/s on MS-MARCO-shaped data ----
+    private_ann = None
+    if not args.no_search:
+        del host_db, out_host, jobs_host, jobs_dev, out_dev, gather_list
+        db.close()
+        torch.cuda.empty_cache()
+        private_ann = private_search(args, rank, world, local_rank, dist if world > 1 else None, dev)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         b_hbm_rank = db_bytes + max_count * E * 8      # per GPU: whole DB read once + its share of the parities
@@ -333,6 +343,7 @@ def main():
                          "xor_gather_gbs": b_xor / world / (kern_ms * 1e-3) / 1e9,
                          "prf_per_s": n_prf / world / (kern_ms * 1e-3)},
             "verified_vs_prf_definition": verified,
+            "private_ann": private_ann,
             "reference_published": {"msmarco_prep_s": "9-10 (1 thread, reproduction/msmarco/README.md:26)"},
         }
         if not args.no_cpu_baseline and world == 1:
@@ -341,6 +352,72 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def private_search(args, rank, world, local_rank, dist, dev):
+    """End-to-end private graph search (graphann.SearchKNN over PIRGraphInfo, private-search.go) on MS-MARCO-shaped
+    synthetic data: 3 201 821 x 192 fp32, degree-32 random graph (genRandomGraph, private-search.go:54-69), k = 100,
+    step 20, parallel 3 (reproduction/msmarco/reproduce.sh:226-230).  Query batches shard across GPUs: every rank
+    owns a replica of the DB and an independent client and answers its own queries.  Preprocessing
+    ("maintenance") is excluded from the per-query time exactly as the reference separates it
+    (private-search.go:219-240) and reported on its own.  Rank 0 also times the CPU oracle on a few queries."""
+    import torch
+    from pacmann_b200 import cabi, graphann
+    from pacmann_b200.keys import mix64
+    n, dim, m, k, step, par = N_ROWS, 192, 32, 100, 20, 3
+    rng = np.random.default_rng(SEED)
+    vec = rng.standard_normal((n, dim), dtype=np.float32) * np.linspace(0.82, 0.29, dim, dtype=np.float32)
+    graph = rng.integers(0, n, (n, m), dtype=np.int32)
+    loop = graph == np.arange(n, dtype=np.int32)[:, None]
+    graph[loop] = (graph[loop] + 1) % n
+    nq = args.search_queries
+    qall = vec[np.random.default_rng(SEED + 1).integers(0, n, nq * world)] + np.float32(0.25)
+    queries = qall[rank * nq:(rank + 1) * nq]
+    seed = SEED + 2
+    f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed, device=local_rank)
+    t0 = time.perf_counter()
+    f.Preprocess()
+    setup_s = time.perf_counter() - t0
+    pir = f.PIR
+    prep_s = pir.PreprocessingTime()
+    f.SearchKNNBatch(queries[:2], k, step, par)
+    if dist is not None:
+        dist.barrier()
+    l0, s0 = cabi.launch_count(), pir.serverQueries
+    t0 = time.perf_counter()
+    f.SearchKNNBatch(queries, k, step, par)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt_max = float(tt[0])
+    out = {
+        "workload": "MS-MARCO-shaped synthetic private graph search (BASELINE.json configs[2])", "n": n, "dim": dim, "m": m, "k": k,
+        "step": step, "parallel": par, "queries": nq * world, "queries_per_gpu": nq, "n_gpus": world,
+        "queries_per_s": nq * world / dt_max, "s_per_query_one_client": dt / nq,
+        "pir_preprocessing_s": prep_s, "setup_s_pack_upload_preprocess": setup_s,
+        "gpu_launches": int(cabi.launch_count() - l0), "server_subqueries": int(pir.serverQueries - s0),
+        "pir_success_rate": f.succQueryNum / max(1, f.totalQueryNum),
+        "client": "GPU-resident hint tables (pm_client_*); maintenance excluded as in private-search.go:219-240",
+        "reference_published": "0.0559 / 0.0640 s per query on SIFT1M, 1 thread (private-search-report.txt:19,44)",
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import oracle as o
+        raw = o.pack_db(vec, graph)
+        o_pir = o.SimpleBatchPianoPIR(n, (dim + m) * 4, m, raw, 8)
+        t0 = time.perf_counter()
+        o_pir.preprocessing(key_seed=mix64(seed, 1), repl_seed=mix64(seed, 2), threads=os.cpu_count())
+        cprep = time.perf_counter() - t0
+        start = f.StartVertexIds()
+        ncpu = 8
+        o.search_knn_private(o_pir, vec, graph, start, queries[:1], k, step, par)
+        t0 = time.perf_counter()
+        o_ret, _, _ = o.search_knn_private(o_pir, vec, graph, start, queries[1:1 + ncpu], k, step, par)
+        cdt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"queries_per_s": ncpu / cdt, "s_per_query": cdt / ncpu, "cores": 1, "kind": "port",
+                               "sample": f"{ncpu} queries, online part single-threaded as the reference",
+                               "pir_preprocessing_s_all_cores": cprep}
+    return out
 
 
 def spot_check(cabi, host_db, parts, rk_all, my_hints, got):
