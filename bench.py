@@ -261,6 +261,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing ----
+    torch.cuda.synchronize()   # buffers above were created on torch's default stream
     sampler = ClockSampler(local_rank)
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):

@@ -1,5 +1,6 @@
 // graphann distance kernels for sm_100a: bit-exact fp32 L2 (A9) and the uint32 inner-product linear
 // scan (A11).  See include/pacmann_cuda.h for the reference seams.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -88,53 +89,72 @@ __global__ void __launch_bounds__(L2_THREADS) l2_pairs_kernel(const float *a, co
 
 // ---------------------------------------------------------------------------------------------
 // A11: uint32 wrapping inner-product scan (graphann/l2_distance_amd64.s:39-68, graphann_test.go:268-273)
-// One thread per row, QT queries per pass held as accumulators; query words come from shared memory
-// as warp-wide broadcasts.  Integer arithmetic mod 2^32 is associative, so any summation order gives
-// the reference's result bit for bit.
+// Tiles of IP_ROWS consecutive rows are contiguous in memory: they are staged into shared memory with fully
+// coalesced 16-byte cp.async copies (row stride padded by one vector so the per-row reads below are bank-conflict
+// free), then one thread per row accumulates QT queries at a time; query words arrive as warp-wide broadcasts.
+// Two CTAs per SM overlap one CTA's copy phase with the other's multiply phase.  Integer arithmetic mod 2^32 is
+// associative, so any summation order gives the reference's result bit for bit.
 // ---------------------------------------------------------------------------------------------
 constexpr int IP_THREADS = 128;
-constexpr int IP_QT = 16;
-__global__ void __launch_bounds__(IP_THREADS) ip_scan_kernel(const uint4 *rows, uint64_t n_rows, uint32_t dim4,
-                                                             const uint32_t *queries, uint32_t n_queries, uint32_t q0,
-                                                             uint32_t *checksum, uint32_t *ip_out) {
-    extern __shared__ __align__(16) uint32_t s_qw[];  // [IP_QT][dim]
-    uint4 *s_q4 = reinterpret_cast<uint4 *>(s_qw);
-    const uint32_t nq = min((uint32_t)IP_QT, n_queries - q0);
-    for (uint32_t i = threadIdx.x; i < IP_QT * dim4; i += IP_THREADS) {
+constexpr int IP_ROWS = 128;
+constexpr int IP_QT_MAX = 16;
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+template <int QT>
+__global__ void __launch_bounds__(IP_THREADS, 2) ip_scan_kernel(const uint4 *rows, uint64_t n_rows, uint32_t dim4, uint32_t tile_rows,
+                                                                const uint32_t *queries, uint32_t n_queries, uint32_t q0,
+                                                                uint32_t *checksum, uint32_t *ip_out) {
+    extern __shared__ __align__(16) uint32_t s_qw[];
+    uint4 *s_q4 = reinterpret_cast<uint4 *>(s_qw);           // [QT][dim4]
+    uint4 *s_tile = s_q4 + QT * dim4;                        // [tile_rows][dim4 + 1]
+    const uint32_t nq = min((uint32_t)QT, n_queries - q0), pitch = dim4 + 1;
+    for (uint32_t i = threadIdx.x; i < QT * dim4; i += IP_THREADS) {
         uint32_t t = i / dim4, c = i % dim4;
         s_q4[i] = t < nq ? reinterpret_cast<const uint4 *>(queries)[(uint64_t)(q0 + t) * dim4 + c] : make_uint4(0, 0, 0, 0);
     }
-    __syncthreads();
-    uint32_t total[IP_QT];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t total[QT];
 #pragma unroll
-    for (int t = 0; t < IP_QT; t++) total[t] = 0;
-    for (uint64_t r = (uint64_t)blockIdx.x * IP_THREADS + threadIdx.x; r < n_rows; r += (uint64_t)gridDim.x * IP_THREADS) {
-        uint32_t acc[IP_QT];
+    for (int t = 0; t < QT; t++) total[t] = 0;
+    const uint64_t n_tiles = (n_rows + tile_rows - 1) / tile_rows;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t r0 = tile * tile_rows;
+        const uint32_t nr = (uint32_t)min((uint64_t)tile_rows, n_rows - r0);
+        __syncthreads();  // previous tile fully consumed (and the queries written, first time round)
+        for (uint32_t r = warp; r < nr; r += IP_THREADS / 32)
+            for (uint32_t c = lane; c < dim4; c += 32) cp_async16(s_tile + r * pitch + c, rows + (r0 + r) * dim4 + c);
+        asm volatile("cp.async.commit_group;");
+        asm volatile("cp.async.wait_group 0;");
+        __syncthreads();
+        if (threadIdx.x < nr) {
+            uint32_t acc[QT];
 #pragma unroll
-        for (int t = 0; t < IP_QT; t++) acc[t] = 0;
-        const uint4 *row = rows + r * dim4;
-#pragma unroll 2
-        for (uint32_t c = 0; c < dim4; c++) {
-            const uint4 v = __ldg(row + c);
+            for (int t = 0; t < QT; t++) acc[t] = 0;
+            const uint4 *row = s_tile + threadIdx.x * pitch;
+#pragma unroll 4
+            for (uint32_t c = 0; c < dim4; c++) {
+                const uint4 v = row[c];
 #pragma unroll
-            for (int t = 0; t < IP_QT; t++) {
-                const uint4 qv = s_q4[t * dim4 + c];
-                acc[t] += v.x * qv.x + v.y * qv.y + v.z * qv.z + v.w * qv.w;
+                for (int t = 0; t < QT; t++) {
+                    const uint4 qv = s_q4[t * dim4 + c];
+                    acc[t] += v.x * qv.x + v.y * qv.y + v.z * qv.z + v.w * qv.w;
+                }
             }
-        }
 #pragma unroll
-        for (int t = 0; t < IP_QT; t++) {
-            total[t] += acc[t];
-            if (ip_out && (uint32_t)t < nq) ip_out[(uint64_t)(q0 + t) * n_rows + r] = acc[t];
+            for (int t = 0; t < QT; t++) {
+                total[t] += acc[t];
+                if (ip_out && (uint32_t)t < nq) ip_out[(uint64_t)(q0 + t) * n_rows + r0 + threadIdx.x] = acc[t];
+            }
         }
     }
     // block reduction, then one atomic per query per block
-    __shared__ uint32_t s_red[IP_THREADS / 32][IP_QT];
+    __shared__ uint32_t s_red[IP_THREADS / 32][IP_QT_MAX];
 #pragma unroll
-    for (int t = 0; t < IP_QT; t++) {
+    for (int t = 0; t < QT; t++) {
         uint32_t v = total[t];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5][t] = v;
+        if (lane == 0) s_red[warp][t] = v;
     }
     __syncthreads();
     if (threadIdx.x < nq) {
@@ -172,19 +192,30 @@ int ip_scan_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n
     if (nq > 0x7fffffffull) return set_error(PM_ERR_UNSUPPORTED, "ip scan: too many queries");
     PM_CUDA(cudaMemsetAsync(checksum, 0, nq * 4, st));
     const uint32_t dim4 = (uint32_t)(dim / 4);
-    const size_t smem = (size_t)IP_QT * dim * 4;
-    PM_CUDA(cudaFuncSetAttribute(ip_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint64_t blocks = (db->n_rows + IP_THREADS - 1) / IP_THREADS;
-    const uint64_t cap = (uint64_t)db->sm_count * 8;
-    if (blocks > cap) blocks = cap;
-    if (blocks == 0) blocks = 1;
-    for (uint64_t q0 = 0; q0 < nq; q0 += IP_QT) {
-        ip_scan_kernel<<<(unsigned)blocks, IP_THREADS, smem, st>>>((const uint4 *)db->d_rows, db->n_rows, dim4, queries,
-                                                                  (uint32_t)nq, (uint32_t)q0, checksum, ip_out);
+    // rows per tile: as many as fit beside the queries in ~100 KB, so that two CTAs share an SM
+    const size_t q_bytes = (size_t)IP_QT_MAX * dim * 4, row_bytes = (size_t)(dim4 + 1) * 16;
+    uint32_t tile_rows = (uint32_t)std::min<size_t>(IP_ROWS, (100 * 1024 - std::min<size_t>(q_bytes, 48 * 1024)) / row_bytes);
+    if (tile_rows == 0) return set_error(PM_ERR_UNSUPPORTED, "ip scan: dim too large");
+    const uint64_t n_tiles = (db->n_rows + tile_rows - 1) / tile_rows;
+    uint64_t blocks = std::min<uint64_t>(n_tiles ? n_tiles : 1, (uint64_t)db->sm_count * 2);
+    auto launch = [&](auto kern, int qt, uint64_t q0) -> int {
+        const size_t smem = (size_t)qt * dim * 4 + (size_t)tile_rows * row_bytes;
+        PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, IP_THREADS, smem, st>>>((const uint4 *)db->d_rows, db->n_rows, dim4, tile_rows, queries, (uint32_t)nq,
+                                                        (uint32_t)q0, checksum, ip_out);
         PM_CHECK_LAUNCH();
         count_launch();
+        return PM_OK;
+    };
+    uint64_t q0 = 0;
+    int rc = PM_OK;
+    while (q0 < nq && rc == PM_OK) {  // passes of 16 queries, then 4, then single queries for the remainder
+        const uint64_t left = nq - q0;
+        if (left >= 16 || left > 4) { rc = launch(ip_scan_kernel<16>, 16, q0); q0 += 16; }
+        else if (left > 1) { rc = launch(ip_scan_kernel<4>, 4, q0); q0 += 4; }
+        else { rc = launch(ip_scan_kernel<1>, 1, q0); q0 += 1; }
     }
-    return PM_OK;
+    return rc;
 }
 
 }  // namespace pm
