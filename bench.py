@@ -20,6 +20,7 @@ timed region, so the job is the same at every N ("strong" scaling: total work fi
 Only the cpu_baseline / --impl reference legs import oracle/; the timed GPU path is the C-ABI library.
 """
 import argparse
+import ctypes as C
 import json
 import math
 import os
@@ -169,13 +170,13 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(parts, n_gpus):
+def workload_config(parts, n_gpus, exchange="none"):
     return {
         "workload": "MS-MARCO-shaped batch-PIR hint preprocessing (BASELINE.json configs[3])",
         "n_entries": N_ROWS, "entry_bytes": ENTRY_U64 * 8, "batch_size": BATCH, "sub_pirs": len(parts),
         "fail_prob_log2": FAIL_LOG2, "chunk_size": parts[0]["chunk"], "set_size": parts[0]["set"],
         "primary_hints": parts[0]["primary"], "backup_hints": parts[0]["set"] * parts[0]["mqpc"],
-        "sharding": f"hint-set x{n_gpus}, DB replicated per GPU",
+        "sharding": f"hint-set x{n_gpus}, DB replicated per GPU", "exchange": exchange,
         "l2_policy": "inputs_exceed_l2 (2.87 GB table vs 126 MB L2)",
     }
 
@@ -187,6 +188,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how parities reach rank 0")
     ap.add_argument("--no-search", action="store_true", help="skip the private-ANN queries/s part")
     ap.add_argument("--search-queries", type=int, default=96, help="private ANN queries per GPU")
     args = ap.parse_args()
@@ -266,9 +268,41 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     comm = torch.cuda.Stream(device=dev)
 
+    # ---- N > 1, default exchange: no gather step at all.  Rank 0 owns the full parity table ([hints][E] per sub-PIR,
+    # in hint order); every other rank maps it over CUDA IPC and its hint kernel stores its shard straight into rank 0's
+    # HBM through NVLink peer memory while it computes.  One 1-element all-reduce per step is the completion signal.
+    p2p_table, p2p_local, jobs_p2p, flag = None, None, None, None
+    part_off = np.concatenate([[0], np.cumsum([p["hints"] for p in parts])]).astype(np.int64)
+    if world > 1 and args.exchange == "p2p":
+        try:
+            handle = [None]
+            if rank == 0:
+                p2p_local = cabi.buf_alloc(int(part_off[-1]) * E * 8, local_rank)
+                handle[0] = cabi.buf_ipc_export(p2p_local, local_rank)
+            dist.broadcast_object_list(handle, src=0)
+            p2p_table = p2p_local if rank == 0 else cabi.buf_ipc_open(handle[0], local_rank)
+            jobs_p2p = [cabi.make_job(p["row0"], p["n_rows"], p["chunk"], p["set"], rk_all[i], a, b - a, p["primary"], p["mqpc"],
+                                      parity_out=p2p_table + (int(part_off[i]) + a) * E * 8)
+                        for i, (p, (a, b)) in enumerate(zip(parts, my_hints))]
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        except Exception as exc:       # e.g. IPC not permitted in this container: fall back to the NCCL gather
+            if rank == 0:
+                print(f"bench.py: peer-memory exchange unavailable ({exc}); using NCCL gather", file=sys.stderr)
+            jobs_p2p = None
+        ok = torch.tensor([1 if jobs_p2p is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok[0]) == 0:
+            jobs_p2p = None
+    exchange = "single GPU" if world == 1 else ("peer-memory stores into rank 0 (CUDA IPC over NVLink) + 1-element all-reduce"
+                                                if jobs_p2p is not None else "NCCL gather overlapped by job group")
+
     def step_device():
         if world == 1:
             cabi.hintgen_dev(db, jobs_dev, stream.cuda_stream)
+            return
+        if jobs_p2p is not None:
+            cabi.hintgen_dev(db, jobs_p2p, stream.cuda_stream)
+            dist.all_reduce(flag)      # stream-ordered after the kernel on every rank: all shards have landed when it returns
             return
         for g in range(n_groups):
             cabi.hintgen_dev(db, jobs_dev[bounds[g]:bounds[g + 1]], stream.cuda_stream)
@@ -350,11 +384,26 @@ def main():
     verified = None
     if rank == 0:
         verified = spot_check(cabi, host_db, parts, rk_all, my_hints, out_host.numpy().view(np.uint64).reshape(-1, E))
+        if jobs_p2p is not None:       # the table every rank wrote into: check hints of every rank's shard
+            full = torch.empty(int(part_off[-1]) * E, dtype=torch.int64)
+            cudart = C.CDLL("libcudart.so.12")
+            assert cudart.cudaMemcpy(C.c_void_p(full.data_ptr()), C.c_void_p(p2p_table), C.c_size_t(full.numel() * 8), 2) == 0
+            all_hints = [(0, p["hints"]) for p in parts]
+            verified = verified and spot_check(cabi, host_db, parts, rk_all, all_hints, full.numpy().view(np.uint64).reshape(-1, E),
+                                               extra=[p["hints"] * r // world for p in parts[:1] for r in range(1, world)])
 
     # ---- second half of the metric: end-to-end private-ANN queries/s on MS-MARCO-shaped data ----
     private_ann = None
     if not args.no_search:
         del host_db, out_host, jobs_host, jobs_dev, out_grp, gather_grp
+        if world > 1:
+            dist.barrier()
+        if p2p_table is not None and rank != 0:
+            cabi.buf_ipc_close(p2p_table, local_rank)
+        if world > 1:
+            dist.barrier()
+        if p2p_local is not None:
+            cabi.buf_free(p2p_local, local_rank)
         db.close()
         torch.cuda.empty_cache()
         private_ann = private_search(args, rank, world, local_rank, dist if world > 1 else None, dev)
@@ -366,7 +415,7 @@ def main():
         line = {
             "metric": "pir_hintgen_db_scan_gbs", "value": value, "unit": "GB/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(parts, world),
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": workload_config(parts, world, exchange),
             "clocks": clocks, "gpu_launches": int(launches) * world,
             "e2e": {"value": db_bytes / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s * 1e3,
@@ -457,13 +506,13 @@ def private_search(args, rank, world, local_rank, dist, dev):
     return out
 
 
-def spot_check(cabi, host_db, parts, rk_all, my_hints, got):
+def spot_check(cabi, host_db, parts, rk_all, my_hints, got, extra=()):
     """Recompute a handful of parities on the host from pm_prf_batch offsets + numpy XOR (no oracle)."""
     ok, off = True, 0
     rng = np.random.default_rng(1)
     for p, (a, b), rk in zip(parts, my_hints, rk_all):
         if b > a:
-            for h in {a, b - 1, int(rng.integers(a, b))}:
+            for h in {a, b - 1, int(rng.integers(a, b))} | {x for x in extra if a <= x < b} | {x - 1 for x in extra if a < x <= b}:
                 cs = np.arange(p["set"], dtype=np.uint64)
                 offs = cabi.prf_batch(rk, np.full(p["set"], h, np.uint64), cs) & np.uint64(p["chunk"] - 1)
                 rows = cs * np.uint64(p["chunk"]) + offs

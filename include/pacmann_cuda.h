@@ -71,6 +71,15 @@ int pm_db_destroy(pm_db *db);
 /* blocks until everything enqueued on the handle's own streams has finished */
 int pm_db_sync(pm_db *db);
 
+/* Plain device buffers shareable between the per-GPU processes of one box (CUDA IPC).  Multi-GPU hint generation:
+ * rank 0 allocates the full parity table, the other ranks map it (pm_buf_ipc_open) and pass addresses inside it as
+ * pm_hint_job.parity_out to pm_hintgen_dev, so every kernel stores its shard straight into rank 0's HBM over NVLink. */
+int pm_buf_alloc(uint64_t bytes, int device, void **dev_ptr);
+int pm_buf_free(void *dev_ptr, int device);
+int pm_buf_ipc_export(void *dev_ptr, int device, uint8_t handle[64]);
+int pm_buf_ipc_open(const uint8_t handle[64], int device, void **dev_ptr);
+int pm_buf_ipc_close(void *dev_ptr, int device);
+
 /* A1: FIPS-197 AES-128 key schedule, 11 round keys as 44 little-endian uint32 (raw 16-byte blocks). */
 int pm_expand_key(const uint8_t key[16], uint32_t rk[44]);
 int pm_expand_key_batch(const uint8_t *keys /* [n][16] */, uint64_t n, uint32_t *rk /* [n][44] */);

@@ -48,6 +48,11 @@ SIGNATURES = {
     "pm_db_info": (C.c_int, [C.c_void_p, u64p, u64p, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "pm_db_destroy": (C.c_int, [C.c_void_p]),
     "pm_db_sync": (C.c_int, [C.c_void_p]),
+    "pm_buf_alloc": (C.c_int, [C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "pm_buf_free": (C.c_int, [C.c_void_p, C.c_int]),
+    "pm_buf_ipc_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pm_buf_ipc_open": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "pm_buf_ipc_close": (C.c_int, [C.c_void_p, C.c_int]),
     "pm_expand_key": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pm_expand_key_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_prf_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -169,6 +174,33 @@ class DB:
             self.close()
         except Exception:
             pass
+
+
+def buf_alloc(nbytes, device=0):
+    p = C.c_void_p()
+    check(lib().pm_buf_alloc(nbytes, device, C.byref(p)))
+    return p.value
+
+
+def buf_free(ptr, device=0):
+    check(lib().pm_buf_free(ptr, device))
+
+
+def buf_ipc_export(ptr, device=0):
+    h = (C.c_uint8 * 64)()
+    check(lib().pm_buf_ipc_export(ptr, device, h))
+    return bytes(h)
+
+
+def buf_ipc_open(handle, device=0):
+    h = (C.c_uint8 * 64).from_buffer_copy(handle)
+    p = C.c_void_p()
+    check(lib().pm_buf_ipc_open(h, device, C.byref(p)))
+    return p.value
+
+
+def buf_ipc_close(ptr, device=0):
+    check(lib().pm_buf_ipc_close(ptr, device))
 
 
 def expand_key(key):

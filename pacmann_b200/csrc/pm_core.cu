@@ -244,3 +244,51 @@ PM_EXPORT int pm_db_destroy(pm_db *db) {
     delete db;
     return PM_OK;
 }
+
+// ---- plain device buffers that can be shared between the per-GPU processes of one box (CUDA IPC) ----
+// Used for the multi-GPU form of hint generation: rank 0 owns the full parity table, every other rank maps it and
+// its hint kernel stores its shard straight into rank 0's HBM over NVLink -- no separate gather step.
+PM_EXPORT int pm_buf_alloc(uint64_t bytes, int device, void **dev_ptr) {
+    if (!dev_ptr) return set_error(PM_ERR_ARG, "pm_buf_alloc: null pointer");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    cudaError_t e = cudaMalloc(dev_ptr, bytes ? bytes : 256);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(PM_ERR_NOMEM, "pm_buf_alloc: cudaMalloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    }
+    return PM_OK;
+}
+PM_EXPORT int pm_buf_free(void *dev_ptr, int device) {
+    if (!dev_ptr) return PM_OK;
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    PM_CUDA(cudaFree(dev_ptr));
+    return PM_OK;
+}
+PM_EXPORT int pm_buf_ipc_export(void *dev_ptr, int device, uint8_t handle[64]) {
+    if (!dev_ptr || !handle) return set_error(PM_ERR_ARG, "pm_buf_ipc_export: null pointer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    PM_CUDA(cudaIpcGetMemHandle(&h, dev_ptr));
+    memcpy(handle, &h, 64);
+    return PM_OK;
+}
+PM_EXPORT int pm_buf_ipc_open(const uint8_t handle[64], int device, void **dev_ptr) {
+    if (!dev_ptr || !handle) return set_error(PM_ERR_ARG, "pm_buf_ipc_open: null pointer");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    PM_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return PM_OK;
+}
+PM_EXPORT int pm_buf_ipc_close(void *dev_ptr, int device) {
+    if (!dev_ptr) return PM_OK;
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    PM_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return PM_OK;
+}
