@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -404,6 +405,9 @@ SimpleBatchPianoPIR::SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNu
     }
 }
 SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
+    if (getenv("PM_HOST_PROFILE") && profQueryCalls)
+        fprintf(stderr, "[host profile] Query calls %llu: %.1f us per call, of which pm_client_query_batch %.1f us\n",
+                (unsigned long long)profQueryCalls, profQueryTotal / profQueryCalls * 1e6, profGpuCall / profQueryCalls * 1e6);
     if (rclient) pm_client_destroy(rclient);
     for (auto *p : subPIR) delete p;
     delete db;
@@ -644,6 +648,11 @@ void SimpleBatchPianoPIR::SyncTablesFromDevice(uint64_t i) {
 }
 
 int SimpleBatchPianoPIR::QueryResident(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret) {
+    struct Timer {
+        double &acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~Timer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+    } timer{profQueryTotal};
+    profQueryCalls += 1;
     const uint64_t PN = config.PartitionNum, PS = config.PartitionSize, E = config.DBEntrySize;
     const uint64_t queryNumToMake = idx.size() / PN;
     std::vector<std::vector<uint64_t>> partitionQueries(PN);
@@ -662,7 +671,9 @@ int SimpleBatchPianoPIR::QueryResident(const std::vector<uint64_t> &idx, std::ve
         std::vector<uint64_t> out(ql.size() * E);
         std::vector<int32_t> status(ql.size());
         if (!ql.empty()) {
+            auto tg = std::chrono::steady_clock::now();
             check(pm_client_query_batch(rclient, ql.data(), ql.size(), out.data(), status.data()), "pm_client_query_batch");
+            profGpuCall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
             serverLaunches += 1;
         }
         std::vector<uint64_t> zero(E, 0);

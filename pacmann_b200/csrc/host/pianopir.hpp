@@ -160,6 +160,8 @@ public:
     void EnableResidentClient();
     void SyncTablesFromDevice(uint64_t i);
     bool resident = false;
+    double profQueryTotal = 0, profGpuCall = 0;  // PM_HOST_PROFILE=1 prints them when the object is destroyed
+    uint64_t profQueryCalls = 0;
     pm_client *rclient = nullptr;
 
 private:

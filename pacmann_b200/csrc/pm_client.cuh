@@ -29,6 +29,7 @@ struct ClientPartDev {
     uint64_t *btags, *bparity, *ridx, *rval;   // [S*M], [S*M][E], [S*M], [S*M][E]
     uint64_t *hist;                            // [S]
     uint64_t *finished;                        // [1]
+    uint16_t *poff;                            // [S][P] offset index of the primary hints (nullptr if chunk_size > 65536)
 };
 
 __device__ __forceinline__ uint64_t mix64_dev(uint64_t seed, uint64_t ctr) {
@@ -59,10 +60,57 @@ __global__ void client_init_kernel(const ClientPartDev *parts, const uint32_t *p
     }
 }
 
+// Ordered list (array order = processing order) of the queries that belong to sub-PIR `part`, built by warp 0 with
+// coalesced reads; replaces a serial scan of the whole query array (one dependent global load per query).
+constexpr uint32_t CL_MAX_LIST = 2048;
+__device__ __forceinline__ uint32_t client_build_list(const uint32_t *query_words /* ClientQueryDev as 8 u32 */, uint32_t q,
+                                                       uint32_t part, uint32_t *s_list) {
+    __shared__ uint32_t s_count;
+    if (threadIdx.x < 32) {
+        uint32_t n = 0;
+        for (uint32_t base = 0; base < q; base += 32) {
+            const uint32_t t = base + threadIdx.x;
+            const bool mine = t < q && query_words[(uint64_t)t * 8] == part;
+            const uint32_t m = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                const uint32_t pos = n + __popc(m & ((1u << threadIdx.x) - 1));
+                if (pos < CL_MAX_LIST) s_list[pos] = t;
+            }
+            n += __popc(m);
+        }
+        if (threadIdx.x == 0) s_count = n;
+    }
+    __syncthreads();
+    return s_count;
+}
+
 struct RkOfPtr {
     const uint32_t *p;
     __device__ __forceinline__ uint32_t operator[](int i) const { return p[i]; }
 };
+
+// Offset index of the primary hints: poff[c][i] = PRF(tag_i, c) & (ChunkSize-1).  With it the online hint search
+// (pir.go:405-414, up to primaryHintNum AES evaluations per query) is a scan of one 2*P-byte column and the set
+// expansion (pir.go:424-427) a strided read of one row; only a promoted backup hint costs SetSize PRF evaluations
+// (its row is rewritten).  Filled once per preprocessing: one thread per hint, all chunks, coalesced 2-byte stores.
+__global__ void __launch_bounds__(256) client_fill_poff_kernel(const ClientPartDev *parts, const uint32_t *part_ids) {
+    extern __shared__ uint32_t smem[];
+    __shared__ uint32_t s_rk[44];
+    const ClientPartDev &D = parts[part_ids[blockIdx.y]];
+    aes_tab_fill<1>(smem, c_te0);
+    if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
+    __syncthreads();
+    if (!D.poff) return;
+    const AesTab<1> T{smem + (threadIdx.x & 31)};
+    const RkOfPtr R{s_rk};
+    const uint64_t P = D.n_primary;
+    const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
+        const PrfTagPart g = prf_tag_part(T, R, D.tags[i]);
+#pragma unroll 2
+        for (uint32_t c = 0; c < S; c++) D.poff[(uint64_t)c * P + i] = (uint16_t)(prf_low<1, 2>(T, R, g, c) & cmask);
+    }
+}
 
 struct ClientQueryDev {  // mirrors pm_client_query
     uint32_t part, kind;
@@ -82,8 +130,10 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     uint32_t *s_tab = smem;                           // replicated Te0
     uint32_t *s_rk = smem + aes_tab_words<1>();       // 44 round-key words
     uint32_t *s_offs = s_rk + 64;                     // [stride]
+    uint32_t *s_list = s_offs + stride;               // [CL_MAX_LIST]
     __shared__ uint32_t s_hit;
     __shared__ int s_status;
+    __shared__ uint64_t s_ingroup, s_newtag;
     const uint32_t part = blockIdx.x;
     const ClientPartDev &D = parts[part];
     aes_tab_fill<1>(s_tab, c_te0);
@@ -94,8 +144,9 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
     const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
 
-    for (uint32_t t = 0; t < q; t++) {
-        if (queries[t].part != part) continue;   // block-uniform
+    const uint32_t n_mine = client_build_list(reinterpret_cast<const uint32_t *>(queries), q, part, s_list);
+    for (uint32_t k = 0; k < n_mine; k++) {
+        const uint32_t t = s_list[k];
         const ClientQueryDev Q = queries[t];
         if (threadIdx.x == 0) {
             a_row0[t] = D.row0; a_nrows[t] = D.n_rows; a_chunk[t] = (uint32_t)C; a_set[t] = S;
@@ -109,9 +160,11 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         const uint64_t chunkId = Q.idx / C, offset = Q.idx % C;
         if (threadIdx.x == 0) {
             int st = 0;
-            if (*D.finished >= D.max_query_num) st = 2;             // pir.go:386-391
-            else if (D.hist[chunkId] >= M) st = 3;                  // pir.go:396-400
+            const uint64_t fin = *D.finished, h = D.hist[chunkId];
+            if (fin >= D.max_query_num) st = 2;                     // pir.go:386-391
+            else if (h >= M) st = 3;                                // pir.go:396-400
             s_status = st;
+            s_ingroup = h;
             s_hit = 0xffffffffu;
         }
         __syncthreads();
@@ -122,76 +175,122 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         }
         // first primary hint whose PRF lands on `offset` and is not programmed inside this chunk (pir.go:405-414)
         uint32_t hit = 0xffffffffu;
-        for (uint64_t base = 0; base < P; base += CL_THREADS) {
-            const uint64_t i = base + threadIdx.x;
-            if (i < P) {
-                const PrfTagPart g = prf_tag_part(T, R, D.tags[i]);
-                const uint32_t ho = prf_low<1, 4>(T, R, g, (uint32_t)chunkId) & cmask;
-                if (ho == (uint32_t)offset) {
-                    const uint64_t pp = D.pp[i];
+        if (D.poff) {  // scan one column of the offset index: no AES
+            const uint16_t *col = D.poff + chunkId * P;
+            for (uint64_t i = threadIdx.x; i < P; i += CL_THREADS) {
+                if ((uint32_t)__ldcg(col + i) == (uint32_t)offset) {
+                    const uint64_t pp = __ldcg(D.pp + i);
                     if (pp == kDefaultProgramPoint || pp / C != chunkId) atomicMin(&s_hit, (uint32_t)i);
                 }
             }
             __syncthreads();
             hit = s_hit;
             __syncthreads();
-            if (hit != 0xffffffffu) break;
+        } else {
+            for (uint64_t base = 0; base < P; base += CL_THREADS) {
+                const uint64_t i = base + threadIdx.x;
+                if (i < P) {
+                    const PrfTagPart g = prf_tag_part(T, R, D.tags[i]);
+                    const uint32_t ho = prf_low<1, 4>(T, R, g, (uint32_t)chunkId) & cmask;
+                    if (ho == (uint32_t)offset) {
+                        const uint64_t pp = D.pp[i];
+                        if (pp == kDefaultProgramPoint || pp / C != chunkId) atomicMin(&s_hit, (uint32_t)i);
+                    }
+                }
+                __syncthreads();
+                hit = s_hit;
+                __syncthreads();
+                if (hit != 0xffffffffu) break;
+            }
         }
         if (hit == 0xffffffffu) {  // pir.go:416-419
             if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, 4, 0}; a_set[t] = 0; }
             continue;
         }
         // expand the hit hint to a full set (pir.go:424-427)
-        {
+        if (D.poff) {
+            for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) s_offs[c] = __ldcg(D.poff + (uint64_t)c * P + hit);
+        } else {
             const PrfTagPart g = prf_tag_part(T, R, D.tags[hit]);
             for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) s_offs[c] = prf_low<1, 4>(T, R, g, c) & cmask;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint64_t pp = D.pp[hit];
+            const uint64_t inGroup = s_ingroup, slot = chunkId * M + inGroup;
+            const uint64_t pp = D.pp[hit], ridx = D.ridx[slot], btag = D.btags[slot], fin = *D.finished;  // independent loads
             if (pp != kDefaultProgramPoint) s_offs[pp / C] = (uint32_t)(pp & cmask);      // pir.go:430-433
-            const uint64_t inGroup = D.hist[chunkId], slot = chunkId * M + inGroup;
-            s_offs[chunkId] = (uint32_t)(D.ridx[slot] & cmask);                           // pir.go:436-439
+            s_offs[chunkId] = (uint32_t)(ridx & cmask);                                   // pir.go:436-439
             meta[t] = ClientMeta{hit, slot, 0, 0};
             // response-independent half of the refresh (pir.go:460-467)
-            D.tags[hit] = D.btags[slot];
+            D.tags[hit] = btag;
             D.pp[hit] = Q.idx;
-            *D.finished += 1;
-            D.hist[chunkId] += 1;
+            *D.finished = fin + 1;
+            D.hist[chunkId] = inGroup + 1;
+            s_newtag = btag;
         }
         __syncthreads();
+        if (D.poff) {  // the promoted backup hint takes over the slot: rewrite its row of the offset index
+            const PrfTagPart g = prf_tag_part(T, R, s_newtag);
+            for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS)
+                D.poff[(uint64_t)c * P + hit] = (uint16_t)(prf_low<1, 2>(T, R, g, c) & cmask);
+        }
         for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) offsets[(uint64_t)t * stride + c] = s_offs[c];
         __threadfence_block();
         __syncthreads();
     }
 }
 
+// Thread w owns word w of every entry, so the only cross-query dependency -- two queries of a part refreshing
+// the same hint slot -- is a read-after-write inside one thread: no barrier is needed, and the operands that do not
+// depend on earlier queries (answer, replacement value, backup parity) are fetched four queries ahead.
 __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev *parts, const ClientQueryDev *queries,
                                                             const ClientMeta *meta, uint32_t q, uint32_t E,
-                                                            const uint64_t *answers, uint64_t *out) {
+                                                            const uint64_t *__restrict__ answers, uint64_t *__restrict__ out) {
     const uint32_t part = blockIdx.x;
     const ClientPartDev &D = parts[part];
     const uint32_t E4 = E & ~3u;  // EntryXor granularity (xorSlices leaves the len%4 tail untouched)
-    for (uint32_t t = 0; t < q; t++) {
-        if (queries[t].part != part) continue;
-        const ClientMeta m = meta[t];
-        if (m.status != 0) {  // dummy or failed: zero entry (pir.go:356-360)
-            for (uint32_t w = threadIdx.x; w < E; w += blockDim.x) out[(uint64_t)t * E + w] = 0;
-            continue;
-        }
-        uint64_t *par = D.parity + m.hit * E;
-        const uint64_t *bpar = D.bparity + m.slot * E, *rv = D.rval + m.slot * E;
-        for (uint32_t w = threadIdx.x; w < E; w += blockDim.x) {
-            uint64_t r = answers[(uint64_t)t * E + w];
-            uint64_t np = bpar[w];                       // copy(primaryParity[hit], backupParity[slot])  pir.go:461
-            if (w < E4) {
-                r ^= rv[w] ^ par[w];                     // pir.go:451,453
-                np ^= r;                                 // pir.go:463
+    __shared__ uint32_t s_list[CL_MAX_LIST];
+    struct FinMeta { uint32_t hit, slot; int32_t status; };
+    __shared__ FinMeta s_meta[CL_MAX_LIST];
+    const uint32_t n_mine = client_build_list(reinterpret_cast<const uint32_t *>(queries), q, part, s_list);
+    for (uint32_t k = threadIdx.x; k < n_mine; k += blockDim.x) {
+        const ClientMeta m = meta[s_list[k]];
+        s_meta[k] = FinMeta{(uint32_t)m.hit, (uint32_t)m.slot, m.status};
+    }
+    __syncthreads();
+    const uint64_t *__restrict__ bparity = D.bparity, *__restrict__ rval = D.rval;
+    constexpr int B = 4;
+    for (uint32_t w = threadIdx.x; w < E; w += blockDim.x) {
+        for (uint32_t k0 = 0; k0 < n_mine; k0 += B) {
+            uint64_t a[B], rv[B], bp[B];
+#pragma unroll
+            for (int j = 0; j < B; j++) {
+                a[j] = rv[j] = bp[j] = 0;
+                if (k0 + j < n_mine && s_meta[k0 + j].status == 0) {
+                    const uint64_t slot = s_meta[k0 + j].slot;
+                    a[j] = answers[(uint64_t)s_list[k0 + j] * E + w];
+                    rv[j] = rval[slot * E + w];
+                    bp[j] = bparity[slot * E + w];
+                }
             }
-            par[w] = np;
-            out[(uint64_t)t * E + w] = r;
+#pragma unroll
+            for (int j = 0; j < B; j++) {
+                if (k0 + j >= n_mine) break;
+                const uint32_t t = s_list[k0 + j];
+                if (s_meta[k0 + j].status != 0) {  // dummy or failed: zero entry (pir.go:356-360)
+                    out[(uint64_t)t * E + w] = 0;
+                    continue;
+                }
+                uint64_t *par = D.parity + (uint64_t)s_meta[k0 + j].hit * E;
+                uint64_t r = a[j], np = bp[j];           // copy(primaryParity[hit], backupParity[slot])  pir.go:461
+                if (w < E4) {
+                    r ^= rv[j] ^ par[w];                 // pir.go:451,453
+                    np ^= r;                             // pir.go:463
+                }
+                par[w] = np;
+                out[(uint64_t)t * E + w] = r;
+            }
         }
-        __syncthreads();  // a later query of this part may hit the hint refreshed here
     }
 }
 
@@ -208,6 +307,11 @@ struct pm_client {
     void *arena;
     uint64_t max_set;
     std::mutex mu;
+    void *stage = nullptr;   // pinned host staging for results
+    size_t stage_bytes = 0;
+    cudaEvent_t ev[6] = {};
+    double prof_ms[5] = {};
+    uint64_t prof_calls = 0;
 };
 
 PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t n_parts, pm_client **out) {
@@ -225,7 +329,8 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
             return set_error(PM_ERR_ARG, "pm_client_create: bad geometry for part %llu", (unsigned long long)i);
         const uint64_t P = p.n_primary, B = p.set_size * p.backup_group;
         words += 2 * P + P * E + 2 * B + 2 * B * E + p.set_size + 2;
-        words = (words + 1) & ~1ull;
+        if (p.chunk_size <= 65536) words += (p.set_size * P * 2 + 7) / 8 + 2;   // offset index
+        words = (words + 3) & ~1ull;
         if (p.set_size > max_set) max_set = p.set_size;
     }
     pm_client *c = new (std::nothrow) pm_client();
@@ -255,6 +360,12 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
         D.hist = cur; cur += p.set_size;
         D.finished = cur; cur += 2;
         if ((uintptr_t)cur & 15) cur += 1;
+        D.poff = nullptr;
+        if (p.chunk_size <= 65536) {
+            D.poff = (uint16_t *)cur;
+            cur += (p.set_size * P * 2 + 7) / 8;
+            if ((uintptr_t)cur & 15) cur += 1;
+        }
     }
     *out = c;
     return PM_OK;
@@ -262,10 +373,15 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
 
 PM_EXPORT int pm_client_destroy(pm_client *c) {
     if (!c) return PM_OK;
+    if (c->prof_calls)
+        fprintf(stderr, "[client profile] %llu calls, us per call: h2d %.1f | prepare %.1f | answer %.1f | finish %.1f | d2h %.1f\n",
+                (unsigned long long)c->prof_calls, c->prof_ms[0] / c->prof_calls * 1e3, c->prof_ms[1] / c->prof_calls * 1e3,
+                c->prof_ms[2] / c->prof_calls * 1e3, c->prof_ms[3] / c->prof_calls * 1e3, c->prof_ms[4] / c->prof_calls * 1e3);
     if (pm::ensure_device(c->db->device) == PM_OK) {
         cudaStreamSynchronize(c->db->stream);
         cudaFree(c->arena);
         cudaFree(c->d_parts);
+        if (c->stage) cudaFreeHost(c->stage);
     }
     delete c;
     return PM_OK;
@@ -300,6 +416,15 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
     client_init_kernel<<<grid, 256, 0, db->stream>>>(c->d_parts, d_ids, d_seed, skip_prep);
     PM_CHECK_LAUNCH();
     count_launch();
+    {
+        uint64_t max_p = 0;
+        for (uint64_t a = 0; a < n; a++) max_p = std::max<uint64_t>(max_p, c->host_parts[part_ids[a]].n_primary);
+        dim3 fgrid((unsigned)std::max<uint64_t>(1, (max_p + 255) / 256), (unsigned)n);
+        PM_CUDA(cudaFuncSetAttribute(client_fill_poff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_tab_words<1>() * 4));
+        client_fill_poff_kernel<<<fgrid, 256, aes_tab_words<1>() * 4, db->stream>>>(c->d_parts, d_ids);
+        PM_CHECK_LAUNCH();
+        count_launch();
+    }
     std::vector<pm_hint_job> jobs;
     for (uint64_t a = 0; a < n; a++) {
         const ClientPartDev &D = c->host_parts[part_ids[a]];
@@ -333,8 +458,11 @@ PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries
     if (q == 0) return PM_OK;
     if (q > 1u << 20) return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: too many queries in one call");
     static_assert(sizeof(pm_client_query) == sizeof(ClientQueryDev), "pm_client_query layout");
+    std::vector<uint32_t> per_part(c->n_parts, 0);
     for (uint64_t t = 0; t < q; t++) {
         if (queries[t].part >= c->n_parts) return set_error(PM_ERR_ARG, "pm_client_query_batch: part id out of range");
+        if (++per_part[queries[t].part] > CL_MAX_LIST)
+            return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: more than %u queries for one sub-PIR in one call", CL_MAX_LIST);
         if (queries[t].kind == 1 && queries[t].idx >= c->host_parts[queries[t].part].n_rows)
             return set_error(PM_ERR_ARG, "pm_client_query_batch: idx %llu is out of range", (unsigned long long)queries[t].idx);  // pir.go:373-378
     }
@@ -346,29 +474,56 @@ PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries
     // staging: queries | meta | offsets | answer descriptors   and   answers | out
     const size_t b_q = q * sizeof(ClientQueryDev), b_meta = q * sizeof(ClientMeta), b_off = q * stride * 4, b_desc = q * 24;
     void *d_in = nullptr, *d_out = nullptr;
-    if ((rc = scratch(db, 1, b_q + b_meta + b_off + b_desc + 64, &d_in))) return rc;
-    if ((rc = scratch(db, 0, 2 * q * E * 8, &d_out))) return rc;
+    if ((rc = scratch(db, 1, b_q + b_off + b_desc + 64, &d_in))) return rc;
+    if ((rc = scratch(db, 0, 2 * q * E * 8 + b_meta, &d_out))) return rc;
     ClientQueryDev *d_q = (ClientQueryDev *)d_in;
-    ClientMeta *d_meta = (ClientMeta *)((char *)d_in + b_q);
-    uint32_t *d_off = (uint32_t *)((char *)d_meta + b_meta);
+    uint32_t *d_off = (uint32_t *)((char *)d_in + b_q);
     uint64_t *d_row0 = (uint64_t *)((char *)d_off + b_off), *d_nrows = d_row0 + q;
     uint32_t *d_chunk = (uint32_t *)(d_nrows + q), *d_set = d_chunk + q;
     uint64_t *d_ans = (uint64_t *)d_out, *d_res = d_ans + q * E;
+    ClientMeta *d_meta = (ClientMeta *)(d_res + q * E);  // results and their status records leave in ONE copy
+    // pinned staging (grow-only): the D2H lands at PCIe speed instead of going through the pageable path
+    const size_t b_back = q * E * 8 + b_meta;
+    if (c->stage_bytes < b_back) {
+        if (c->stage) cudaFreeHost(c->stage);
+        c->stage = nullptr;
+        c->stage_bytes = 0;
+        PM_CUDA(cudaHostAlloc(&c->stage, b_back + b_back / 2, cudaHostAllocDefault));
+        c->stage_bytes = b_back + b_back / 2;
+    }
+    // PM_CLIENT_PROFILE=1: CUDA-event breakdown of the call (H2D | prepare | answer | finish | D2H), printed at destroy
+    static const bool prof = getenv("PM_CLIENT_PROFILE") != nullptr;
+    if (prof && !c->ev[0]) for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
+    auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], db->stream); };
+    mark(0);
     PM_CUDA(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, db->stream));
-    const size_t smem = (aes_tab_words<1>() + 64 + stride) * 4;
+    mark(1);
+    const size_t smem = (aes_tab_words<1>() + 64 + stride + CL_MAX_LIST) * 4;
     PM_CUDA(cudaFuncSetAttribute(client_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     client_prepare_kernel<<<(unsigned)c->n_parts, CL_THREADS, smem, db->stream>>>(c->d_parts, d_q, (uint32_t)q, (uint32_t)stride, d_off,
                                                                                   d_meta, d_row0, d_nrows, d_chunk, d_set);
     PM_CHECK_LAUNCH();
     count_launch();
+    mark(2);
     if ((rc = answer_enqueue(db, d_row0, d_nrows, d_chunk, d_set, d_off, stride, q, (uint32_t)stride, d_ans, db->stream))) return rc;
+    mark(3);
     client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, db->stream>>>(c->d_parts, d_q, d_meta, (uint32_t)q, (uint32_t)E, d_ans, d_res);
     PM_CHECK_LAUNCH();
     count_launch();
-    PM_CUDA(cudaMemcpyAsync(out, d_res, q * E * 8, cudaMemcpyDeviceToHost, db->stream));
-    std::vector<ClientMeta> meta(q);
-    PM_CUDA(cudaMemcpyAsync(meta.data(), d_meta, b_meta, cudaMemcpyDeviceToHost, db->stream));
+    mark(4);
+    PM_CUDA(cudaMemcpyAsync(c->stage, d_res, b_back, cudaMemcpyDeviceToHost, db->stream));
+    mark(5);
     PM_CUDA(cudaStreamSynchronize(db->stream));
+    memcpy(out, c->stage, q * E * 8);
+    const ClientMeta *meta = (const ClientMeta *)((const char *)c->stage + q * E * 8);
+    if (prof) {
+        for (int i = 0; i < 5; i++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+            c->prof_ms[i] += ms;
+        }
+        c->prof_calls++;
+    }
     for (uint64_t t = 0; t < q; t++) status[t] = meta[t].status < 0 ? 0 : meta[t].status;
     return PM_OK;
 }

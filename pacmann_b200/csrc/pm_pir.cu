@@ -103,7 +103,6 @@ __global__ void __launch_bounds__(256) prf_batch_kernel(const __grid_constant__ 
 // from HBM once and re-hit in L2 by the other ~H'/ChunkSize hints that select rows of it.
 constexpr int HG_THREADS = 512;
 constexpr int HG_MAX_JOBS = 16;
-constexpr uint32_t ROW_INVALID = 0xffffffffu;
 
 struct HintJobDev {
     uint32_t rk[44];
