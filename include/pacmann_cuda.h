@@ -154,6 +154,10 @@ int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint64_t n, con
  * exceeded, 3 too many queries in the chunk, 4 no hit hint (pir.go:386-419).  The caller keeps the local cache
  * (pir.go:381-383) and therefore never sends an index twice between two preprocessings. */
 int pm_client_query_batch(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status);
+/* same, and dist_out[i] = L2Dist(first `dim` fp32 of out[i], query_vec) computed on the device right behind the
+ * answers (the per-step L2Dist call site of SearchKNN, graphann/search.go:204), saving a second round trip */
+int pm_client_query_batch_l2(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
+                             const float *query_vec, uint64_t dim, float *dist_out);
 /* copy one table of one part to the host (tests / checkpointing): 0 primaryShortTag, 1 primaryParity,
  * 2 primaryProgramPoint, 3 replacementIdx, 4 replacementVal, 5 backupShortTag, 6 backupParity, 7 QueryHistogram,
  * 8 FinishedQueryNum */

@@ -89,9 +89,22 @@ void PIRGraphInfo::Preprocess() {
     else PIR->Preprocessing();
 }
 
+int GetGraphInfo::GetVertexInfoWithDist(const std::vector<int64_t> &ids, const float *, std::vector<Vertex> *out,
+                                        std::vector<float> *dists) {
+    dists->assign(ids.size(), std::nanf(""));
+    return GetVertexInfo(ids, out);
+}
+
 int PIRGraphInfo::GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) {
+    std::vector<float> unused;
+    return GetVertexInfoWithDist(ids, nullptr, out, &unused);
+}
+
+int PIRGraphInfo::GetVertexInfoWithDist(const std::vector<int64_t> &ids, const float *query, std::vector<Vertex> *out,
+                                        std::vector<float> *dists) {
     totalQueryNum += (int64_t)ids.size();
     out->resize(ids.size());
+    dists->assign(ids.size(), std::nanf(""));
     if (NonPrivateMode) {
         for (size_t i = 0; i < ids.size(); i++) {
             Vertex &v = (*out)[i];
@@ -101,13 +114,14 @@ int PIRGraphInfo::GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Ver
         }
         return 0;
     }
-    std::vector<uint64_t> indices(ids.begin(), ids.end());
-    std::vector<std::vector<uint64_t>> responses;
-    if (PIR->Query(indices, &responses) != 0) return -1;
+    const uint64_t E = DBEntryByteNum / 8;
+    wsIdx.assign(ids.begin(), ids.end());
+    wsResp.resize(ids.size() * E);
+    if (PIR->QueryFlat(wsIdx.data(), wsIdx.size(), wsResp.data(), query, (uint64_t)Dim, query ? dists->data() : nullptr) != 0) return -1;
     for (size_t i = 0; i < ids.size(); i++) {
         Vertex &v = (*out)[i];
         v.Id = ids[i];
-        Entry2VectorAndNeighbors(Dim, M, responses[i].data(), &v.Vector, &v.Neighbors);
+        Entry2VectorAndNeighbors(Dim, M, &wsResp[i * E], &v.Vector, &v.Neighbors);
         bool correctQ = true;
         for (int64_t j = 0; j < M; j++)
             if (v.Neighbors[j] != (int64_t)(uint32_t)graph[ids[i] * M + j]) { correctQ = false; break; }
@@ -209,6 +223,7 @@ int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t max
     }
 
     std::vector<Vertex> queryResults;
+    std::vector<float> srcDists;
     for (int64_t step = 0; step < maxStep; step++) {  // search.go:150-208
         std::vector<int64_t> batchQ;
         batchQ.reserve((size_t)(parallel * m));
@@ -221,7 +236,7 @@ int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t max
                 batchQ.insert(batchQ.end(), v.Neighbors.begin(), v.Neighbors.end());
             }
         }
-        if (Graph->GetVertexInfo(batchQ, &queryResults) != 0) return -1;
+        if (Graph->GetVertexInfoWithDist(batchQ, benchmarking ? nullptr : queryVector, &queryResults, &srcDists) != 0) return -1;
         if (benchmarking) continue;
         // newly discovered vertices of this step: one distance launch for all of them
         std::vector<size_t> fresh;
@@ -235,9 +250,21 @@ int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t max
             for (int64_t nb : v.Neighbors) if (nb != 0) { ok = true; break; }
             if (ok) fresh.push_back(i);
         }
+        // distances of the newly discovered vertices (search.go:204): taken from the vertex source when it computed them
+        // behind the fetch, one extra launch only for the ones it did not (e.g. entries served from the local cache)
+        dists.assign(fresh.size(), 0.f);
         std::vector<const float *> ptrs;
-        for (size_t i : fresh) ptrs.push_back(queryResults[i].Vector.data());
-        dist_many(ptrs, dim, queryVector, device, &dists);
+        std::vector<size_t> missing;
+        for (size_t t = 0; t < fresh.size(); t++) {
+            const float d = srcDists[fresh[t]];
+            if (std::isnan(d)) { missing.push_back(t); ptrs.push_back(queryResults[fresh[t]].Vector.data()); }
+            else dists[t] = d;
+        }
+        if (!missing.empty()) {
+            std::vector<float> md;
+            dist_many(ptrs, dim, queryVector, device, &md);
+            for (size_t k = 0; k < missing.size(); k++) dists[missing[k]] = md[k];
+        }
         for (size_t t = 0; t < fresh.size(); t++) {
             const Vertex &v = queryResults[fresh[t]];
             knownVertices[v.Id] = v;

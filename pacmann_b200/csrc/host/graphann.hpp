@@ -25,6 +25,10 @@ public:
     virtual void GetMetadata(int64_t *n, int64_t *dim, int64_t *m) const = 0;
     virtual int GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) = 0;
     virtual int GetStartVertex(std::vector<Vertex> *out) = 0;
+    // GetVertexInfo plus, where the source can provide it for free, dists[i] = L2Dist(out[i].Vector, query);
+    // NaN = not provided (the caller evaluates L2Dist itself).  Default: no distances.
+    virtual int GetVertexInfoWithDist(const std::vector<int64_t> &ids, const float *query, std::vector<Vertex> *out,
+                                      std::vector<float> *dists);
     virtual int Device() const { return 0; }
 };
 
@@ -53,6 +57,8 @@ public:
     void Preprocess() override;                                                        // :355-412
     void GetMetadata(int64_t *n, int64_t *dim, int64_t *m) const override { *n = N; *dim = Dim; *m = M; }
     int GetVertexInfo(const std::vector<int64_t> &ids, std::vector<Vertex> *out) override;  // :441-506
+    int GetVertexInfoWithDist(const std::vector<int64_t> &ids, const float *query, std::vector<Vertex> *out,
+                              std::vector<float> *dists) override;
     int GetStartVertex(std::vector<Vertex> *out) override;                             // :508-531
     int Device() const override { return device; }
     int64_t N, Dim, M;
@@ -64,6 +70,7 @@ public:
     std::vector<uint64_t> rawDB;
     pianopir::SimpleBatchPianoPIR *PIR = nullptr;
     int64_t totalQueryNum = 0, succQueryNum = 0;
+    std::vector<uint64_t> wsIdx, wsResp;  // per-call scratch
     uint64_t seed;
     int device;
 };

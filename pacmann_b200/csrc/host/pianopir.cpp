@@ -648,60 +648,97 @@ void SimpleBatchPianoPIR::SyncTablesFromDevice(uint64_t i) {
 }
 
 int SimpleBatchPianoPIR::QueryResident(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret) {
+    const uint64_t E = config.DBEntrySize;
+    std::vector<uint64_t> flat(idx.size() * E);
+    int rc = QueryFlat(idx.data(), idx.size(), flat.data(), nullptr, 0, nullptr);
+    if (rc != 0) return rc;
+    ret->resize(idx.size());
+    for (size_t i = 0; i < idx.size(); i++) (*ret)[i].assign(flat.begin() + i * E, flat.begin() + (i + 1) * E);
+    return 0;
+}
+
+// Flat form of Query for the resident client: out is [n][DBEntrySize].  With query_vec != nullptr it also returns
+// dists[i] = L2Dist(vector part of out[i], query_vec) from the same GPU call (NaN where the entry came from the
+// local cache and no distance was computed).  Scratch vectors are members: no allocation on the steady-state path.
+int SimpleBatchPianoPIR::QueryFlat(const uint64_t *idx, size_t n, uint64_t *out, const float *query_vec, uint64_t dim, float *dists) {
+    const uint64_t PN = config.PartitionNum, PS = config.PartitionSize, E = config.DBEntrySize;
+    const float kNaN = std::nanf("");
+    if (!resident) {
+        std::vector<uint64_t> v(idx, idx + n);
+        std::vector<std::vector<uint64_t>> r;
+        int rc = Query(v, &r);
+        if (rc != 0) return rc;
+        for (size_t i = 0; i < n; i++) memcpy(out + i * E, r[i].data(), E * 8);
+        if (dists) for (size_t i = 0; i < n; i++) dists[i] = kNaN;
+        return 0;
+    }
     struct Timer {
         double &acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
         ~Timer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
     } timer{profQueryTotal};
     profQueryCalls += 1;
-    const uint64_t PN = config.PartitionNum, PS = config.PartitionSize, E = config.DBEntrySize;
-    const uint64_t queryNumToMake = idx.size() / PN;
-    std::vector<std::vector<uint64_t>> partitionQueries(PN);
-    for (uint64_t v : idx) {
-        uint64_t pi = v / PS;
+    const uint64_t queryNumToMake = n / PN;
+    auto &lists = wsLists;
+    lists.resize(PN);
+    for (auto &l : lists) l.clear();
+    for (size_t i = 0; i < n; i++) {
+        uint64_t pi = idx[i] / PS;
         if (pi >= PN) return -1;
-        partitionQueries[pi].push_back(v);
+        lists[pi].push_back(idx[i]);
     }
-    struct Pend { uint64_t part, global, local; int kind; /* 0 dummy, 1 real, 2 cached */ int64_t qpos; };
-    std::unordered_map<uint64_t, std::vector<uint64_t>> responses;
-    std::vector<Pend> pend;
-    std::vector<pm_client_query> ql;
+    struct Resp { const uint64_t *entry; float dist; };
+    std::unordered_map<uint64_t, Resp> responses;
+    responses.reserve(n * 2);
+    auto &pend = wsPend;
+    auto &ql = wsQueries;
+    pend.clear();
+    ql.clear();
+    wsOut.resize(n * E);
+    wsStatus.resize(n);
+    wsDist.resize(n);
+    wsZero.assign(E, 0);
     std::vector<uint64_t> pendingReal(PN, 0);
+    size_t qbase = 0, pbase = 0;   // queries / pending records already settled by an earlier flush of this call
 
     auto flush = [&]() {
-        std::vector<uint64_t> out(ql.size() * E);
-        std::vector<int32_t> status(ql.size());
-        if (!ql.empty()) {
+        const size_t cnt = ql.size() - qbase;
+        if (cnt) {
             auto tg = std::chrono::steady_clock::now();
-            check(pm_client_query_batch(rclient, ql.data(), ql.size(), out.data(), status.data()), "pm_client_query_batch");
+            if (query_vec)
+                check(pm_client_query_batch_l2(rclient, ql.data() + qbase, cnt, wsOut.data() + qbase * E, wsStatus.data() + qbase,
+                                               query_vec, dim, wsDist.data() + qbase), "pm_client_query_batch_l2");
+            else
+                check(pm_client_query_batch(rclient, ql.data() + qbase, cnt, wsOut.data() + qbase * E, wsStatus.data() + qbase),
+                      "pm_client_query_batch");
             profGpuCall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
             serverLaunches += 1;
         }
-        std::vector<uint64_t> zero(E, 0);
-        for (const Pend &pd : pend) {
+        for (size_t a = pbase; a < pend.size(); a++) {
+            const PendRec &pd = pend[a];
             PianoPIRClient &c = subPIR[pd.part]->client;
             if (pd.kind == 0) { serverQueries += 1; continue; }
             if (pd.kind == 2) {  // served from the local cache (pir.go:381-383); an earlier failure of the same index repeats as zeros
                 auto it = c.localCache.find(pd.local);
-                responses[pd.global] = it != c.localCache.end() ? it->second : zero;
+                responses[pd.global] = Resp{it != c.localCache.end() ? it->second.data() : wsZero.data(), kNaN};
                 continue;
             }
-            std::vector<uint64_t> r(out.begin() + pd.qpos * (int64_t)E, out.begin() + (pd.qpos + 1) * (int64_t)E);
-            if (status[pd.qpos] == 0) {
+            const uint64_t *r = wsOut.data() + (size_t)pd.qpos * E;
+            if (wsStatus[pd.qpos] == 0) {
                 serverQueries += 1;
                 c.FinishedQueryNum += 1;
-                c.localCache[pd.local] = r;
+                c.localCache[pd.local].assign(r, r + E);
             }
             for (size_t k = 0; k < c.pendingCached.size(); k++)
                 if (c.pendingCached[k] == pd.local) { c.pendingCached.erase(c.pendingCached.begin() + (long)k); break; }
-            responses[pd.global] = r;
+            responses[pd.global] = Resp{r, query_vec ? wsDist[pd.qpos] : kNaN};
         }
-        pend.clear();
-        ql.clear();
+        qbase = ql.size();
+        pbase = pend.size();
         std::fill(pendingReal.begin(), pendingReal.end(), 0);
     };
 
     for (uint64_t i = 0; i < PN; i++) {
-        auto &lst = partitionQueries[i];
+        auto &lst = lists[i];
         while (lst.size() < queryNumToMake) lst.push_back(DefaultValue);
         PianoPIR *p = subPIR[i];
         PianoPIRClient &c = p->client;
@@ -714,33 +751,37 @@ int SimpleBatchPianoPIR::QueryResident(const std::vector<uint64_t> &idx, std::ve
             if (lst[j] == DefaultValue) {
                 ql.push_back(pm_client_query{(uint32_t)i, 0, 0, c.dummySeed, c.dummyCtr});
                 c.dummyCtr += p->config.SetSize;
-                pend.push_back(Pend{i, DefaultValue, 0, 0, (int64_t)ql.size() - 1});
+                pend.push_back(PendRec{i, DefaultValue, 0, 0, (int64_t)ql.size() - 1});
                 continue;
             }
             const uint64_t local = lst[j] - i * PS;
             bool cached = c.localCache.count(local) != 0;
             for (size_t k = 0; !cached && k < c.pendingCached.size(); k++) cached = c.pendingCached[k] == local;
             if (cached) {
-                pend.push_back(Pend{i, lst[j], local, 2, -1});
+                pend.push_back(PendRec{i, lst[j], local, 2, -1});
             } else {
                 ql.push_back(pm_client_query{(uint32_t)i, 1, local, 0, 0});
                 c.pendingCached.push_back(local);
                 pendingReal[i] += 1;
-                pend.push_back(Pend{i, lst[j], local, 1, (int64_t)ql.size() - 1});
+                pend.push_back(PendRec{i, lst[j], local, 1, (int64_t)ql.size() - 1});
             }
         }
     }
     flush();
-    ret->resize(idx.size());
-    for (size_t i = 0; i < idx.size(); i++) {
+    for (size_t i = 0; i < n; i++) {
         auto it = responses.find(idx[i]);
-        if (it != responses.end()) (*ret)[i] = it->second;
-        else (*ret)[i].assign(E, 0);
+        if (it != responses.end()) {
+            memcpy(out + i * E, it->second.entry, E * 8);
+            if (dists) dists[i] = it->second.dist;
+        } else {
+            memset(out + i * E, 0, E * 8);
+            if (dists) dists[i] = kNaN;
+        }
     }
     if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) {
         Preprocessing();
     } else {
-        FinishedBatchNum += idx.size() / config.BatchSize;
+        FinishedBatchNum += n / config.BatchSize;
         QueriesMadeInPartition += queryNumToMake;
     }
     return 0;

@@ -159,12 +159,20 @@ public:
     // request (SyncTablesFromDevice), counters and the local cache stay on the host.
     void EnableResidentClient();
     void SyncTablesFromDevice(uint64_t i);
+    int QueryFlat(const uint64_t *idx, size_t n, uint64_t *out, const float *query_vec, uint64_t dim, float *dists);
     bool resident = false;
     double profQueryTotal = 0, profGpuCall = 0;  // PM_HOST_PROFILE=1 prints them when the object is destroyed
     uint64_t profQueryCalls = 0;
     pm_client *rclient = nullptr;
 
 private:
+    struct PendRec { uint64_t part, global, local; int kind; /* 0 dummy, 1 real, 2 cached */ int64_t qpos; };
+    std::vector<std::vector<uint64_t>> wsLists;   // per-call scratch, kept to avoid reallocation
+    std::vector<PendRec> wsPend;
+    std::vector<pm_client_query> wsQueries;
+    std::vector<uint64_t> wsOut, wsZero;
+    std::vector<int32_t> wsStatus;
+    std::vector<float> wsDist;
     void PreprocessResident(const std::vector<uint32_t> &ids, bool skipPrep);
     int QueryResident(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret);
     void Flush(std::vector<PendingQuery> &pend, std::vector<uint64_t> &pend_part, std::vector<uint64_t> &pend_global,

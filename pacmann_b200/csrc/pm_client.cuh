@@ -122,6 +122,10 @@ struct ClientMeta {
     int32_t pad;
 };
 
+// Per query the critical path is two global round trips and one PRF: phase A loads the query's column of the offset
+// index together with the budget counters, phase B the hit hint's row together with the scalars thread 0 needs,
+// phase C rewrites the promoted backup hint's row.  Program points are mirrored in shared memory (u32) so the
+// not-programmed-in-this-chunk test needs no dependent load.
 __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const ClientPartDev *parts, const ClientQueryDev *queries,
                                                                     uint32_t q, uint32_t stride, uint32_t *offsets,
                                                                     ClientMeta *meta, uint64_t *a_row0, uint64_t *a_nrows,
@@ -131,20 +135,25 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     uint32_t *s_rk = smem + aes_tab_words<1>();       // 44 round-key words
     uint32_t *s_offs = s_rk + 64;                     // [stride]
     uint32_t *s_list = s_offs + stride;               // [CL_MAX_LIST]
+    uint32_t *s_pp = s_list + CL_MAX_LIST;            // [P] program points (only when the offset index is in use)
     __shared__ uint32_t s_hit;
     __shared__ int s_status;
-    __shared__ uint64_t s_ingroup, s_newtag;
+    __shared__ uint64_t s_ingroup, s_newtag, s_fin;
     const uint32_t part = blockIdx.x;
     const ClientPartDev &D = parts[part];
+    const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
+    const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
+    const uint32_t n_mine = client_build_list(reinterpret_cast<const uint32_t *>(queries), q, part, s_list);
+    if (n_mine == 0) return;
     aes_tab_fill<1>(s_tab, c_te0);
     if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
+    const bool indexed = D.poff != nullptr;
+    if (indexed)
+        for (uint64_t i = threadIdx.x; i < P; i += CL_THREADS) s_pp[i] = (uint32_t)D.pp[i];   // values < 2^31 or 0x7fffffff
     __syncthreads();
     const AesTab<1> T{s_tab + (threadIdx.x & 31)};
     const RkOfPtr R{s_rk};
-    const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
-    const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
 
-    const uint32_t n_mine = client_build_list(reinterpret_cast<const uint32_t *>(queries), q, part, s_list);
     for (uint32_t k = 0; k < n_mine; k++) {
         const uint32_t t = s_list[k];
         const ClientQueryDev Q = queries[t];
@@ -158,34 +167,65 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             continue;
         }
         const uint64_t chunkId = Q.idx / C, offset = Q.idx % C;
-        if (threadIdx.x == 0) {
-            int st = 0;
-            const uint64_t fin = *D.finished, h = D.hist[chunkId];
-            if (fin >= D.max_query_num) st = 2;                     // pir.go:386-391
-            else if (h >= M) st = 3;                                // pir.go:396-400
-            s_status = st;
-            s_ingroup = h;
-            s_hit = 0xffffffffu;
-        }
+        // ---- phase A: budget counters + first-match search (pir.go:386-414) ----
+        if (threadIdx.x == 0) s_hit = 0xffffffffu;
         __syncthreads();
-        if (s_status != 0) {
-            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, s_status, 0}; a_set[t] = 0; }
-            __syncthreads();
-            continue;
+        if (threadIdx.x == 32) {   // a lane of another warp than the one that is busiest in the scan tail
+            const uint64_t fin = *D.finished, h = D.hist[chunkId];
+            s_status = fin >= D.max_query_num ? 2 : (h >= M ? 3 : 0);   // pir.go:386-391, 396-400
+            s_ingroup = h;
+            s_fin = fin;
         }
-        // first primary hint whose PRF lands on `offset` and is not programmed inside this chunk (pir.go:405-414)
         uint32_t hit = 0xffffffffu;
-        if (D.poff) {  // scan one column of the offset index: no AES
+        if (indexed) {  // scan one column of the offset index: no AES
+            // all loads of the column are issued before the first compare (a compare-and-branch per load would
+            // serialise one L2 round trip per element): 16-byte vectors of 8 offsets, up to 4 per thread per pass
             const uint16_t *col = D.poff + chunkId * P;
-            for (uint64_t i = threadIdx.x; i < P; i += CL_THREADS) {
-                if ((uint32_t)__ldcg(col + i) == (uint32_t)offset) {
-                    const uint64_t pp = __ldcg(D.pp + i);
-                    if (pp == kDefaultProgramPoint || pp / C != chunkId) atomicMin(&s_hit, (uint32_t)i);
+            auto consider = [&](uint64_t i, uint32_t v) {
+                if (v == (uint32_t)offset) {
+                    const uint32_t pp = s_pp[i];
+                    if (pp == (uint32_t)kDefaultProgramPoint || pp / C != chunkId) atomicMin(&s_hit, (uint32_t)i);
+                }
+            };
+            if ((P & 7) == 0) {
+                const uint4 *col4 = reinterpret_cast<const uint4 *>(col);
+                const uint64_t nv = P / 8;
+                for (uint64_t v0 = 0; v0 < nv; v0 += 4 * CL_THREADS) {
+                    uint4 w[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint64_t vi = v0 + u * CL_THREADS + threadIdx.x;
+                        w[u] = vi < nv ? __ldcg(col4 + vi) : make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint64_t vi = v0 + u * CL_THREADS + threadIdx.x;
+                        if (vi >= nv) continue;
+                        const uint32_t x[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            consider(vi * 8 + 2 * e, x[e] & 0xffffu);
+                            consider(vi * 8 + 2 * e + 1, x[e] >> 16);
+                        }
+                    }
+                }
+            } else {
+                for (uint64_t i0 = 0; i0 < P; i0 += 8 * CL_THREADS) {
+                    uint32_t v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const uint64_t i = i0 + u * CL_THREADS + threadIdx.x;
+                        v[u] = i < P ? (uint32_t)__ldcg(col + i) : 0xffffffffu;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const uint64_t i = i0 + u * CL_THREADS + threadIdx.x;
+                        if (i < P) consider(i, v[u]);
+                    }
                 }
             }
             __syncthreads();
             hit = s_hit;
-            __syncthreads();
         } else {
             for (uint64_t base = 0; base < P; base += CL_THREADS) {
                 const uint64_t i = base + threadIdx.x;
@@ -202,13 +242,23 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
                 __syncthreads();
                 if (hit != 0xffffffffu) break;
             }
+            __syncthreads();
         }
-        if (hit == 0xffffffffu) {  // pir.go:416-419
-            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, 4, 0}; a_set[t] = 0; }
+        const int status = s_status != 0 ? s_status : (hit == 0xffffffffu ? 4 : 0);   // pir.go:416-419
+        if (status != 0) {
+            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, status, 0}; a_set[t] = 0; }
+            __syncthreads();
             continue;
         }
-        // expand the hit hint to a full set (pir.go:424-427)
-        if (D.poff) {
+        // ---- phase B: expand the hit hint to a full set (pir.go:424-427) + the scalars of the refresh ----
+        const uint64_t inGroup = s_ingroup, slot = chunkId * M + inGroup;
+        uint64_t ridx = 0, btag = 0, pp_hit = 0;
+        if (threadIdx.x == 0) {
+            ridx = D.ridx[slot];
+            btag = D.btags[slot];
+            pp_hit = indexed ? (uint64_t)s_pp[hit] : D.pp[hit];
+        }
+        if (indexed) {
             for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) s_offs[c] = __ldcg(D.poff + (uint64_t)c * P + hit);
         } else {
             const PrfTagPart g = prf_tag_part(T, R, D.tags[hit]);
@@ -216,25 +266,25 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint64_t inGroup = s_ingroup, slot = chunkId * M + inGroup;
-            const uint64_t pp = D.pp[hit], ridx = D.ridx[slot], btag = D.btags[slot], fin = *D.finished;  // independent loads
-            if (pp != kDefaultProgramPoint) s_offs[pp / C] = (uint32_t)(pp & cmask);      // pir.go:430-433
-            s_offs[chunkId] = (uint32_t)(ridx & cmask);                                   // pir.go:436-439
+            if (pp_hit != kDefaultProgramPoint) s_offs[pp_hit / C] = (uint32_t)(pp_hit & cmask);   // pir.go:430-433
+            s_offs[chunkId] = (uint32_t)(ridx & cmask);                                            // pir.go:436-439
             meta[t] = ClientMeta{hit, slot, 0, 0};
             // response-independent half of the refresh (pir.go:460-467)
             D.tags[hit] = btag;
             D.pp[hit] = Q.idx;
-            *D.finished = fin + 1;
+            if (indexed) s_pp[hit] = (uint32_t)Q.idx;
+            *D.finished = s_fin + 1;
             D.hist[chunkId] = inGroup + 1;
             s_newtag = btag;
         }
         __syncthreads();
-        if (D.poff) {  // the promoted backup hint takes over the slot: rewrite its row of the offset index
+        // ---- phase C: hand the offsets to the server kernel; the promoted backup hint takes over the slot ----
+        for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) offsets[(uint64_t)t * stride + c] = s_offs[c];
+        if (indexed) {
             const PrfTagPart g = prf_tag_part(T, R, s_newtag);
             for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS)
                 D.poff[(uint64_t)c * P + hit] = (uint16_t)(prf_low<1, 2>(T, R, g, c) & cmask);
         }
-        for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) offsets[(uint64_t)t * stride + c] = s_offs[c];
         __threadfence_block();
         __syncthreads();
     }
@@ -452,7 +502,19 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
     return PM_OK;
 }
 
+static int client_query_impl(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
+                             const float *query_vec, uint64_t dim, float *dist_out);
 PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status) {
+    return client_query_impl(c, queries, q, out, status, nullptr, 0, nullptr);
+}
+PM_EXPORT int pm_client_query_batch_l2(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
+                                       const float *query_vec, uint64_t dim, float *dist_out) {
+    if (!query_vec || !dist_out || dim == 0) return pm::set_error(PM_ERR_ARG, "pm_client_query_batch_l2: null pointer");
+    if (c && dim * 4 > c->E * 8) return pm::set_error(PM_ERR_ARG, "pm_client_query_batch_l2: dim does not fit in an entry");
+    return client_query_impl(c, queries, q, out, status, query_vec, dim, dist_out);
+}
+static int client_query_impl(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
+                             const float *query_vec, uint64_t dim, float *dist_out) {
     using namespace pm;
     if (!c || (q && (!queries || !out || !status))) return set_error(PM_ERR_ARG, "pm_client_query_batch: null pointer");
     if (q == 0) return PM_OK;
@@ -474,8 +536,9 @@ PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries
     // staging: queries | meta | offsets | answer descriptors   and   answers | out
     const size_t b_q = q * sizeof(ClientQueryDev), b_meta = q * sizeof(ClientMeta), b_off = q * stride * 4, b_desc = q * 24;
     void *d_in = nullptr, *d_out = nullptr;
-    if ((rc = scratch(db, 1, b_q + b_off + b_desc + 64, &d_in))) return rc;
-    if ((rc = scratch(db, 0, 2 * q * E * 8 + b_meta, &d_out))) return rc;
+    const size_t b_qv = (dim * 4 + 15) & ~15ull, b_dist = dist_out ? q * 4 : 0;
+    if ((rc = scratch(db, 1, b_q + b_off + b_desc + b_qv + 64, &d_in))) return rc;
+    if ((rc = scratch(db, 0, 2 * q * E * 8 + b_meta + b_dist, &d_out))) return rc;
     ClientQueryDev *d_q = (ClientQueryDev *)d_in;
     uint32_t *d_off = (uint32_t *)((char *)d_in + b_q);
     uint64_t *d_row0 = (uint64_t *)((char *)d_off + b_off), *d_nrows = d_row0 + q;
@@ -483,7 +546,8 @@ PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries
     uint64_t *d_ans = (uint64_t *)d_out, *d_res = d_ans + q * E;
     ClientMeta *d_meta = (ClientMeta *)(d_res + q * E);  // results and their status records leave in ONE copy
     // pinned staging (grow-only): the D2H lands at PCIe speed instead of going through the pageable path
-    const size_t b_back = q * E * 8 + b_meta;
+    float *d_qv = (float *)((((uintptr_t)(d_set + q)) + 15) & ~(uintptr_t)15), *d_dist = (float *)(d_meta + q);
+    const size_t b_back = q * E * 8 + b_meta + b_dist;
     if (c->stage_bytes < b_back) {
         if (c->stage) cudaFreeHost(c->stage);
         c->stage = nullptr;
@@ -498,7 +562,10 @@ PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries
     mark(0);
     PM_CUDA(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, db->stream));
     mark(1);
-    const size_t smem = (aes_tab_words<1>() + 64 + stride + CL_MAX_LIST) * 4;
+    uint64_t max_p = 0;
+    for (uint64_t i = 0; i < c->n_parts; i++) if (c->host_parts[i].poff) max_p = std::max<uint64_t>(max_p, c->host_parts[i].n_primary);
+    const size_t smem = (aes_tab_words<1>() + 64 + stride + CL_MAX_LIST + max_p) * 4;
+    if (smem > 200 * 1024) return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: primaryHintNum too large for the shared-memory mirror");
     PM_CUDA(cudaFuncSetAttribute(client_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     client_prepare_kernel<<<(unsigned)c->n_parts, CL_THREADS, smem, db->stream>>>(c->d_parts, d_q, (uint32_t)q, (uint32_t)stride, d_off,
                                                                                   d_meta, d_row0, d_nrows, d_chunk, d_set);
@@ -510,12 +577,17 @@ PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries
     client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, db->stream>>>(c->d_parts, d_q, d_meta, (uint32_t)q, (uint32_t)E, d_ans, d_res);
     PM_CHECK_LAUNCH();
     count_launch();
+    if (dist_out) {  // distances of the answered entries' vectors to the search query, on the same stream (A10 call site)
+        PM_CUDA(cudaMemcpyAsync(d_qv, query_vec, dim * 4, cudaMemcpyHostToDevice, db->stream));
+        if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, 0, q, (uint32_t)dim, d_dist, db->stream))) return rc;
+    }
     mark(4);
     PM_CUDA(cudaMemcpyAsync(c->stage, d_res, b_back, cudaMemcpyDeviceToHost, db->stream));
     mark(5);
     PM_CUDA(cudaStreamSynchronize(db->stream));
     memcpy(out, c->stage, q * E * 8);
     const ClientMeta *meta = (const ClientMeta *)((const char *)c->stage + q * E * 8);
+    if (dist_out) memcpy(dist_out, (const char *)c->stage + q * E * 8 + b_meta, q * 4);
     if (prof) {
         for (int i = 0; i < 5; i++) {
             float ms = 0;

@@ -35,7 +35,9 @@ int set_error(int code, const char *fmt, ...);
 void count_launch(uint64_t n = 1);
 int ensure_device(int device);  // cudaSetDevice + one-time table upload; returns PM_OK / error
 int sm_count(int device);
-const void *zero_page(int device);  // 4 KB of device zeros, allocated once per device
+const void *zero_page(int device);
+int l2_rows_enqueue(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride, uint64_t n, uint32_t dim, float *out,
+                    cudaStream_t st);  // pm_ann.cu  // 4 KB of device zeros, allocated once per device
 // grow-only scratch slot on a handle
 int scratch(pm_db *db, int slot, size_t bytes, void **out);
 unsigned int *sync_counter(pm_db *db);  // next barrier counter of the handle's pool
