@@ -152,6 +152,22 @@ int PIRGraphInfo::GetStartVertex(std::vector<Vertex> *out) {
 void GraphANNFrontend::Preprocess() {
     Graph->Preprocess();
     if (Graph->GetStartVertex(&StartVertices) != 0) throw std::runtime_error("GetStartVertex failed");
+    UploadStartVertices();
+}
+// keep the start vertices' vectors resident on the GPU: rows of dim fp32 viewed as dim/2 uint64 (needs an even dim)
+void GraphANNFrontend::UploadStartVertices() {
+    if (startDb) { pm_db_destroy(startDb); startDb = nullptr; }
+    int64_t n, dim, m;
+    Graph->GetMetadata(&n, &dim, &m);
+    if (StartVertices.empty() || (dim & 1)) return;
+    std::vector<uint64_t> rows(StartVertices.size() * (size_t)(dim / 2));
+    for (size_t i = 0; i < StartVertices.size(); i++) memcpy(&rows[i * (size_t)(dim / 2)], StartVertices[i].Vector.data(), (size_t)dim * 4);
+    check(pm_db_create(rows.data(), StartVertices.size(), (uint64_t)(dim / 2), Graph->Device(), &startDb), "pm_db_create(start vertices)");
+    startIds.resize(StartVertices.size());
+    for (size_t i = 0; i < startIds.size(); i++) startIds[i] = (int64_t)i;
+}
+GraphANNFrontend::~GraphANNFrontend() {
+    if (startDb) pm_db_destroy(startDb);
 }
 
 namespace {
@@ -192,69 +208,92 @@ struct ExploreQueue {
 };
 }  // namespace
 
+// Distances of every start vertex to one query (search.go:131-134).  The start vertices are fixed plaintext copies,
+// so their vectors are uploaded once (Preprocess) and each search only sends the query.
+void GraphANNFrontend::StartDistances(const float *queryVector, int64_t dim, int device, std::vector<float> *out) {
+    out->assign(StartVertices.size(), 0.f);
+    if (StartVertices.empty()) return;
+    if (startDb) {
+        check(pm_l2_batch(startDb, (uint64_t)dim, queryVector, 1, startIds.data(), startIds.size(), out->data()), "pm_l2_batch");
+        return;
+    }
+    std::vector<const float *> ptrs;
+    for (auto &v : StartVertices) ptrs.push_back(v.Vector.data());
+    dist_many(ptrs, dim, queryVector, device, out);
+}
+
 int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking,
                                 std::vector<int64_t> *ret, std::vector<int64_t> *stepRet) {
     int64_t n, dim, m;
     Graph->GetMetadata(&n, &dim, &m);
     const int device = Graph->Device();
-    std::unordered_map<int64_t, int64_t> reachStep;
-    std::unordered_map<int64_t, Vertex> knownVertices;
-    std::vector<int64_t> knownOrder;  // insertion order, only to make iteration deterministic
+    // knownVertices / reachStep (search.go:117-118) as a slot table: the reference keeps whole Vertex objects in maps, but
+    // only ids, neighbour lists, reach steps and distances are read back.  A vertex's distance is evaluated once, when it
+    // becomes known, and reused by the final ranking (search.go:212-218 recomputes L2Dist on the same vector: same bits).
+    std::unordered_map<int64_t, int32_t> slotOf;
+    slotOf.reserve((size_t)(maxStep * parallel * m * 2 + 64));
+    std::vector<int64_t> knownId, knownStep, nbrPool;
+    std::vector<float> knownDist;
+    auto add_known = [&](const Vertex &v, float dist, int64_t step) {
+        slotOf[v.Id] = (int32_t)knownId.size();
+        knownId.push_back(v.Id);
+        knownDist.push_back(dist);
+        knownStep.push_back(step);
+        nbrPool.insert(nbrPool.end(), v.Neighbors.begin(), v.Neighbors.end());
+    };
     ExploreQueue toBeExplored;
     const uint64_t rseed = Mix64(randSeed, queryCounter++);
     uint64_t rctr = 0;
     std::vector<float> dists;
 
     if (!benchmarking) {  // search.go:129-148
-        std::vector<const float *> ptrs;
-        for (auto &v : StartVertices) ptrs.push_back(v.Vector.data());
-        dist_many(ptrs, dim, queryVector, device, &dists);
+        StartDistances(queryVector, dim, device, &dists);
         std::vector<size_t> order(StartVertices.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dists[a] < dists[b]; });
         for (size_t i = 0; (int64_t)toBeExplored.Len() < parallel && i < order.size(); i++) {
             const Vertex &v = StartVertices[order[i]];
-            if (knownVertices.count(v.Id)) continue;
-            knownVertices[v.Id] = v;
-            knownOrder.push_back(v.Id);
+            if (slotOf.count(v.Id)) continue;
+            add_known(v, dists[order[i]], 0);
             toBeExplored.Push({dists[order[i]], v.Id});
-            reachStep[v.Id] = 0;
         }
     }
 
-    std::vector<Vertex> queryResults;
-    std::vector<float> srcDists;
+    std::vector<Vertex> &queryResults = wsResults;
+    std::vector<float> &srcDists = wsSrcDists;
+    std::vector<int64_t> batchQ;
+    std::vector<size_t> fresh, missing;
+    std::vector<const float *> ptrs;
     for (int64_t step = 0; step < maxStep; step++) {  // search.go:150-208
-        std::vector<int64_t> batchQ;
-        batchQ.reserve((size_t)(parallel * m));
+        batchQ.clear();
         for (int64_t rept = 0; rept < parallel; rept++) {
             if (toBeExplored.Len() == 0 || benchmarking) {
                 for (int64_t i = 0; i < m; i++) batchQ.push_back((int64_t)(Mix64(rseed, rctr++) % (uint64_t)n));
             } else {
                 VD item = toBeExplored.Pop();
-                const Vertex &v = knownVertices[item.id];
-                batchQ.insert(batchQ.end(), v.Neighbors.begin(), v.Neighbors.end());
+                const int64_t *nb = &nbrPool[(size_t)slotOf[item.id] * (size_t)m];
+                batchQ.insert(batchQ.end(), nb, nb + m);
             }
         }
         if (Graph->GetVertexInfoWithDist(batchQ, benchmarking ? nullptr : queryVector, &queryResults, &srcDists) != 0) return -1;
         if (benchmarking) continue;
-        // newly discovered vertices of this step: one distance launch for all of them
-        std::vector<size_t> fresh;
+        // newly discovered vertices of this step, in batch order (a repeated id is "already known" by its second occurrence)
+        fresh.clear();
         for (size_t i = 0; i < queryResults.size(); i++) {
             const Vertex &v = queryResults[i];
-            if (knownVertices.count(v.Id)) continue;
-            bool dup = false;  // a duplicate id inside this batch is "already known" by the time the loop reaches it
+            if (slotOf.count(v.Id)) continue;
+            bool dup = false;
             for (size_t f : fresh) dup = dup || queryResults[f].Id == v.Id;
             if (dup) continue;
             bool ok = false;
-            for (int64_t nb : v.Neighbors) if (nb != 0) { ok = true; break; }
+            for (int64_t nb : v.Neighbors) if (nb != 0) { ok = true; break; }   // all-zero list = failed fetch (search.go:192-199)
             if (ok) fresh.push_back(i);
         }
-        // distances of the newly discovered vertices (search.go:204): taken from the vertex source when it computed them
-        // behind the fetch, one extra launch only for the ones it did not (e.g. entries served from the local cache)
+        // their distances (search.go:204): taken from the vertex source when it computed them behind the fetch, one extra
+        // launch only for the ones it did not (e.g. entries served from the local cache)
         dists.assign(fresh.size(), 0.f);
-        std::vector<const float *> ptrs;
-        std::vector<size_t> missing;
+        ptrs.clear();
+        missing.clear();
         for (size_t t = 0; t < fresh.size(); t++) {
             const float d = srcDists[fresh[t]];
             if (std::isnan(d)) { missing.push_back(t); ptrs.push_back(queryResults[fresh[t]].Vector.data()); }
@@ -263,29 +302,24 @@ int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t max
         if (!missing.empty()) {
             std::vector<float> md;
             dist_many(ptrs, dim, queryVector, device, &md);
-            for (size_t k = 0; k < missing.size(); k++) dists[missing[k]] = md[k];
+            for (size_t j = 0; j < missing.size(); j++) dists[missing[j]] = md[j];
         }
         for (size_t t = 0; t < fresh.size(); t++) {
             const Vertex &v = queryResults[fresh[t]];
-            knownVertices[v.Id] = v;
-            knownOrder.push_back(v.Id);
-            reachStep[v.Id] = step;
+            add_known(v, dists[t], step);
             toBeExplored.Push({dists[t], v.Id});
         }
     }
 
     // search.go:210-233
-    std::vector<const float *> ptrs;
-    for (int64_t id : knownOrder) ptrs.push_back(knownVertices[id].Vector.data());
-    dist_many(ptrs, dim, queryVector, device, &dists);
-    std::vector<VD> all(knownOrder.size());
-    for (size_t i = 0; i < all.size(); i++) all[i] = {dists[i], knownOrder[i]};
+    std::vector<VD> all(knownId.size());
+    for (size_t i = 0; i < all.size(); i++) all[i] = {knownDist[i], knownId[i]};
     std::sort(all.begin(), all.end(), [](const VD &a, const VD &b) { return a.dist < b.dist || (a.dist == b.dist && a.id < b.id); });
     ret->assign(k, -1);
     stepRet->assign(k, -1);
     for (int64_t i = 0; i < k && i < (int64_t)all.size(); i++) {
         (*ret)[i] = all[i].id;
-        (*stepRet)[i] = reachStep[all[i].id];
+        (*stepRet)[i] = knownStep[(size_t)slotOf[all[i].id]];
     }
     return 0;
 }

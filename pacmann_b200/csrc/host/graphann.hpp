@@ -83,7 +83,9 @@ void PackEntry(int64_t dim, int64_t m, const float *vector, const int32_t *neigh
 class GraphANNFrontend {  // search.go:69-245
 public:
     explicit GraphANNFrontend(GetGraphInfo *g) : Graph(g) {}
+    ~GraphANNFrontend();
     void Preprocess();
+    void UploadStartVertices();   // call again after editing StartVertices by hand
     void GetMetadata(int64_t *n, int64_t *dim, int64_t *m) const { Graph->GetMetadata(n, dim, m); }
     // returns the k nearest ids and the step at which each was reached (-1 padding), search.go:114-234
     int SearchKNN(const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking,
@@ -94,6 +96,13 @@ public:
     std::vector<Vertex> StartVertices;
     uint64_t randSeed = 0;   // stands in for Go's global math/rand in the "random query" branch (search.go:155-159)
     uint64_t queryCounter = 0;
+
+private:
+    void StartDistances(const float *queryVector, int64_t dim, int device, std::vector<float> *out);
+    pm_db *startDb = nullptr;            // start vertices' vectors, resident on the GPU
+    std::vector<int64_t> startIds;       // 0..n_start-1
+    std::vector<Vertex> wsResults;       // per-step scratch reused across steps and searches
+    std::vector<float> wsSrcDists;
 };
 
 }  // namespace graphann

@@ -266,6 +266,11 @@ PMH void pmh_frontend_set_start_ids(void *h, const int64_t *ids, int64_t n) {
     } else {
         b->g->GetVertexInfo(v, &b->f->StartVertices);
     }
+    try {
+        b->f->UploadStartVertices();
+    } catch (const std::exception &e) {
+        t_err = e.what();
+    }
 }
 PMH void pmh_frontend_set_rand_seed(void *h, uint64_t seed) {
     ((FrontBox *)h)->f->randSeed = seed;
