@@ -286,3 +286,81 @@ def test_hintgen_low_bits_path_equals_full_prf(cabi, oracle):
     want = oracle.prf_batch(rk, np.arange(H, dtype=np.uint64), np.zeros(H, np.uint64)) & np.uint64(C - 1)
     assert (out[:, 0] == want).all()
     db.close()
+
+
+def test_expand_key_batch(cabi, oracle):
+    import ctypes as C
+    rng = np.random.default_rng(31)
+    keys = rng.integers(0, 256, (9, 16), dtype=np.uint8)
+    rk = np.zeros((9, 44), np.uint32)
+    cabi.check(cabi.lib().pm_expand_key_batch(keys.ctypes.data_as(C.c_void_p), 9, rk.ctypes.data_as(C.c_void_p)))
+    for i in range(9):
+        assert (rk[i] == oracle.expand_key(bytes(keys[i]))).all()
+
+
+def test_argument_errors_are_reported_not_swallowed(cabi):
+    rows = splitmix_db(100, 4, seed=32)
+    db = cabi.DB(rows)
+    rk = cabi.expand_key(KEY)
+    out = np.zeros((10, 4), np.uint64)
+    with pytest.raises(cabi.PacmannError) as e:      # chunk size must be a power of two
+        cabi.hintgen(db, [cabi.make_job(0, 100, 24, 5, rk, 0, 10, 10, 0, parity_out=out)])
+    assert e.value.code == cabi.PM_ERR_ARG
+    with pytest.raises(cabi.PacmannError) as e:      # slice past the end of the table
+        cabi.hintgen(db, [cabi.make_job(50, 100, 32, 4, rk, 0, 10, 10, 0, parity_out=out)])
+    assert e.value.code == cabi.PM_ERR_ARG
+    with pytest.raises(cabi.PacmannError):           # inner-product scan needs dim % 16 == 0 (reference loop)
+        cabi.ip_u32_scan(db, 8, np.zeros(8, np.uint32))
+    with pytest.raises(cabi.PacmannError):
+        cabi.gather_rows(db, 90, 20, np.zeros(1, np.uint64))
+    # empty inputs are fine
+    assert cabi.prf_batch(rk, np.zeros(0, np.uint64), np.zeros(0, np.uint64)).size == 0
+    assert cabi.gather_rows(db, 0, 100, np.zeros(0, np.uint64)).shape == (0, 4)
+    empty = np.zeros((0, 4), np.uint64)
+    cabi.hintgen(db, [cabi.make_job(0, 100, 32, 4, rk, 0, 0, 0, 0, parity_out=empty)])
+    db.close()
+
+
+def test_client_query_with_fused_distances(cabi, oracle):
+    """pm_client_query_batch_l2: the distances returned with the answers equal L2Dist on the returned vectors."""
+    import ctypes as C
+    n, dim, m = 20000, 64, 16
+    rng = np.random.default_rng(33)
+    vec = rng.standard_normal((n, dim)).astype(np.float32)
+    graph = rng.integers(1, n, (n, m), dtype=np.int32)
+    raw = oracle.pack_db(vec, graph)
+    E = (dim + m) // 2
+    db = cabi.DB(raw.reshape(n, E))
+    p = oracle.client_params(n, 8)
+    part = np.array([0, n, p["chunk_size"], p["set_size"], p["primary_hint_num"], p["max_query_per_chunk"], p["max_query_num"]], np.uint64)
+    h = C.c_void_p()
+    cabi.check(cabi.lib().pm_client_create(db.h, part.ctypes.data_as(C.c_void_p), 1, C.byref(h)))
+    ids = np.zeros(1, np.uint32)
+    rk = cabi.expand_key(KEY)
+    seed = np.array([5], np.uint64)
+    cabi.check(cabi.lib().pm_client_preprocess(h, ids.ctypes.data_as(C.c_void_p), 1, rk.ctypes.data_as(C.c_void_p), seed.ctypes.data_as(C.c_void_p), 0))
+    qn = 24
+    idx = rng.choice(n, qn, replace=False)
+    queries = np.zeros(qn, dtype=[("part", np.uint32), ("kind", np.uint32), ("idx", np.uint64), ("ds", np.uint64), ("dc", np.uint64)])
+    queries["kind"] = 1
+    queries["idx"] = idx
+    queries["kind"][5] = 0                                   # one dummy query in the middle
+    out = np.zeros((qn, E), np.uint64)
+    status = np.zeros(qn, np.int32)
+    dist = np.zeros(qn, np.float32)
+    qv = rng.standard_normal(dim).astype(np.float32)
+    cabi.check(cabi.lib().pm_client_query_batch_l2(h, queries.ctypes.data_as(C.c_void_p), qn, out.ctypes.data_as(C.c_void_p),
+                                                  status.ctypes.data_as(C.c_void_p), qv.ctypes.data_as(C.c_void_p), dim,
+                                                  dist.ctypes.data_as(C.c_void_p)))
+    got_vec = out.view(np.float32).reshape(qn, 2 * E)[:, :dim]
+    for i in range(qn):
+        if i == 5:
+            assert (out[i] == 0).all()
+        elif status[i] == 0:
+            assert (out[i] == raw.reshape(n, E)[idx[i]]).all()
+        else:
+            assert (out[i] == 0).all() and status[i] in (3, 4)
+        assert dist[i].view(np.uint32) == oracle.l2dist(got_vec[i], qv).view(np.uint32)
+    assert (status == 0).sum() >= qn - 6
+    cabi.check(cabi.lib().pm_client_destroy(h))
+    db.close()
