@@ -485,6 +485,8 @@ def private_search(args, rank, world, local_rank, dist, dev):
         "gpu_launches": int(cabi.launch_count() - l0), "server_subqueries": int(pir.serverQueries - s0),
         "pir_success_rate": f.succQueryNum / max(1, f.totalQueryNum),
         "client": "GPU-resident hint tables (pm_client_*); maintenance excluded as in private-search.go:219-240",
+        "pir_preprocessing_note": "wall clock of SimpleBatchPianoPIR.Preprocessing() with the resident client: key schedules, table "
+                                  "init, offset index, hint kernel, replacement gather; nothing returns to the host",
         "reference_published": "0.0559 / 0.0640 s per query on SIFT1M, 1 thread (private-search-report.txt:19,44)",
     }
     if rank == 0 and not args.no_cpu_baseline:
