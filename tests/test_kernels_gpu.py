@@ -364,3 +364,47 @@ def test_client_query_with_fused_distances(cabi, oracle):
     assert (status == 0).sum() >= qn - 6
     cabi.check(cabi.lib().pm_client_destroy(h))
     db.close()
+
+
+@pytest.mark.parametrize("n_rows", [1, 2, 5, 10, 100, 513])
+def test_hintgen_tiny_instances(cabi, oracle, n_rows):
+    """Degenerate geometries: fewer rows than a chunk, SetSize smaller than a lane group, no backup hints."""
+    E = 4
+    rows = splitmix_db(n_rows, E, seed=100 + n_rows)
+    pir_o = oracle.PianoPIR(n_rows, E * 8, rows.reshape(-1), 8)
+    pir_o.preprocessing(KEY, repl_seed=3)
+    want = oracle_parities(pir_o)
+    db = cabi.DB(rows)
+    got = _hintgen_all(cabi, db, pir_o, cabi.expand_key(KEY))
+    assert got.shape == want.shape and (got == want).all()
+    if want.shape[0] and pir_o.set_size:
+        offs = np.zeros((3, pir_o.set_size), np.uint32)
+        offs[1] = pir_o.chunk_size - 1
+        offs[2] = np.arange(pir_o.set_size) % pir_o.chunk_size
+        ans = cabi.answer_batch(db, 0, n_rows, pir_o.chunk_size, pir_o.set_size, offs)
+        for i in range(3):
+            assert (ans[i] == pir_o.private_query(offs[i])).all()
+    db.close()
+
+
+def test_hintgen_more_jobs_than_one_launch_holds(cabi, oracle):
+    """40 sub-PIRs in one call: the library splits them over several launches (16 job descriptors per launch)."""
+    n_rows, E, batch = 24000, 8, 80
+    rows = splitmix_db(n_rows, E, seed=120)
+    b_o = oracle.SimpleBatchPianoPIR(n_rows, E * 8, batch, rows.reshape(-1), 8)
+    b_o.preprocessing(key_seed=9, repl_seed=1, threads=4)
+    assert b_o.partition_num == 40
+    db = cabi.DB(rows)
+    jobs, outs = [], []
+    for i in range(b_o.partition_num):
+        sub = b_o.sub(i)
+        H = sub.primary_hint_num + sub.set_size * sub.max_query_per_chunk
+        out = np.zeros((H, E), np.uint64)
+        outs.append(out)
+        rk = cabi.expand_key(oracle.derive_key(9, 0, b_o.partition_num, i))
+        jobs.append(cabi.make_job(i * b_o.partition_size, sub.db_size, sub.chunk_size, sub.set_size, rk, 0, H,
+                                  sub.primary_hint_num, sub.max_query_per_chunk, parity_out=out))
+    cabi.hintgen(db, jobs)
+    for i in range(b_o.partition_num):
+        assert (outs[i] == oracle_parities(b_o.sub(i))).all(), f"partition {i}"
+    db.close()
