@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how parities reach rank 0")
     ap.add_argument("--no-search", action="store_true", help="skip the private-ANN queries/s part")
     ap.add_argument("--search-queries", type=int, default=96, help="private ANN queries per GPU")
+    ap.add_argument("--search-clients", type=int, default=8, help="concurrent clients per GPU in the serving measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -489,6 +490,36 @@ def private_search(args, rank, world, local_rank, dist, dev):
                                   "init, offset index, hint kernel, replacement gather; nothing returns to the host",
         "reference_published": "0.0559 / 0.0640 s per query on SIFT1M, 1 thread (private-search-report.txt:19,44)",
     }
+    # serving form: several clients (one per user: own keys, hint tables, search state) over the ONE resident DB replica,
+    # driven from host threads; every client still answers its queries sequentially, exactly as a single one does
+    K = args.search_clients
+    if K > 1:
+        import threading
+        fs = [f] + [graphann.GraphANNFrontend(vec, graph, seed=seed + 100 + i, share_db_with=f) for i in range(K - 1)]
+        for g in fs[1:]:
+            g.Preprocess()
+            g.SearchKNNBatch(queries[:1], k, step, par)
+        per = max(8, nq // 2)
+        qs = [vec[np.random.default_rng(SEED + 10 + rank * K + i).integers(0, n, per)] + np.float32(0.25) for i in range(K)]
+
+        def work(i):
+            fs[i].SearchKNNBatch(qs[i], k, step, par)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(K)]
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        mdt = time.perf_counter() - t0
+        tm = torch.tensor([mdt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        out["multi_client"] = {"clients_per_gpu": K, "queries": K * per * world, "queries_per_s": K * per * world / float(tm[0]),
+                               "s_per_query_per_client": mdt / per}
+        del fs
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as o
         raw = o.pack_db(vec, graph)

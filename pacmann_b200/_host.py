@@ -42,6 +42,7 @@ SIG = {
     "pmh_l2dist": (C.c_float, [vp, vp, u64, C.c_int]),
     "pmh_frontend_basic": (vp, [i64, i64, i64, vp, vp]),
     "pmh_frontend_pir": (vp, [i64, i64, i64, vp, vp, C.c_int, C.c_int, u64, C.c_int, C.c_int]),
+    "pmh_frontend_pir_shared": (vp, [vp, u64, C.c_int]),
     "pmh_frontend_free": (None, [vp]),
     "pmh_frontend_preprocess": (C.c_int, [vp]),
     "pmh_frontend_start_ids": (i64, [vp, vp, i64]),

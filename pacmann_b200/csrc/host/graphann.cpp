@@ -79,10 +79,15 @@ PIRGraphInfo::~PIRGraphInfo() { delete PIR; }
 void PIRGraphInfo::Preprocess() {
     DBEntryByteNum = (uint64_t)(Dim * 4 + M * 4);
     const uint64_t E = DBEntryByteNum / 8;
-    rawDB.assign((uint64_t)N * E, 0);
-    for (int64_t i = 0; i < N; i++) PackEntry(Dim, M, vectors + i * Dim, graph + i * M, &rawDB[(uint64_t)i * E]);
     DBTotalSize = (uint64_t)N * DBEntryByteNum;
-    PIR = new pianopir::SimpleBatchPianoPIR((uint64_t)N, DBEntryByteNum, (uint64_t)M, rawDB.data(), rawDB.size(), 8, device);
+    if (shareDBWith && shareDBWith->PIR) {   // the DB is already packed and resident: only a new client is created
+        PIR = new pianopir::SimpleBatchPianoPIR((uint64_t)N, DBEntryByteNum, (uint64_t)M, shareDBWith->PIR->db, 8);
+    } else {
+        rawDB.assign((uint64_t)N * E, 0);
+        for (int64_t i = 0; i < N; i++) PackEntry(Dim, M, vectors + i * Dim, graph + i * M, &rawDB[(uint64_t)i * E]);
+        PIR = new pianopir::SimpleBatchPianoPIR((uint64_t)N, DBEntryByteNum, (uint64_t)M, rawDB.data(), rawDB.size(), 8, device);
+        std::vector<uint64_t>().swap(rawDB);  // the device copy is the server's DB from here on
+    }
     PIR->SetSeeds(Mix64(seed, 1), Mix64(seed, 2));
     if (residentClient && !NonPrivateMode) PIR->EnableResidentClient();
     if (skipPrep) PIR->DummyPreprocessing();

@@ -66,6 +66,7 @@ public:
     const float *vectors;
     bool skipPrep, NonPrivateMode;
     bool residentClient = true;  // keep the hint tables on the GPU (pm_client_*)
+    PIRGraphInfo *shareDBWith = nullptr;  // another client's graph info whose resident rawDB this one reuses (one per user)
     uint64_t DBEntryByteNum = 0, DBTotalSize = 0;
     std::vector<uint64_t> rawDB;
     pianopir::SimpleBatchPianoPIR *PIR = nullptr;

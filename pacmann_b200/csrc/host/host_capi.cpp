@@ -231,6 +231,20 @@ PMH void *pmh_frontend_pir(int64_t n, int64_t dim, int64_t m, const int32_t *gra
     return b;
     PMH_CATCH(nullptr)
 }
+// one more client (its own keys, hint tables and search state) over the rawDB that `other` already keeps on the GPU
+PMH void *pmh_frontend_pir_shared(void *other, uint64_t seed, int resident) {
+    PMH_TRY
+    auto *og = dynamic_cast<graphann::PIRGraphInfo *>(((FrontBox *)other)->g);
+    if (!og || !og->PIR) throw std::runtime_error("pmh_frontend_pir_shared: the other frontend has no preprocessed PIR");
+    auto *b = new FrontBox();
+    auto *pg = new graphann::PIRGraphInfo(og->N, og->Dim, og->M, og->graph, og->vectors, og->skipPrep, false, seed, og->device);
+    pg->residentClient = resident != 0;
+    pg->shareDBWith = og;
+    b->g = pg;
+    b->f = new graphann::GraphANNFrontend(b->g);
+    return b;
+    PMH_CATCH(nullptr)
+}
 PMH void pmh_frontend_free(void *h) {
     auto *b = (FrontBox *)h;
     if (!b) return;

@@ -384,8 +384,20 @@ int PianoPIR::Query(uint64_t idx, bool realQuery, std::vector<uint64_t> *ret) {
 // ---------------------------------------------------------------------------------------------
 SimpleBatchPianoPIR::SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, const uint64_t *rawDB,
                                          uint64_t len_rawDB, uint64_t FailureProbLog2, int device) {
+    if (len_rawDB != DBSize * (DBEntryByteNum / 8)) throw std::runtime_error("BatchPIR: len(rawDB) != DBSize*DBEntrySize");  // batch-pir.go:57-59
+    Init(DBSize, DBEntryByteNum, BatchSize, new DeviceDB(rawDB, DBSize, DBEntryByteNum / 8, device), true, FailureProbLog2);
+}
+SimpleBatchPianoPIR::SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, DeviceDB *sharedDB,
+                                         uint64_t FailureProbLog2) {
+    if (!sharedDB || sharedDB->n_rows != DBSize || sharedDB->entry_u64 != DBEntryByteNum / 8)
+        throw std::runtime_error("BatchPIR: shared rawDB does not match DBSize*DBEntrySize");
+    Init(DBSize, DBEntryByteNum, BatchSize, sharedDB, false, FailureProbLog2);
+}
+void SimpleBatchPianoPIR::Init(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, DeviceDB *theDB, bool owns,
+                               uint64_t FailureProbLog2) {
     const uint64_t E = DBEntryByteNum / 8;
-    if (len_rawDB != DBSize * E) throw std::runtime_error("BatchPIR: len(rawDB) != DBSize*DBEntrySize");  // batch-pir.go:57-59
+    const int device = theDB->device;
+    (void)device;
     config.DBEntryByteNum = DBEntryByteNum;
     config.DBEntrySize = E;
     config.DBSize = DBSize;
@@ -394,7 +406,8 @@ SimpleBatchPianoPIR::SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNu
     config.PartitionSize = (DBSize + config.PartitionNum - 1) / config.PartitionNum;
     config.ThreadNum = 1;
     config.FailureProbLog2 = FailureProbLog2;
-    db = new DeviceDB(rawDB, DBSize, E, device);
+    db = theDB;
+    ownsDB = owns;
     for (uint64_t i = 0; i < config.PartitionNum; i++) {
         uint64_t start = i * config.PartitionSize, end = std::min((i + 1) * config.PartitionSize, DBSize);
         PianoPIR *p = new PianoPIR(end - start, DBEntryByteNum, db, start, FailureProbLog2);
@@ -410,7 +423,7 @@ SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
                 (unsigned long long)profQueryCalls, profQueryTotal / profQueryCalls * 1e6, profGpuCall / profQueryCalls * 1e6);
     if (rclient) pm_client_destroy(rclient);
     for (auto *p : subPIR) delete p;
-    delete db;
+    if (ownsDB) delete db;
 }
 void SimpleBatchPianoPIR::SetSeeds(uint64_t keySeed, uint64_t replSeed) {
     for (auto *p : subPIR) {

@@ -133,6 +133,8 @@ public:
     // rawDB is uploaded once (replicated on `device`); len_rawDB must equal DBSize*DBEntryByteNum/8 (batch-pir.go:57-59)
     SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, const uint64_t *rawDB,
                         uint64_t len_rawDB, uint64_t FailureProbLog2, int device = 0);
+    // a further client over a rawDB that is already resident (one DB replica per GPU, one client per user)
+    SimpleBatchPianoPIR(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, DeviceDB *sharedDB, uint64_t FailureProbLog2);
     ~SimpleBatchPianoPIR();
     void SetSeeds(uint64_t keySeed, uint64_t replSeed);
     void Preprocessing();
@@ -149,6 +151,7 @@ public:
     SimpleBatchPianoPIRConfig config;
     std::vector<PianoPIR *> subPIR;
     DeviceDB *db = nullptr;
+    bool ownsDB = true;
     uint64_t FinishedBatchNum = 0, QueriesMadeInPartition = 0, SupportBatchNum = 0;
     uint64_t localStorage = 0, commCostPerBatchOnline = 0, commCostPerBatchOffline = 0;
     double preprocessingTime = 0;
@@ -166,6 +169,7 @@ public:
     pm_client *rclient = nullptr;
 
 private:
+    void Init(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_t BatchSize, DeviceDB *theDB, bool owns, uint64_t FailureProbLog2);
     struct PendRec { uint64_t part, global, local; int kind; /* 0 dummy, 1 real, 2 cached */ int64_t qpos; };
     std::vector<std::vector<uint64_t>> wsLists;   // per-call scratch, kept to avoid reallocation
     std::vector<PendRec> wsPend;

@@ -357,12 +357,35 @@ struct pm_client {
     void *arena;
     uint64_t max_set;
     std::mutex mu;
+    cudaStream_t stream = nullptr;          // every client owns its stream, scratch and lock, so several clients that
+    void *wbuf[2] = {nullptr, nullptr};     // share one pm_db (one per user) can be driven from different host threads
+    size_t wbytes[2] = {0, 0};
     void *stage = nullptr;   // pinned host staging for results
     size_t stage_bytes = 0;
     cudaEvent_t ev[6] = {};
     double prof_ms[5] = {};
     uint64_t prof_calls = 0;
 };
+
+static int client_scratch(pm_client *c, int slot, size_t bytes, void **out) {
+    if (c->wbytes[slot] < bytes) {
+        if (c->wbuf[slot]) {
+            PM_CUDA(cudaStreamSynchronize(c->stream));
+            PM_CUDA(cudaFree(c->wbuf[slot]));
+            c->wbuf[slot] = nullptr;
+            c->wbytes[slot] = 0;
+        }
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMalloc(&c->wbuf[slot], want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return pm::set_error(PM_ERR_NOMEM, "pm_client: cudaMalloc(%zu) for scratch failed: %s", want, cudaGetErrorString(e));
+        }
+        c->wbytes[slot] = want;
+    }
+    *out = c->wbuf[slot];
+    return PM_OK;
+}
 
 PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t n_parts, pm_client **out) {
     using namespace pm;
@@ -417,6 +440,8 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
             if ((uintptr_t)cur & 15) cur += 1;
         }
     }
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { cudaFree(c->arena); cudaFree(c->d_parts); delete c; return set_error(PM_ERR_CUDA, "pm_client_create: stream creation failed"); }
     *out = c;
     return PM_OK;
 }
@@ -428,10 +453,12 @@ PM_EXPORT int pm_client_destroy(pm_client *c) {
                 (unsigned long long)c->prof_calls, c->prof_ms[0] / c->prof_calls * 1e3, c->prof_ms[1] / c->prof_calls * 1e3,
                 c->prof_ms[2] / c->prof_calls * 1e3, c->prof_ms[3] / c->prof_calls * 1e3, c->prof_ms[4] / c->prof_calls * 1e3);
     if (pm::ensure_device(c->db->device) == PM_OK) {
-        cudaStreamSynchronize(c->db->stream);
+        cudaStreamSynchronize(c->stream);
         cudaFree(c->arena);
         cudaFree(c->d_parts);
+        for (int i = 0; i < 2; i++) if (c->wbuf[i]) cudaFree(c->wbuf[i]);
         if (c->stage) cudaFreeHost(c->stage);
+        cudaStreamDestroy(c->stream);
     }
     delete c;
     return PM_OK;
@@ -445,7 +472,7 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
     int rc = ensure_device(c->db->device);
     if (rc) return rc;
     pm_db *db = c->db;
-    std::lock_guard<std::mutex> lock(db->mu);
+    std::lock_guard<std::mutex> lock(c->mu);
     const uint64_t E = c->E;
     uint64_t max_n = 0;
     for (uint64_t a = 0; a < n; a++) {
@@ -455,15 +482,15 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
         const uint64_t P = D.n_primary, B = D.set_size * D.backup_group;
         max_n = std::max(max_n, std::max(P, B));
     }
-    PM_CUDA(cudaMemcpyAsync(c->d_parts, c->host_parts.data(), c->n_parts * sizeof(ClientPartDev), cudaMemcpyHostToDevice, db->stream));
+    PM_CUDA(cudaMemcpyAsync(c->d_parts, c->host_parts.data(), c->n_parts * sizeof(ClientPartDev), cudaMemcpyHostToDevice, c->stream));
     void *d_tmp = nullptr;
-    if ((rc = scratch(db, 1, n * 16, &d_tmp))) return rc;
+    if ((rc = client_scratch(c, 1, n * 16, &d_tmp))) return rc;
     uint32_t *d_ids = (uint32_t *)d_tmp;
     uint64_t *d_seed = (uint64_t *)((char *)d_tmp + ((n * 4 + 7) & ~7ull));
-    PM_CUDA(cudaMemcpyAsync(d_ids, part_ids, n * 4, cudaMemcpyHostToDevice, db->stream));
-    PM_CUDA(cudaMemcpyAsync(d_seed, repl_seed, n * 8, cudaMemcpyHostToDevice, db->stream));
+    PM_CUDA(cudaMemcpyAsync(d_ids, part_ids, n * 4, cudaMemcpyHostToDevice, c->stream));
+    PM_CUDA(cudaMemcpyAsync(d_seed, repl_seed, n * 8, cudaMemcpyHostToDevice, c->stream));
     dim3 grid((unsigned)std::min<uint64_t>((max_n + 255) / 256, 64), (unsigned)n);
-    client_init_kernel<<<grid, 256, 0, db->stream>>>(c->d_parts, d_ids, d_seed, skip_prep);
+    client_init_kernel<<<grid, 256, 0, c->stream>>>(c->d_parts, d_ids, d_seed, skip_prep);
     PM_CHECK_LAUNCH();
     count_launch();
     {
@@ -471,7 +498,7 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
         for (uint64_t a = 0; a < n; a++) max_p = std::max<uint64_t>(max_p, c->host_parts[part_ids[a]].n_primary);
         dim3 fgrid((unsigned)std::max<uint64_t>(1, (max_p + 255) / 256), (unsigned)n);
         PM_CUDA(cudaFuncSetAttribute(client_fill_poff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_tab_words<1>() * 4));
-        client_fill_poff_kernel<<<fgrid, 256, aes_tab_words<1>() * 4, db->stream>>>(c->d_parts, d_ids);
+        client_fill_poff_kernel<<<fgrid, 256, aes_tab_words<1>() * 4, c->stream>>>(c->d_parts, d_ids);
         PM_CHECK_LAUNCH();
         count_launch();
     }
@@ -480,7 +507,7 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
         const ClientPartDev &D = c->host_parts[part_ids[a]];
         const uint64_t P = D.n_primary, B = D.set_size * D.backup_group;
         if (skip_prep) {  // DummyPreprocessing (pir.go:520-523): Initialization only, parities and replacement values zero
-            PM_CUDA(cudaMemsetAsync(D.parity, 0, (P + 2 * B) * E * 8, db->stream));
+            PM_CUDA(cudaMemsetAsync(D.parity, 0, (P + 2 * B) * E * 8, c->stream));
             continue;
         }
         pm_hint_job j;
@@ -492,13 +519,13 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
         jobs.push_back(j);
     }
     if (!jobs.empty()) {
-        if ((rc = hintgen_enqueue(db, jobs.data(), jobs.size(), db->stream))) return rc;
+        if ((rc = hintgen_enqueue(db, jobs.data(), jobs.size(), c->stream))) return rc;
         for (uint64_t a = 0; a < n; a++) {  // replacement values (pir.go:348)
             const ClientPartDev &D = c->host_parts[part_ids[a]];
-            if ((rc = gather_enqueue(db, D.row0, D.n_rows, D.ridx, D.set_size * D.backup_group, D.rval, db->stream))) return rc;
+            if ((rc = gather_enqueue(db, D.row0, D.n_rows, D.ridx, D.set_size * D.backup_group, D.rval, c->stream))) return rc;
         }
     }
-    PM_CUDA(cudaStreamSynchronize(db->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
     return PM_OK;
 }
 
@@ -531,14 +558,14 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     int rc = ensure_device(c->db->device);
     if (rc) return rc;
     pm_db *db = c->db;
-    std::lock_guard<std::mutex> lock(db->mu);
+    std::lock_guard<std::mutex> lock(c->mu);
     const uint64_t E = c->E, stride = (c->max_set + 3) & ~3ull;
     // staging: queries | meta | offsets | answer descriptors   and   answers | out
     const size_t b_q = q * sizeof(ClientQueryDev), b_meta = q * sizeof(ClientMeta), b_off = q * stride * 4, b_desc = q * 24;
     void *d_in = nullptr, *d_out = nullptr;
     const size_t b_qv = (dim * 4 + 15) & ~15ull, b_dist = dist_out ? q * 4 : 0;
-    if ((rc = scratch(db, 1, b_q + b_off + b_desc + b_qv + 64, &d_in))) return rc;
-    if ((rc = scratch(db, 0, 2 * q * E * 8 + b_meta + b_dist, &d_out))) return rc;
+    if ((rc = client_scratch(c, 1, b_q + b_off + b_desc + b_qv + 64, &d_in))) return rc;
+    if ((rc = client_scratch(c, 0, 2 * q * E * 8 + b_meta + b_dist, &d_out))) return rc;
     ClientQueryDev *d_q = (ClientQueryDev *)d_in;
     uint32_t *d_off = (uint32_t *)((char *)d_in + b_q);
     uint64_t *d_row0 = (uint64_t *)((char *)d_off + b_off), *d_nrows = d_row0 + q;
@@ -558,33 +585,33 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     // PM_CLIENT_PROFILE=1: CUDA-event breakdown of the call (H2D | prepare | answer | finish | D2H), printed at destroy
     static const bool prof = getenv("PM_CLIENT_PROFILE") != nullptr;
     if (prof && !c->ev[0]) for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
-    auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], db->stream); };
+    auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], c->stream); };
     mark(0);
-    PM_CUDA(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, db->stream));
+    PM_CUDA(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, c->stream));
     mark(1);
     uint64_t max_p = 0;
     for (uint64_t i = 0; i < c->n_parts; i++) if (c->host_parts[i].poff) max_p = std::max<uint64_t>(max_p, c->host_parts[i].n_primary);
     const size_t smem = (aes_tab_words<1>() + 64 + stride + CL_MAX_LIST + max_p) * 4;
     if (smem > 200 * 1024) return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: primaryHintNum too large for the shared-memory mirror");
     PM_CUDA(cudaFuncSetAttribute(client_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    client_prepare_kernel<<<(unsigned)c->n_parts, CL_THREADS, smem, db->stream>>>(c->d_parts, d_q, (uint32_t)q, (uint32_t)stride, d_off,
+    client_prepare_kernel<<<(unsigned)c->n_parts, CL_THREADS, smem, c->stream>>>(c->d_parts, d_q, (uint32_t)q, (uint32_t)stride, d_off,
                                                                                   d_meta, d_row0, d_nrows, d_chunk, d_set);
     PM_CHECK_LAUNCH();
     count_launch();
     mark(2);
-    if ((rc = answer_enqueue(db, d_row0, d_nrows, d_chunk, d_set, d_off, stride, q, (uint32_t)stride, d_ans, db->stream))) return rc;
+    if ((rc = answer_enqueue(db, d_row0, d_nrows, d_chunk, d_set, d_off, stride, q, (uint32_t)stride, d_ans, c->stream))) return rc;
     mark(3);
-    client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, db->stream>>>(c->d_parts, d_q, d_meta, (uint32_t)q, (uint32_t)E, d_ans, d_res);
+    client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, c->stream>>>(c->d_parts, d_q, d_meta, (uint32_t)q, (uint32_t)E, d_ans, d_res);
     PM_CHECK_LAUNCH();
     count_launch();
     if (dist_out) {  // distances of the answered entries' vectors to the search query, on the same stream (A10 call site)
-        PM_CUDA(cudaMemcpyAsync(d_qv, query_vec, dim * 4, cudaMemcpyHostToDevice, db->stream));
-        if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, 0, q, (uint32_t)dim, d_dist, db->stream))) return rc;
+        PM_CUDA(cudaMemcpyAsync(d_qv, query_vec, dim * 4, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, 0, q, (uint32_t)dim, d_dist, c->stream))) return rc;
     }
     mark(4);
-    PM_CUDA(cudaMemcpyAsync(c->stage, d_res, b_back, cudaMemcpyDeviceToHost, db->stream));
+    PM_CUDA(cudaMemcpyAsync(c->stage, d_res, b_back, cudaMemcpyDeviceToHost, c->stream));
     mark(5);
-    PM_CUDA(cudaStreamSynchronize(db->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(out, c->stage, q * E * 8);
     const ClientMeta *meta = (const ClientMeta *)((const char *)c->stage + q * E * 8);
     if (dist_out) memcpy(dist_out, (const char *)c->stage + q * E * 8 + b_meta, q * 4);
@@ -623,8 +650,8 @@ PM_EXPORT int pm_client_download(pm_client *c, uint32_t part, int table, uint64_
     }
     if (cap_words < words) return set_error(PM_ERR_ARG, "pm_client_download: buffer too small (%llu < %llu words)",
                                             (unsigned long long)cap_words, (unsigned long long)words);
-    std::lock_guard<std::mutex> lock(c->db->mu);
-    PM_CUDA(cudaMemcpyAsync(out, src, words * 8, cudaMemcpyDeviceToHost, c->db->stream));
-    PM_CUDA(cudaStreamSynchronize(c->db->stream));
+    std::lock_guard<std::mutex> lock(c->mu);
+    PM_CUDA(cudaMemcpyAsync(out, src, words * 8, cudaMemcpyDeviceToHost, c->stream));
+    PM_CUDA(cudaStreamSynchronize(c->stream));
     return PM_OK;
 }

@@ -23,20 +23,26 @@ def L2Dist(v1, v2, device=0):
 class GraphANNFrontend:
     """graphann.GraphANNFrontend over BasicGraphInfo (non-private) or PIRGraphInfo (private, private-search.go)."""
 
-    def __init__(self, vectors, graph, private=False, skipPrep=False, nonPrivateMode=False, seed=1, device=0, resident=True):
+    def __init__(self, vectors, graph, private=False, skipPrep=False, nonPrivateMode=False, seed=1, device=0, resident=True,
+                 share_db_with=None):
+        """share_db_with: another private frontend (already preprocessed) whose GPU-resident rawDB this client reuses --
+        one DB replica per GPU, one client (keys, hint tables, search state) per user."""
         self.vectors = np.ascontiguousarray(vectors, np.float32)
         self.graph = np.ascontiguousarray(graph, np.int32)
         self.n, self.dim = self.vectors.shape
         self.m = self.graph.shape[1]
         L = _host.lib()
-        if private:
+        self._shared = share_db_with      # keep the owner of the DB alive
+        if share_db_with is not None:
+            h = L.pmh_frontend_pir_shared(share_db_with.h, seed, int(resident))
+        elif private:
             h = L.pmh_frontend_pir(self.n, self.dim, self.m, _p(self.graph), _p(self.vectors), int(skipPrep), int(nonPrivateMode), seed, device, int(resident))
         else:
             h = L.pmh_frontend_basic(self.n, self.dim, self.m, _p(self.graph), _p(self.vectors))
         if not h:
             raise _host.HostError(L.pmh_last_error().decode())
         self.h = C.c_void_p(h)
-        self.private = private
+        self.private = private or share_db_with is not None
 
     def __del__(self):
         if getattr(self, "h", None):

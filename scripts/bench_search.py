@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--step", type=int, default=20)
     ap.add_argument("--parallel", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--clients", type=int, default=1, help="concurrent clients (one per user) sharing the resident DB")
     a = ap.parse_args()
     n = a.n or (1000000 if a.shape == "sift" else 3201821)
     dim = 128 if a.shape == "sift" else 192
@@ -58,6 +59,27 @@ def main():
                gpu_prep_s=prep_s, gpu_pir_prep_s=pir.PreprocessingTime(), gpu_s_per_query=dt / a.q, gpu_qps=a.q / dt,
                gpu_launches=cabi.launch_count() - l0, server_subqueries=pir.serverQueries - s0,
                success_rate=f.succQueryNum / max(1, f.totalQueryNum))
+    if a.clients > 1:
+        import threading
+        fs = [f] + [graphann.GraphANNFrontend(vec, graph, seed=seed + 100 + i, share_db_with=f) for i in range(a.clients - 1)]
+        for g in fs[1:]:
+            g.Preprocess()
+            g.SearchKNNBatch(queries[:1], k, a.step, a.parallel)
+        per = max(1, a.q // 2)
+        qs = [vec[np.random.default_rng(50 + i).integers(0, n, per)] + np.float32(0.5) for i in range(a.clients)]
+        outs = [None] * a.clients
+
+        def work(i):
+            outs[i] = fs[i].SearchKNNBatch(qs[i], k, a.step, a.parallel)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(a.clients)]
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        mdt = time.perf_counter() - t0
+        res.update(clients=a.clients, multi_client_qps=a.clients * per / mdt, multi_client_s_per_query_per_client=mdt / per)
     if not a.no_cpu:
         from oracle import oracle as o
         raw = o.pack_db(vec, graph)
