@@ -38,6 +38,7 @@ ENTRY_U64 = 112
 BATCH = 32
 FAIL_LOG2 = 8
 SEED = 20241600
+NCU_DRAM_BYTES_PER_LAUNCH = 9896459000 + 295330304   # profiles/r01_hintgen_msmarco_v3_ncu_full.csv
 
 
 def pir_params(n, fail_log2):
@@ -424,7 +425,10 @@ def main():
                     "note": "DB is uploaded once at pm_db_create (as rawDB is built once in NewSimpleBatchPianoPIR); "
                             "per step only job descriptors go in and all parities come back to pinned host memory"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "hintgen_kernel<uint4,8,7,...>",
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if world == 1 else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel at N=1, one ncu --set full "
+                                           "capture (profiles/r01_hintgen_msmarco_v3_ncu_full.csv)",
+                         "peak_source": peak_src, "kernel": "hintgen_kernel<uint4,8,7,...>",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": b_hbm_rank,
                          "binding_term": "not HBM: L1 data-pipe wavefronts (row gather + AES T-table LDS) and ALU; see DESIGN.md",
                          "xor_gather_gbs": b_xor / world / (kern_ms * 1e-3) / 1e9,
