@@ -202,6 +202,12 @@ int ip_scan_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n
     if (dim != db->entry_u64 * 2) return set_error(PM_ERR_ARG, "ip scan: dim must equal 2*entry_u64");
     if (dim > 2048) return set_error(PM_ERR_UNSUPPORTED, "ip scan: dim too large");
     if (nq > 0x7fffffffull) return set_error(PM_ERR_UNSUPPORTED, "ip scan: too many queries");
+    if (ipgemm_applicable(db, dim, nq, ip_out)) {  // many queries, checksums only: int8 limb GEMM on the tensor cores
+        void *ws = nullptr;
+        int rc = scratch(db, 2, ipgemm_scratch_bytes(dim, nq), &ws);
+        if (rc) return rc;
+        return ipgemm_enqueue(db, dim, queries, nq, checksum, ws, st);
+    }
     PM_CUDA(cudaMemsetAsync(checksum, 0, nq * 4, st));
     const uint32_t dim4 = (uint32_t)(dim / 4);
     // rows per tile: as many as fit beside the queries in ~100 KB, so that two CTAs share an SM
@@ -319,5 +325,6 @@ PM_EXPORT int pm_ip_u32_scan(pm_db *db, uint64_t dim, const uint32_t *queries, u
     PM_CUDA(cudaMemcpyAsync(checksum_out, d_out, cb, cudaMemcpyDeviceToHost, db->stream));
     if (pb) PM_CUDA(cudaMemcpyAsync(ip_out, d_ip, pb, cudaMemcpyDeviceToHost, db->stream));
     PM_CUDA(cudaStreamSynchronize(db->stream));
+    if (ipgemm_applicable(db, dim, n_queries, ip_out)) return ipgemm_check(db->scratch[2], dim, n_queries);
     return PM_OK;
 }

@@ -408,3 +408,21 @@ def test_hintgen_more_jobs_than_one_launch_holds(cabi, oracle):
     for i in range(b_o.partition_num):
         assert (outs[i] == oracle_parities(b_o.sub(i))).all(), f"partition {i}"
     db.close()
+
+
+@pytest.mark.parametrize("n,d,nq", [(1000, 128, 64), (20001, 192, 200), (5000, 32, 130), (300, 64, 1000)])
+def test_ip_scan_tensor_core_path_matches_oracle(cabi, oracle, n, d, nq):
+    """nq >= 64 and dim % 32 == 0 route the scan to the tcgen05 int8-limb GEMM (pm_ipgemm.cu); the checksums must
+    still be the reference's wrapping uint32 sums, bit for bit, also for ragged row / query counts."""
+    rng = np.random.default_rng(n + nq)
+    rows = rng.integers(0, 2**32, (n, d), dtype=np.uint32)
+    qs = rng.integers(0, 2**32, (nq, d), dtype=np.uint32)
+    rows[0] = 0xFFFFFFFF                      # extreme limbs: 255 * 255 * 4 * dim must not overflow the s32 accumulators
+    qs[0] = 0xFFFFFFFF
+    db = cabi.DB(rows.view(np.uint64).reshape(n, d // 2))
+    got = cabi.ip_u32_scan(db, d, qs)
+    assert (got == oracle.ip_scan(rows, qs, threads=4)).all()
+    # the integer-pipe kernel (per-row products requested) agrees as well
+    got2, _ = cabi.ip_u32_scan(db, d, qs[:70], want_products=True)
+    assert (got2 == got[:70]).all()
+    db.close()
