@@ -1,22 +1,24 @@
 // A11 for many queries at once: the uint32 wrapping inner-product scan (graphann/l2_distance_amd64.s:39-68,
 // graphann_test.go:268-273) as an int8 GEMM on the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators
-// in TMEM, operands staged by TMA) -- the one place on this path where tensor cores are the right tool
+// kept in TMEM across the whole row sweep, operands staged by TMA) -- the one place on this path where tensor cores are the right tool
 // (BASELINE.json north_star; SURVEY.md 7.5: 6.15e11 32-bit MACs at Q = 1000 are integer-pipe bound).
 //
-// Formulation.  A u32 x u32 product mod 2^32 is  sum_{a+b<=3} A_a * B_b * 2^(8(a+b))  over the byte limbs.  Instead of
-// extracting limbs from the row matrix, the rows are used AS THEY LIE IN MEMORY: A' = the table viewed as
-// [N][4*dim] uint8 (k' = 4j + a is byte a of element j), and for every shift s = a + b in 0..3 a small operand
-//     B'_s[t][4j + a] = byte (s - a) of q_t[j]   if a <= s,  else 0
-// is built from the queries, so that   IP(i, t) = sum_s (A' B'_s^T)[i][t] << 8s   (mod 2^32).
-// Four u8 x u8 -> s32 GEMMs with K' = 4*dim; every partial sum is <= 4*dim*255^2 < 2^31 for dim <= 8192: exact.
-// Only the checksum sum_i IP(i, t) leaves the kernel: the epilogue folds the four accumulators and sums over rows.
+// Formulation.  A u32 x u32 product mod 2^32 is  sum_{a+b<=3} A_a * B_b * 2^(8(a+b))  over the byte limbs, i.e. ten
+// u8 x u8 -> s32 GEMMs grouped by shift s = a + b into four accumulators D_s, and IP(i,t) = sum_s D_s[i][t] << 8s.
+// Every partial sum is <= 4*dim*255^2 < 2^31 for dim <= 8192: exact.  Only the checksum sum_i IP(i,t) leaves the
+// kernel: the epilogue folds the four accumulators and sums over rows.
 //
-// Kernel: one persistent CTA per SM, 128 threads.  Thread 0 is TMA producer and MMA issuer (tcgen05.mma is a
-// single-thread instruction); all four warps are the epilogue (warp w reads TMEM lanes 32w..32w+31 = rows of the
-// tile).  Per (query tile of 128, row tile of 128): 4*dim/128 K-chunks, each one A tile (128 x 128 B, 128-byte
-// swizzle) and four B tiles through a 2-stage TMA/mbarrier ring, 4 shifts x 4 MMAs (M128 N128 K32) per chunk into
-// 4 x 128 TMEM columns (all 512).  Every mbarrier wait is bounded: on a timeout the kernel raises an error flag and
-// drains instead of hanging.
+// Operands.  The row table is consumed AS IT LIES IN MEMORY: TMA drops 128 rows x 128 B (32 elements per row) into
+// shared memory, and each thread then sorts the bytes of its row by limb in place -- [limb 0 of 32 elements | limb 1 |
+// limb 2 | limb 3], 32 B each -- so that every UMMA K = 32 slice of the 128-byte swizzled row is one pure limb plane.
+// The query operand is written limb-sorted the same way by a small kernel ([Q][4*dim] bytes, one copy).  Limb pair
+// (a, b) is then the MMA of A slice a with B slice b of the same 128-byte chunk: 10 MMAs per chunk.
+//
+// Kernel: one persistent CTA per SM, 128 threads.  Thread 0 is TMA producer (4 chunks ahead in a 6-stage mbarrier
+// ring of 16 KB A + 16 KB B) and tcgen05.mma issuer (single-thread instruction, M128 N128 K32, kind::i8, both operands
+// K-major with the 128-byte swizzle the tensor maps write); the four accumulators fill all 512 TMEM columns; all four
+// warps sort limbs and are the epilogue (warp w reads TMEM lanes 32w..32w+31 = rows of the tile).  Every mbarrier
+// wait is bounded: on a timeout the kernel raises an error flag and drains instead of hanging.
 #include <cuda.h>
 
 #include <algorithm>
@@ -27,21 +29,19 @@
 namespace pm {
 
 constexpr int G_THREADS = 128;
-constexpr int G_TILE_M = 128, G_TILE_N = 128, G_KCHUNK = 128, G_UMMA_K = 32, G_STAGES = 2;
+constexpr int G_TILE_M = 128, G_TILE_N = 128, G_KCHUNK = 128, G_UMMA_K = 32, G_STAGES = 6, G_PREFETCH = 4;
 constexpr uint32_t G_TILE_BYTES = G_TILE_M * G_KCHUNK;           // 16 KB
-constexpr uint32_t G_STAGE_BYTES = 5 * G_TILE_BYTES;             // A + 4 shifts of B
+constexpr uint32_t G_STAGE_BYTES = 2 * G_TILE_BYTES;             // A + B
 constexpr uint32_t G_TMEM_COLS = 512;
 
 // ---- B'_s operand ------------------------------------------------------------------------------------------
+// bmat[t][128*g + 32*b + e] = byte b of q_t[32*g + e]   (rows t >= nq are zero)
 __global__ void ipgemm_build_b_kernel(const uint32_t *queries, uint32_t nq, uint32_t q_pad, uint32_t dim, uint8_t *bmat) {
-    const uint64_t kbytes = (uint64_t)dim * 4, total = 4ull * q_pad * kbytes;
+    const uint64_t kbytes = (uint64_t)dim * 4, total = (uint64_t)q_pad * kbytes;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t kp = (uint32_t)(i % kbytes), a = kp & 3, j = kp >> 2;
-        const uint64_t row = i / kbytes;
-        const uint32_t s = (uint32_t)(row / q_pad), t = (uint32_t)(row % q_pad);
-        uint8_t v = 0;
-        if (t < nq && a <= s) v = (uint8_t)(queries[(uint64_t)t * dim + j] >> (8 * (s - a)));
-        bmat[i] = v;
+        const uint32_t kp = (uint32_t)(i % kbytes), t = (uint32_t)(i / kbytes);
+        const uint32_t g = kp >> 7, b = (kp >> 5) & 3, e = kp & 31;
+        bmat[i] = t < nq ? (uint8_t)(queries[(uint64_t)t * dim + 32 * g + e] >> (8 * b)) : (uint8_t)0;
     }
 }
 
@@ -100,6 +100,34 @@ struct GemmParams {
     int *error_flag;
 };
 
+// In-place limb sort of one 128-byte row of the A tile (32 uint32 elements): output 32-byte slice a = byte a of the
+// 32 elements.  The row is stored as eight 16-byte chunks, chunk c at physical position c ^ (row & 7) (128-byte swizzle).
+__device__ __forceinline__ void limb_sort_row(uint8_t *tile, uint32_t row) {
+    uint4 *rowp = reinterpret_cast<uint4 *>(tile + row * 128);
+    const uint32_t x = row & 7;
+    uint32_t w[32];
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+        const uint4 v = rowp[c ^ x];
+        w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {   // output chunk 2a + h holds limb a of elements 16h .. 16h+15
+            uint32_t o[4];
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const int e = 16 * h + 4 * m;
+                const uint32_t lo = __byte_perm(w[e], w[e + 1], 0x0040 + a * 0x0011);        // (w[e].b_a, w[e+1].b_a, -, -)
+                const uint32_t hi = __byte_perm(w[e + 2], w[e + 3], 0x0040 + a * 0x0011);
+                o[m] = __byte_perm(lo, hi, 0x5410);
+            }
+            rowp[(2 * a + h) ^ x] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b, const GemmParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -127,70 +155,77 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
     const uint32_t tmem_base = s_tmem_base;
     const uint32_t idesc = umma_idesc_u8(G_TILE_M, G_TILE_N);
 
-    uint32_t it = 0;          // K-chunk iterations issued so far by thread 0 (stage = it % 2, ring parity from it / 2)
+    // this CTA's work, flattened: iteration j = ((qt * my_tiles) + r) * k_chunks + kc,  row tile = blockIdx.x + r * gridDim.x
+    const uint32_t my_tiles = P.n_row_tiles > blockIdx.x ? (P.n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t per_qt = my_tiles * P.k_chunks, total = per_qt * P.n_q_tiles;
+    auto issue_tma = [&](uint32_t j) -> bool {   // thread 0 only
+        const uint32_t stage = j % G_STAGES, ring = (j / G_STAGES) & 1;
+        if (j >= (uint32_t)G_STAGES && !mbar_wait(&bar_empty[stage], ring ^ 1)) return false;
+        const uint32_t qt = j / per_qt, rem = j % per_qt, rt = blockIdx.x + (rem / P.k_chunks) * gridDim.x, kc = rem % P.k_chunks;
+        uint8_t *sa = smem + stage * G_STAGE_BYTES;
+        mbar_expect_tx(&bar_full[stage], G_STAGE_BYTES);
+        tma_load_2d(sa, &map_a, &bar_full[stage], (int32_t)(kc * G_KCHUNK), (int32_t)(rt * G_TILE_M));
+        tma_load_2d(sa + G_TILE_BYTES, &map_b, &bar_full[stage], (int32_t)(kc * G_KCHUNK), (int32_t)(qt * G_TILE_N));
+        return true;
+    };
+    if (threadIdx.x == 0)
+        for (uint32_t j = 0; j < (uint32_t)G_PREFETCH && j < total; j++)
+            if (!issue_tma(j)) s_abort = 1;
+    __syncthreads();
+
+    // The accumulators are NOT drained per row tile: D_s keeps accumulating over all row tiles of a query tile.  s32
+    // accumulation wraps mod 2^32 and only sum_i D_s[i][t] << 8s mod 2^32 is wanted, so the wrap is harmless, and the
+    // TMEM read-out (256 KB) happens once per query tile instead of once per (query tile, row tile).
     uint32_t accum_phase = 0;
-    for (uint32_t qt = 0; qt < P.n_q_tiles; qt++) {
-        uint32_t colsum[G_TILE_N];
-#pragma unroll
-        for (int j = 0; j < G_TILE_N; j++) colsum[j] = 0;
-        for (uint32_t rt = blockIdx.x; rt < P.n_row_tiles; rt += gridDim.x) {
-            if (threadIdx.x == 0 && !s_abort) {
-                for (uint32_t kc = 0; kc < P.k_chunks; kc++, it++) {
-                    const uint32_t stage = it % G_STAGES, ring = (it / G_STAGES) & 1;
-                    uint8_t *sa = smem + stage * G_STAGE_BYTES;
-                    if (it >= G_STAGES && !mbar_wait(&bar_empty[stage], ring ^ 1)) { s_abort = 1; break; }
-                    mbar_expect_tx(&bar_full[stage], G_STAGE_BYTES);
-                    tma_load_2d(sa, &map_a, &bar_full[stage], (int32_t)(kc * G_KCHUNK), (int32_t)(rt * G_TILE_M));
-                    for (uint32_t s = 0; s < 4; s++)
-                        tma_load_2d(sa + (1 + s) * G_TILE_BYTES, &map_b, &bar_full[stage], (int32_t)(kc * G_KCHUNK),
-                                    (int32_t)(s * P.q_pad + qt * G_TILE_N));
-                    if (!mbar_wait(&bar_full[stage], ring)) { s_abort = 2; break; }
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = smem_u32(sa);
-                    for (uint32_t s = 0; s < 4; s++) {
-                        const uint32_t b_addr = a_addr + (1 + s) * G_TILE_BYTES;
-#pragma unroll
-                        for (uint32_t k4 = 0; k4 < G_KCHUNK / G_UMMA_K; k4++)
-                            umma_i8(tmem_base + s * G_TILE_N, umma_desc_sw128(a_addr + k4 * G_UMMA_K), umma_desc_sw128(b_addr + k4 * G_UMMA_K),
-                                    idesc, (kc | k4) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(&bar_empty[stage]);   // the stage may be refilled once these MMAs have read it
-                }
-                umma_commit(&bar_accum);              // all MMAs of this (query tile, row tile) have landed in TMEM
-            }
-            __syncthreads();
-            if (s_abort) break;
-            if (!mbar_wait(&bar_accum, accum_phase)) s_abort = 3;
-            accum_phase ^= 1;
+    for (uint32_t j = 0; j < total; j++) {
+        const uint32_t stage = j % G_STAGES, ring = (j / G_STAGES) & 1, rem = j % per_qt;
+        uint8_t *sa = smem + stage * G_STAGE_BYTES;
+        if (threadIdx.x == 0 && j + G_PREFETCH < total && !issue_tma(j + G_PREFETCH)) s_abort = 1;
+        if (!mbar_wait(&bar_full[stage], ring)) s_abort = 2;
+        limb_sort_row(sa, threadIdx.x);                                     // generic-proxy writes to the A tile ...
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // ... made visible to the tensor core's async proxy
+        __syncthreads();
+        if (s_abort) break;   // uniform: every writer of s_abort wrote before the barrier
+        if (threadIdx.x == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            // epilogue: thread = TMEM lane = row of the tile; fold the four shifted accumulators, add into the column sums
-            if (!s_abort) {
-                const uint32_t lane_addr = tmem_base + ((warp * 32u) << 16);
+            const uint32_t a_addr = smem_u32(sa), b_addr = a_addr + G_TILE_BYTES;
 #pragma unroll
-                for (int c0 = 0; c0 < G_TILE_N; c0 += 16) {
-                    uint32_t d0[16], d1[16], d2[16], d3[16];
-                    tmem_ld16(lane_addr + 0 * G_TILE_N + c0, d0);
-                    tmem_ld16(lane_addr + 1 * G_TILE_N + c0, d1);
-                    tmem_ld16(lane_addr + 2 * G_TILE_N + c0, d2);
-                    tmem_ld16(lane_addr + 3 * G_TILE_N + c0, d3);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            for (uint32_t a = 0; a < 4; a++)
 #pragma unroll
-                    for (int j = 0; j < 16; j++) colsum[c0 + j] += d0[j] + (d1[j] << 8) + (d2[j] << 16) + (d3[j] << 24);
+                for (uint32_t b = 0; a + b < 4; b++)   // limb pair (a, b) accumulates into D_{a+b}; the first pair of a shift is a = 0
+                    umma_i8(tmem_base + (a + b) * G_TILE_N, umma_desc_sw128(a_addr + a * G_UMMA_K), umma_desc_sw128(b_addr + b * G_UMMA_K),
+                            idesc, (rem != 0 || a != 0) ? 1u : 0u);
+            umma_commit(&bar_empty[stage]);                 // the stage may be refilled once these MMAs have read it
+            if (rem + 1 == per_qt) umma_commit(&bar_accum); // every MMA of this query tile has landed in TMEM
+        }
+        if (rem + 1 != per_qt) continue;
+        // ---- end of a query tile: fold the four shifted accumulators, sum over the rows, publish ----
+        if (!mbar_wait(&bar_accum, accum_phase)) s_abort = 3;
+        accum_phase ^= 1;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!s_abort) {  // thread = TMEM lane; warp w owns lanes 32w..32w+31
+            const uint32_t lane_addr = tmem_base + ((warp * 32u) << 16), qt = j / per_qt;
+#pragma unroll 1
+            for (int c0 = 0; c0 < G_TILE_N; c0 += 16) {
+                uint32_t d0[16], d1[16], d2[16], d3[16];
+                tmem_ld16(lane_addr + 0 * G_TILE_N + c0, d0);
+                tmem_ld16(lane_addr + 1 * G_TILE_N + c0, d1);
+                tmem_ld16(lane_addr + 2 * G_TILE_N + c0, d2);
+                tmem_ld16(lane_addr + 3 * G_TILE_N + c0, d3);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int e = 0; e < 16; e++) {
+                    uint32_t v = d0[e] + (d1[e] << 8) + (d2[e] << 16) + (d3[e] << 24);
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && v) atomicAdd(P.checksum + qt * G_TILE_N + c0 + e, v);
                 }
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncthreads();   // TMEM is overwritten by the next row tile's first MMA
-            if (s_abort) break;
         }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();   // TMEM is overwritten by the next query tile's first MMAs
         if (s_abort) break;
-        // column sums over the 128 rows held by the 128 threads: warp shuffle tree, then one atomic per warp and column
-#pragma unroll
-        for (int j = 0; j < G_TILE_N; j++) {
-            uint32_t v = colsum[j];
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0 && v) atomicAdd(P.checksum + qt * G_TILE_N + j, v);
-        }
     }
+    __syncthreads();
     if (s_abort && threadIdx.x == 0) atomicExch(P.error_flag, s_abort);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -229,22 +264,22 @@ bool ipgemm_applicable(const pm_db *db, uint64_t dim, uint64_t nq, const uint32_
 }
 
 // checksum[t] = sum_i InnerProduct(row_i, q_t) mod 2^32 for all nq queries; `scratch_dev` must hold
-// 4*q_pad*dim*4 bytes (B') + q_pad*4 (padded checksums) + 16.  Enqueues on st; *err_host is valid after a sync.
+// q_pad*dim*4 bytes (limb-sorted queries) + q_pad*4 (padded checksums) + 16.  Enqueues on st; *err_host is valid after a sync.
 int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq, uint32_t *checksum, void *scratch_dev, cudaStream_t st) {
     const uint32_t q_pad = (uint32_t)((nq + G_TILE_N - 1) / G_TILE_N * G_TILE_N);
     const uint64_t kbytes = dim * 4;
     uint8_t *bmat = (uint8_t *)scratch_dev;
-    uint32_t *cs_pad = (uint32_t *)(bmat + 4ull * q_pad * kbytes);
+    uint32_t *cs_pad = (uint32_t *)(bmat + (uint64_t)q_pad * kbytes);
     int *err = (int *)(cs_pad + q_pad);
     PM_CUDA(cudaMemsetAsync(cs_pad, 0, (size_t)q_pad * 4 + 16, st));
-    ipgemm_build_b_kernel<<<(unsigned)std::min<uint64_t>((4ull * q_pad * kbytes + 255) / 256, 148 * 16), 256, 0, st>>>(queries, (uint32_t)nq, q_pad,
+    ipgemm_build_b_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)q_pad * kbytes + 255) / 256, 148 * 16), 256, 0, st>>>(queries, (uint32_t)nq, q_pad,
                                                                                                                   (uint32_t)dim, bmat);
     PM_CHECK_LAUNCH();
     count_launch();
     CUtensorMap map_a, map_b;
     int rc;
     if ((rc = make_map(&map_a, db->d_rows, db->n_rows, kbytes))) return rc;
-    if ((rc = make_map(&map_b, bmat, 4ull * q_pad, kbytes))) return rc;
+    if ((rc = make_map(&map_b, bmat, q_pad, kbytes))) return rc;
     GemmParams P;
     P.n_rows = db->n_rows;
     P.n_row_tiles = (uint32_t)((db->n_rows + G_TILE_M - 1) / G_TILE_M);
@@ -264,13 +299,13 @@ int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq
 }
 size_t ipgemm_scratch_bytes(uint64_t dim, uint64_t nq) {
     const uint64_t q_pad = (nq + G_TILE_N - 1) / G_TILE_N * G_TILE_N;
-    return 4ull * q_pad * dim * 4 + q_pad * 4 + 64;
+    return q_pad * dim * 4 + q_pad * 4 + 64;
 }
 // reads the error flag written by the kernel (after the stream has been synchronised)
 int ipgemm_check(void *scratch_dev, uint64_t dim, uint64_t nq) {
     const uint64_t q_pad = (nq + G_TILE_N - 1) / G_TILE_N * G_TILE_N;
     int err = 0;
-    PM_CUDA(cudaMemcpy(&err, (uint8_t *)scratch_dev + 4ull * q_pad * dim * 4 + q_pad * 4, 4, cudaMemcpyDeviceToHost));
+    PM_CUDA(cudaMemcpy(&err, (uint8_t *)scratch_dev + q_pad * dim * 4 + q_pad * 4, 4, cudaMemcpyDeviceToHost));
     if (err) return set_error(PM_ERR_CUDA, "ip gemm: tensor-core pipeline timed out (code %d)", err);
     return PM_OK;
 }

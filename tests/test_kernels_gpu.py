@@ -426,3 +426,20 @@ def test_ip_scan_tensor_core_path_matches_oracle(cabi, oracle, n, d, nq):
     got2, _ = cabi.ip_u32_scan(db, d, qs[:70], want_products=True)
     assert (got2 == got[:70]).all()
     db.close()
+
+
+def test_ip_scan_tensor_core_accumulators_wrap_harmlessly(cabi, oracle):
+    """The tensor-core scan never drains its s32 accumulators between row tiles; with all-ones limbs each CTA's
+    accumulators wrap past 2^31 many times over (several hundred tiles per CTA), and the checksums must still be exact."""
+    n, d, nq = 6_000_000, 32, 64
+    rows = np.full((n, d), 0xFFFFFFFF, np.uint32)
+    rows[::7, ::3] = np.random.default_rng(5).integers(0, 2**32, rows[::7, ::3].shape, dtype=np.uint32)
+    qs = np.full((nq, d), 0xFFFFFFFF, np.uint32)
+    qs[1::2] = np.random.default_rng(6).integers(0, 2**32, qs[1::2].shape, dtype=np.uint32)
+    db = cabi.DB(rows.view(np.uint64).reshape(n, d // 2))
+    got = cabi.ip_u32_scan(db, d, qs)
+    want = oracle.ip_scan(rows, qs[:8], threads=8)            # CPU oracle on the first queries ...
+    assert (got[:8] == want).all()
+    got_int, _ = cabi.ip_u32_scan(db, d, qs[:48], want_products=True)   # ... and the integer-pipe kernel on 48 of them
+    assert (got[:48] == got_int).all()
+    db.close()
