@@ -9,16 +9,24 @@
 // kernel: the epilogue folds the four accumulators and sums over rows.
 //
 // Operands.  The row table is consumed AS IT LIES IN MEMORY: TMA drops 128 rows x 128 B (32 elements per row) into
-// shared memory, and each thread then sorts the bytes of its row by limb in place -- [limb 0 of 32 elements | limb 1 |
-// limb 2 | limb 3], 32 B each -- so that every UMMA K = 32 slice of the 128-byte swizzled row is one pure limb plane.
-// The query operand is written limb-sorted the same way by a small kernel ([Q][4*dim] bytes, one copy).  Limb pair
-// (a, b) is then the MMA of A slice a with B slice b of the same 128-byte chunk: 10 MMAs per chunk.
+// shared memory; each sorter thread reads its row, sorts the bytes by limb in registers -- [limb 0 of the 32 elements |
+// limb 1 | limb 2 | limb 3], 32 B each -- and stores them with tcgen05.st into its TMEM lane: the MMA takes A FROM
+// TMEM (lane = row, four K bytes per 32-bit column, 8 columns per K = 32 slice).  The query operand is written
+// limb-sorted the same way by a small kernel ([Q][4*dim] bytes, one copy) and staged by TMA in shared memory.  Limb
+// pair (a, b) is then the MMA of A slice a with B slice b of the same 128-byte chunk: 10 MMAs per chunk.
 //
-// Kernel: one persistent CTA per SM, 128 threads.  Thread 0 is TMA producer (4 chunks ahead in a 6-stage mbarrier
-// ring of 16 KB A + 16 KB B) and tcgen05.mma issuer (single-thread instruction, M128 N128 K32, kind::i8, both operands
-// K-major with the 128-byte swizzle the tensor maps write); the four accumulators fill all 512 TMEM columns; all four
-// warps sort limbs and are the epilogue (warp w reads TMEM lanes 32w..32w+31 = rows of the tile).  Every mbarrier
-// wait is bounded: on a timeout the kernel raises an error flag and drains instead of hanging.
+// Why A lives in TMEM: with both operands in shared memory an M128 N128 K32 MMA reads 8 KB for 64 clk of math, i.e.
+// the whole 128 B/clk of the SM's shared memory, and the TMA fills and the limb sort come on top (measured: 1240 clk
+// per chunk against 640 of math).  With A in TMEM the shared-memory traffic per chunk drops from 144 KB to 81 KB.
+// TMEM budget: 4 accumulators x 112 columns + 2 A buffers x 32 columns = 512, hence the query tile of 112.
+//
+// Kernel: one persistent CTA per SM, warp-specialised.  One thread of the TMA warp is the producer of a 6-stage
+// mbarrier ring (16 KB A + 14 KB B per stage); two groups of four warps sort the limbs of alternate A tiles as they
+// land (thread = row = TMEM lane) and signal `sorted`; one thread of the MMA warp issues the tcgen05.mma (M128 N112
+// K32, kind::i8, B K-major with the 128-byte swizzle the tensor map writes) and commits `empty`, which releases both
+// the stage to the producer and the A buffer to its sorter group.  Warps 0-3 are also the epilogue (warp w reads TMEM
+// lanes 32w..32w+31 = rows of the tile) once per query tile.  Every mbarrier wait is bounded: on a timeout the kernel
+// raises an error flag and drains instead of hanging.
 #include <cuda.h>
 
 #include <algorithm>
@@ -28,11 +36,15 @@
 
 namespace pm {
 
-constexpr int G_THREADS = 128;
-constexpr int G_TILE_M = 128, G_TILE_N = 128, G_KCHUNK = 128, G_UMMA_K = 32, G_STAGES = 6, G_PREFETCH = 4;
-constexpr uint32_t G_TILE_BYTES = G_TILE_M * G_KCHUNK;           // 16 KB
-constexpr uint32_t G_STAGE_BYTES = 2 * G_TILE_BYTES;             // A + B
+constexpr int G_SORT_GROUPS = 2, G_SORTERS = 128;   // sorter group g = warps 4g..4g+3 takes chunks j = g (mod G_SORT_GROUPS)
+constexpr int G_WARP_TMA = 4 * G_SORT_GROUPS, G_WARP_MMA = G_WARP_TMA + 1, G_THREADS = 32 * (G_WARP_MMA + 1);
+constexpr int G_TILE_M = 128, G_TILE_N = 112, G_KCHUNK = 128, G_UMMA_K = 32, G_MAX_STAGES = 8;
+constexpr uint32_t G_TILE_BYTES = G_TILE_M * G_KCHUNK;           // A tile, 16 KB
+constexpr uint32_t G_BTILE_BYTES = G_TILE_N * G_KCHUNK;          // B tile, 14 KB
+constexpr uint32_t G_STAGE_BYTES = 2 * G_TILE_BYTES;             // A + B (B padded so that every tile stays 1024-byte aligned)
 constexpr uint32_t G_TMEM_COLS = 512;
+constexpr uint32_t G_TMEM_A = 4 * G_TILE_N;                      // columns 448..511: two limb-sorted A tiles of 4 x 8 columns
+static_assert(G_TMEM_A + 2 * 32 <= G_TMEM_COLS, "accumulators + two A buffers must fit TMEM");
 
 // ---- B'_s operand ------------------------------------------------------------------------------------------
 // bmat[t][128*g + 32*b + e] = byte b of q_t[32*g + e]   (rows t >= nq are zero)
@@ -54,16 +66,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // bounded wait: false on timeout (~2 s), so a programming error can never hang the GPU
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+    if (mbar_try(addr, parity)) return true;
     const long long t0 = clock64();
-    for (;;) {
-        uint32_t done;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-        if (done) return true;
+    while (!mbar_try(addr, parity))
         if (clock64() - t0 > 4000000000ll) return false;
-    }
+    return true;
+}
+// one lane of a converged warp (the warp stays convergent, so the compiler keeps descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int32_t x, int32_t y) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -78,10 +99,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 __device__ __forceinline__ uint32_t umma_idesc_u8(int m, int n) {
     return (2u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// A operand from TMEM (lane = row, 4 bytes of K per 32-bit column), B operand from shared memory
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
-                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -93,17 +115,30 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+                 "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+                   "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+                   "r"(r[30]), "r"(r[31]) : "memory");
+}
+
 struct GemmParams {
     uint64_t n_rows;
     uint32_t n_row_tiles, n_q_tiles, q_pad, k_chunks;
-    uint32_t *checksum;   // [q_pad]
+    uint32_t q_slots, groups;       // CTA b works on query tiles b % q_slots (+ q_slots, ...) and row tiles b / q_slots (+ groups, ...)
+    uint32_t n_stages, stage_bytes; // A ring (16 KB stages) when the B tile is resident, A + B ring (32 KB stages) otherwise
+    uint32_t b_resident;            // bytes of the resident B tile (k_chunks * G_BTILE_BYTES) or 0
+    uint32_t *checksum;             // [q_pad]
     int *error_flag;
 };
 
-// In-place limb sort of one 128-byte row of the A tile (32 uint32 elements): output 32-byte slice a = byte a of the
-// 32 elements.  The row is stored as eight 16-byte chunks, chunk c at physical position c ^ (row & 7) (128-byte swizzle).
-__device__ __forceinline__ void limb_sort_row(uint8_t *tile, uint32_t row) {
-    uint4 *rowp = reinterpret_cast<uint4 *>(tile + row * 128);
+// Limb sort of one 128-byte row of the A tile (32 uint32 elements) into registers: out[8a .. 8a+7] = byte a of the 32
+// elements, in element order.  The row is stored as eight 16-byte chunks, chunk c at physical position c ^ (row & 7)
+// (the 128-byte swizzle TMA wrote).
+__device__ __forceinline__ void limb_sort_row(const uint8_t *tile, uint32_t row, uint32_t (&out)[32]) {
+    const uint4 *rowp = reinterpret_cast<const uint4 *>(tile + row * 128);
     const uint32_t x = row & 7;
     uint32_t w[32];
 #pragma unroll
@@ -112,34 +147,36 @@ __device__ __forceinline__ void limb_sort_row(uint8_t *tile, uint32_t row) {
         w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
     }
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
+    for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int h = 0; h < 2; h++) {   // output chunk 2a + h holds limb a of elements 16h .. 16h+15
-            uint32_t o[4];
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
-                const int e = 16 * h + 4 * m;
-                const uint32_t lo = __byte_perm(w[e], w[e + 1], 0x0040 + a * 0x0011);        // (w[e].b_a, w[e+1].b_a, -, -)
-                const uint32_t hi = __byte_perm(w[e + 2], w[e + 3], 0x0040 + a * 0x0011);
-                o[m] = __byte_perm(lo, hi, 0x5410);
-            }
-            rowp[(2 * a + h) ^ x] = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int m = 0; m < 8; m++) {
+            const int e = 4 * m;
+            const uint32_t lo = __byte_perm(w[e], w[e + 1], 0x0040 + a * 0x0011);        // (w[e].b_a, w[e+1].b_a, -, -)
+            const uint32_t hi = __byte_perm(w[e + 2], w[e + 3], 0x0040 + a * 0x0011);
+            out[8 * a + m] = __byte_perm(lo, hi, 0x5410);
         }
-    }
 }
 
 __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                               const __grid_constant__ CUtensorMap map_b, const GemmParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t bar_full[G_STAGES], bar_empty[G_STAGES], bar_accum;
+    uint8_t *smem_b = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_b + P.b_resident;   // the ring
+    __shared__ uint64_t bar_full[G_MAX_STAGES], bar_sorted[G_MAX_STAGES], bar_empty[G_MAX_STAGES], bar_accum, bar_tmem_free, bar_b, bar_b_free;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < G_STAGES; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < G_MAX_STAGES; i++) {
+            mbar_init(&bar_full[i], 1);
+            mbar_init(&bar_sorted[i], G_SORTERS);
+            mbar_init(&bar_empty[i], 1);
+        }
         mbar_init(&bar_accum, 1);
+        mbar_init(&bar_tmem_free, G_SORTERS);
+        mbar_init(&bar_b, 1);
+        mbar_init(&bar_b_free, 1);
         s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -153,58 +190,111 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = s_tmem_base;
-    const uint32_t idesc = umma_idesc_u8(G_TILE_M, G_TILE_N);
 
-    // this CTA's work, flattened: iteration j = ((qt * my_tiles) + r) * k_chunks + kc,  row tile = blockIdx.x + r * gridDim.x
-    const uint32_t my_tiles = P.n_row_tiles > blockIdx.x ? (P.n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t per_qt = my_tiles * P.k_chunks, total = per_qt * P.n_q_tiles;
-    auto issue_tma = [&](uint32_t j) -> bool {   // thread 0 only
-        const uint32_t stage = j % G_STAGES, ring = (j / G_STAGES) & 1;
-        if (j >= (uint32_t)G_STAGES && !mbar_wait(&bar_empty[stage], ring ^ 1)) return false;
-        const uint32_t qt = j / per_qt, rem = j % per_qt, rt = blockIdx.x + (rem / P.k_chunks) * gridDim.x, kc = rem % P.k_chunks;
-        uint8_t *sa = smem + stage * G_STAGE_BYTES;
-        mbar_expect_tx(&bar_full[stage], G_STAGE_BYTES);
-        tma_load_2d(sa, &map_a, &bar_full[stage], (int32_t)(kc * G_KCHUNK), (int32_t)(rt * G_TILE_M));
-        tma_load_2d(sa + G_TILE_BYTES, &map_b, &bar_full[stage], (int32_t)(kc * G_KCHUNK), (int32_t)(qt * G_TILE_N));
-        return true;
-    };
-    if (threadIdx.x == 0)
-        for (uint32_t j = 0; j < (uint32_t)G_PREFETCH && j < total; j++)
-            if (!issue_tma(j)) s_abort = 1;
-    __syncthreads();
-
+    // This CTA's work.  CTAs that share b / q_slots sweep the SAME row tiles at the same pace, each against its own
+    // query tile, so a row tile comes from HBM once and from L2 for the other q_slots - 1 readers; the query tile of a
+    // CTA stays resident in shared memory for the whole sweep when it fits.  Flattened iteration
+    // j = ((qi * my_tiles) + r) * k_chunks + kc,  query tile = slot + qi * q_slots,  row tile = rg + r * groups.
     // The accumulators are NOT drained per row tile: D_s keeps accumulating over all row tiles of a query tile.  s32
     // accumulation wraps mod 2^32 and only sum_i D_s[i][t] << 8s mod 2^32 is wanted, so the wrap is harmless, and the
-    // TMEM read-out (256 KB) happens once per query tile instead of once per (query tile, row tile).
-    uint32_t accum_phase = 0;
-    for (uint32_t j = 0; j < total; j++) {
-        const uint32_t stage = j % G_STAGES, ring = (j / G_STAGES) & 1, rem = j % per_qt;
-        uint8_t *sa = smem + stage * G_STAGE_BYTES;
-        if (threadIdx.x == 0 && j + G_PREFETCH < total && !issue_tma(j + G_PREFETCH)) s_abort = 1;
-        if (!mbar_wait(&bar_full[stage], ring)) s_abort = 2;
-        limb_sort_row(sa, threadIdx.x);                                     // generic-proxy writes to the A tile ...
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // ... made visible to the tensor core's async proxy
-        __syncthreads();
-        if (s_abort) break;   // uniform: every writer of s_abort wrote before the barrier
-        if (threadIdx.x == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_addr = smem_u32(sa), b_addr = a_addr + G_TILE_BYTES;
-#pragma unroll
-            for (uint32_t a = 0; a < 4; a++)
-#pragma unroll
-                for (uint32_t b = 0; a + b < 4; b++)   // limb pair (a, b) accumulates into D_{a+b}; the first pair of a shift is a = 0
-                    umma_i8(tmem_base + (a + b) * G_TILE_N, umma_desc_sw128(a_addr + a * G_UMMA_K), umma_desc_sw128(b_addr + b * G_UMMA_K),
-                            idesc, (rem != 0 || a != 0) ? 1u : 0u);
-            umma_commit(&bar_empty[stage]);                 // the stage may be refilled once these MMAs have read it
-            if (rem + 1 == per_qt) umma_commit(&bar_accum); // every MMA of this query tile has landed in TMEM
+    // TMEM read-out (224 KB) happens once per query tile instead of once per (query tile, row tile).
+    const uint32_t slot = blockIdx.x % P.q_slots, rg = blockIdx.x / P.q_slots;
+    const uint32_t my_tiles = P.n_row_tiles > rg ? (P.n_row_tiles - rg + P.groups - 1) / P.groups : 0;
+    const uint32_t my_qts = P.n_q_tiles > slot ? (P.n_q_tiles - slot + P.q_slots - 1) / P.q_slots : 0;
+    const uint32_t per_qt = my_tiles * P.k_chunks, total = per_qt * my_qts;
+    const uint32_t n_stages = P.n_stages;
+    volatile int *abort_flag = &s_abort;
+
+    if (warp == G_WARP_TMA) {
+        // ---- TMA producer: the warp runs the loop convergently, one elected lane issues ----
+        uint32_t qi = 0, r = 0, kc = 0, stage = 0, ring = 0;
+        for (uint32_t j = 0; j < total; j++) {
+            const int32_t q_row = (int32_t)((slot + qi * P.q_slots) * G_TILE_N);
+            if (P.b_resident && r == 0 && kc == 0) {   // (re)load this CTA's query tile: all K chunks, one barrier
+                if (qi > 0 && !mbar_wait(&bar_b_free, (qi - 1) & 1)) { *abort_flag = 7; break; }
+                if (elect_one()) {
+                    mbar_expect_tx(&bar_b, P.b_resident);
+                    for (uint32_t c = 0; c < P.k_chunks; c++)
+                        tma_load_2d(smem_b + c * G_BTILE_BYTES, &map_b, &bar_b, (int32_t)(c * G_KCHUNK), q_row);
+                }
+                __syncwarp();
+            }
+            if (j >= n_stages && !mbar_wait(&bar_empty[stage], ring ^ 1)) { *abort_flag = 1; break; }
+            if (elect_one()) {
+                uint8_t *sa = smem + stage * P.stage_bytes;
+                mbar_expect_tx(&bar_full[stage], P.b_resident ? G_TILE_BYTES : G_TILE_BYTES + G_BTILE_BYTES);
+                tma_load_2d(sa, &map_a, &bar_full[stage], (int32_t)(kc * G_KCHUNK), (int32_t)((rg + r * P.groups) * G_TILE_M));
+                if (!P.b_resident) tma_load_2d(sa + G_TILE_BYTES, &map_b, &bar_full[stage], (int32_t)(kc * G_KCHUNK), q_row);
+            }
+            __syncwarp();
+            if (++kc == P.k_chunks) { kc = 0; if (++r == my_tiles) { r = 0; qi++; } }
+            if (++stage == n_stages) { stage = 0; ring ^= 1; }
         }
-        if (rem + 1 != per_qt) continue;
-        // ---- end of a query tile: fold the four shifted accumulators, sum over the rows, publish ----
-        if (!mbar_wait(&bar_accum, accum_phase)) s_abort = 3;
-        accum_phase ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (!s_abort) {  // thread = TMEM lane; warp w owns lanes 32w..32w+31
-            const uint32_t lane_addr = tmem_base + ((warp * 32u) << 16), qt = j / per_qt;
+    } else if (warp == G_WARP_MMA) {
+        // ---- MMA issuer: the warp runs the loop convergently, one elected lane issues 10 tcgen05.mma per sorted chunk ----
+        const uint32_t idesc = umma_idesc_u8(G_TILE_M, G_TILE_N);
+        uint32_t rem = 0, kc = 0, qi = 0, stage = 0, ring = 0;
+        for (uint32_t j = 0; j < total; j++) {
+            if (!mbar_wait(&bar_sorted[stage], ring) || !mbar_wait(&bar_full[stage], ring)) { *abort_flag = 2; break; }
+            if (rem == 0) {
+                if (P.b_resident && !mbar_wait(&bar_b, qi & 1)) { *abort_flag = 8; break; }
+                // the epilogue of the previous query tile must have read TMEM out
+                if (qi > 0 && !mbar_wait(&bar_tmem_free, (qi - 1) & 1)) { *abort_flag = 4; break; }
+            }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_tmem = tmem_base + G_TMEM_A + (j % G_SORT_GROUPS) * 32;
+            const uint32_t b_addr = P.b_resident ? smem_u32(smem_b + kc * G_BTILE_BYTES) : smem_u32(smem + stage * P.stage_bytes) + G_TILE_BYTES;
+            const bool last = rem + 1 == per_qt;
+            if (elect_one()) {
+#pragma unroll
+                for (uint32_t a = 0; a < 4; a++)
+#pragma unroll
+                    for (uint32_t b = 0; a + b < 4; b++)   // limb pair (a, b) accumulates into D_{a+b}; the first pair of a shift is a = 0
+                        umma_i8_ts(tmem_base + (a + b) * G_TILE_N, a_tmem + a * 8, umma_desc_sw128(b_addr + b * G_UMMA_K), idesc,
+                                   (rem != 0 || a != 0) ? 1u : 0u);
+                umma_commit(&bar_empty[stage]);   // the stage may be refilled and the A buffer rewritten once these MMAs have read them
+                if (last) {                       // every MMA of this query tile has landed; its B tile may be replaced
+                    umma_commit(&bar_accum);
+                    if (P.b_resident) umma_commit(&bar_b_free);
+                }
+            }
+            __syncwarp();
+            if (++kc == P.k_chunks) kc = 0;
+            if (last) { rem = 0; qi++; } else rem++;
+            if (++stage == n_stages) { stage = 0; ring ^= 1; }
+        }
+    } else {
+        // ---- limb sorters (thread = row of the A tile = TMEM lane) and epilogue ----
+        // group g sorts chunks j = g (mod G_SORT_GROUPS); group 0 is also the epilogue
+        const uint32_t group = warp >> 2, row = threadIdx.x & (G_SORTERS - 1);
+        const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16);
+        uint32_t rem = 0, qi = 0, stage = 0, ring = 0;
+        uint32_t pstage = 0, pring = 0;   // stage / ring of chunk j - G_SORT_GROUPS
+        for (uint32_t j = 0; j < total; j++) {
+            if (j % G_SORT_GROUPS == group) {
+                if (!mbar_wait(&bar_full[stage], ring)) { *abort_flag = 3; break; }
+                uint32_t limbs[32];
+                limb_sort_row(smem + stage * P.stage_bytes, row, limbs);
+                // this group's A buffer in TMEM was last read by the MMAs of chunk j - G_SORT_GROUPS
+                if (j >= (uint32_t)G_SORT_GROUPS) {
+                    if (!mbar_wait(&bar_empty[pstage], pring)) { *abort_flag = 6; break; }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                tmem_st32(lane_addr + G_TMEM_A + group * 32, limbs);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_sorted[stage])) : "memory");
+            }
+            if (j >= (uint32_t)G_SORT_GROUPS && ++pstage == n_stages) { pstage = 0; pring ^= 1; }
+            if (++stage == n_stages) { stage = 0; ring ^= 1; }
+            if (++rem != per_qt) continue;
+            rem = 0;
+            qi++;
+            if (group != 0) continue;
+            // end of a query tile: fold the four shifted accumulators, sum over the rows, publish
+            if (!mbar_wait(&bar_accum, (qi - 1) & 1)) { *abort_flag = 5; break; }
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t q0 = (slot + (qi - 1) * P.q_slots) * G_TILE_N;
 #pragma unroll 1
             for (int c0 = 0; c0 < G_TILE_N; c0 += 16) {
                 uint32_t d0[16], d1[16], d2[16], d3[16];
@@ -217,13 +307,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
                 for (int e = 0; e < 16; e++) {
                     uint32_t v = d0[e] + (d1[e] << 8) + (d2[e] << 16) + (d3[e] << 24);
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0 && v) atomicAdd(P.checksum + qt * G_TILE_N + c0 + e, v);
+                    if (lane == 0 && v) atomicAdd(P.checksum + q0 + c0 + e, v);
                 }
             }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_tmem_free)) : "memory");
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();   // TMEM is overwritten by the next query tile's first MMAs
-        if (s_abort) break;
     }
     __syncthreads();
     if (s_abort && threadIdx.x == 0) atomicExch(P.error_flag, s_abort);
@@ -246,11 +335,11 @@ static EncodeTiledFn get_encode() {
     }
     return fn;
 }
-static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t row_bytes) {
+static int make_map(CUtensorMap *m, const void *base, uint64_t rows, uint64_t row_bytes, uint32_t box_rows) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_error(PM_ERR_CUDA, "ip gemm: cuTensorMapEncodeTiled is not available");
     cuuint64_t dims[2] = {row_bytes, rows}, strides[1] = {row_bytes};
-    cuuint32_t box[2] = {G_KCHUNK, G_TILE_M}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {G_KCHUNK, box_rows}, estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(PM_ERR_CUDA, "ip gemm: cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -278,8 +367,8 @@ int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq
     count_launch();
     CUtensorMap map_a, map_b;
     int rc;
-    if ((rc = make_map(&map_a, db->d_rows, db->n_rows, kbytes))) return rc;
-    if ((rc = make_map(&map_b, bmat, q_pad, kbytes))) return rc;
+    if ((rc = make_map(&map_a, db->d_rows, db->n_rows, kbytes, G_TILE_M))) return rc;
+    if ((rc = make_map(&map_b, bmat, q_pad, kbytes, G_TILE_N))) return rc;
     GemmParams P;
     P.n_rows = db->n_rows;
     P.n_row_tiles = (uint32_t)((db->n_rows + G_TILE_M - 1) / G_TILE_M);
@@ -288,10 +377,34 @@ int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq
     P.k_chunks = (uint32_t)(kbytes / G_KCHUNK);
     P.checksum = cs_pad;
     P.error_flag = err;
-    const size_t smem = (size_t)G_STAGES * G_STAGE_BYTES + 1024;
+    // shared memory: the CTA's query tile resident (all K chunks) + a ring of A tiles, or a ring of A + B tiles
+    const size_t smem_avail = 227 * 1024 - 2048;
+    const size_t b_all = (size_t)P.k_chunks * G_BTILE_BYTES;
+    if (b_all + 4 * G_TILE_BYTES <= smem_avail) {
+        P.b_resident = (uint32_t)b_all;
+        P.stage_bytes = G_TILE_BYTES;
+        P.n_stages = (uint32_t)std::min<size_t>(G_MAX_STAGES, (smem_avail - b_all) / G_TILE_BYTES);
+    } else {
+        P.b_resident = 0;
+        P.stage_bytes = G_STAGE_BYTES;
+        P.n_stages = 6;
+    }
+    // CTA grid = q_slots x groups <= SMs.  The table is swept ceil(n_q_tiles / q_slots) times from HBM, so take the most
+    // query tiles side by side whose busiest CTA stays within 6 % of the fewest chunks any split achieves.
+    const uint32_t sms = (uint32_t)db->sm_count, qs_max = std::min(P.n_q_tiles, sms);
+    auto chunks_of = [&](uint32_t qs) {
+        const uint32_t g = std::max(1u, std::min(sms / qs, P.n_row_tiles));
+        return (uint64_t)((P.n_q_tiles + qs - 1) / qs) * ((P.n_row_tiles + g - 1) / g);
+    };
+    uint64_t best = ~0ull;
+    for (uint32_t qs = 1; qs <= qs_max; qs++) best = std::min(best, chunks_of(qs));
+    P.q_slots = 1;
+    for (uint32_t qs = 1; qs <= qs_max; qs++)
+        if (chunks_of(qs) * 100 <= best * 106) P.q_slots = qs;
+    P.groups = std::max(1u, std::min(sms / P.q_slots, P.n_row_tiles));
+    const size_t smem = (size_t)P.b_resident + (size_t)P.n_stages * P.stage_bytes + 1024;
     PM_CUDA(cudaFuncSetAttribute(ipgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)std::min<uint32_t>(P.n_row_tiles, (uint32_t)db->sm_count);
-    ipgemm_kernel<<<grid, G_THREADS, smem, st>>>(map_a, map_b, P);
+    ipgemm_kernel<<<P.q_slots * P.groups, G_THREADS, smem, st>>>(map_a, map_b, P);
     PM_CHECK_LAUNCH();
     count_launch();
     PM_CUDA(cudaMemcpyAsync(checksum, cs_pad, nq * 4, cudaMemcpyDeviceToDevice, st));

@@ -410,7 +410,10 @@ def test_hintgen_more_jobs_than_one_launch_holds(cabi, oracle):
     db.close()
 
 
-@pytest.mark.parametrize("n,d,nq", [(1000, 128, 64), (20001, 192, 200), (5000, 32, 130), (300, 64, 1000)])
+# (20001, 192, 200): query tile resident in shared memory, several CTA groups; (12000, 512, 300): 4*dim too large for a
+# resident query tile -> both operands streamed; (300, 32, 17000): more query tiles than SMs -> query tiles reloaded
+@pytest.mark.parametrize("n,d,nq", [(1000, 128, 64), (20001, 192, 200), (5000, 32, 130), (300, 64, 1000), (12000, 512, 300),
+                                    (300, 32, 17000), (129, 256, 113)])
 def test_ip_scan_tensor_core_path_matches_oracle(cabi, oracle, n, d, nq):
     """nq >= 64 and dim % 32 == 0 route the scan to the tcgen05 int8-limb GEMM (pm_ipgemm.cu); the checksums must
     still be the reference's wrapping uint32 sums, bit for bit, also for ragged row / query counts."""
