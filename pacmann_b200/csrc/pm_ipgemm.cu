@@ -17,12 +17,14 @@
 //
 // Why A lives in TMEM: with both operands in shared memory an M128 N128 K32 MMA reads 8 KB for 64 clk of math, i.e.
 // the whole 128 B/clk of the SM's shared memory, and the TMA fills and the limb sort come on top (measured: 1240 clk
-// per chunk against 640 of math).  With A in TMEM the shared-memory traffic per chunk drops from 144 KB to 81 KB.
-// TMEM budget: 4 accumulators x 112 columns + 2 A buffers x 32 columns = 512, hence the query tile of 112.
+// per chunk against 640 of math).  With A in TMEM the shared-memory traffic per chunk drops from 144 KB to 62 KB.
+// TMEM budget: 4 accumulators x 96 columns + 4 A buffers x 32 columns = 512, hence the query tile of 96.  Four A
+// buffers because refilling one waits for the MMAs that read it: with two, the chain "MMA done -> sorter wakes ->
+// tcgen05.st -> arrive -> issuer wakes" (~600 clk) was as long as one chunk of MMAs and the tensor pipe idled 35 %.
 //
 // Kernel: one persistent CTA per SM, warp-specialised.  One thread of the TMA warp is the producer of a 6-stage
-// mbarrier ring (16 KB A + 14 KB B per stage); two groups of four warps sort the limbs of alternate A tiles as they
-// land (thread = row = TMEM lane) and signal `sorted`; one thread of the MMA warp issues the tcgen05.mma (M128 N112
+// mbarrier ring (16 KB A, + 12 KB B when the query tile is streamed); two groups of four warps sort the limbs of alternate A tiles as they
+// land (thread = row = TMEM lane) and signal `sorted`; two MMA warps take alternate chunks and one thread of each issues the tcgen05.mma (M128 N96
 // K32, kind::i8, B K-major with the 128-byte swizzle the tensor map writes) and commits `empty`, which releases both
 // the stage to the producer and the A buffer to its sorter group.  Warps 0-3 are also the epilogue (warp w reads TMEM
 // lanes 32w..32w+31 = rows of the tile) once per query tile.  Every mbarrier wait is bounded: on a timeout the kernel
@@ -37,14 +39,18 @@
 namespace pm {
 
 constexpr int G_SORT_GROUPS = 2, G_SORTERS = 128;   // sorter group g = warps 4g..4g+3 takes chunks j = g (mod G_SORT_GROUPS)
-constexpr int G_WARP_TMA = 4 * G_SORT_GROUPS, G_WARP_MMA = G_WARP_TMA + 1, G_THREADS = 32 * (G_WARP_MMA + 1);
-constexpr int G_TILE_M = 128, G_TILE_N = 112, G_KCHUNK = 128, G_UMMA_K = 32, G_MAX_STAGES = 8;
+constexpr int G_WARP_TMA = 4 * G_SORT_GROUPS, G_WARP_MMA = G_WARP_TMA + 1, G_ISSUERS = 2, G_THREADS = 32 * (G_WARP_MMA + G_ISSUERS);
+#ifndef PM_G_TILE_N
+#define PM_G_TILE_N 96
+#define PM_G_ABUFS 4
+#endif
+constexpr int G_TILE_M = 128, G_TILE_N = PM_G_TILE_N, G_KCHUNK = 128, G_UMMA_K = 32, G_MAX_STAGES = 8, G_ABUFS = PM_G_ABUFS;
 constexpr uint32_t G_TILE_BYTES = G_TILE_M * G_KCHUNK;           // A tile, 16 KB
-constexpr uint32_t G_BTILE_BYTES = G_TILE_N * G_KCHUNK;          // B tile, 14 KB
+constexpr uint32_t G_BTILE_BYTES = G_TILE_N * G_KCHUNK;          // B tile, 12 KB
 constexpr uint32_t G_STAGE_BYTES = 2 * G_TILE_BYTES;             // A + B (B padded so that every tile stays 1024-byte aligned)
 constexpr uint32_t G_TMEM_COLS = 512;
-constexpr uint32_t G_TMEM_A = 4 * G_TILE_N;                      // columns 448..511: two limb-sorted A tiles of 4 x 8 columns
-static_assert(G_TMEM_A + 2 * 32 <= G_TMEM_COLS, "accumulators + two A buffers must fit TMEM");
+constexpr uint32_t G_TMEM_A = 4 * G_TILE_N;                      // columns 384..511: four limb-sorted A tiles of 4 x 8 columns
+static_assert(G_TMEM_A + G_ABUFS * 32 <= G_TMEM_COLS, "accumulators + A buffers must fit TMEM");
 
 // ---- B'_s operand ------------------------------------------------------------------------------------------
 // bmat[t][128*g + 32*b + e] = byte b of q_t[32*g + e]   (rows t >= nq are zero)
@@ -132,7 +138,14 @@ struct GemmParams {
     uint32_t b_resident;            // bytes of the resident B tile (k_chunks * G_BTILE_BYTES) or 0
     uint32_t *checksum;             // [q_pad]
     int *error_flag;
+    unsigned long long *trace;      // debug build (-DPM_IPGEMM_TRACE): per-chunk clock stamps of CTA 0, else unused
 };
+#ifdef PM_IPGEMM_TRACE
+#define G_TRACE_N 512
+#define G_TRACE(role, j) do { if (blockIdx.x == 0 && (j) < G_TRACE_N && (threadIdx.x & 31) == 0) P.trace[(role) * G_TRACE_N + (j)] = clock64(); } while (0)
+#else
+#define G_TRACE(role, j) do { } while (0)
+#endif
 
 // Limb sort of one 128-byte row of the A tile (32 uint32 elements) into registers: out[8a .. 8a+7] = byte a of the 32
 // elements, in element order.  The row is stored as eight 16-byte chunks, chunk c at physical position c ^ (row & 7)
@@ -162,7 +175,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem_b = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem = smem_b + P.b_resident;   // the ring
-    __shared__ uint64_t bar_full[G_MAX_STAGES], bar_sorted[G_MAX_STAGES], bar_empty[G_MAX_STAGES], bar_accum, bar_tmem_free, bar_b, bar_b_free;
+    __shared__ uint64_t bar_full[G_MAX_STAGES], bar_sorted[G_MAX_STAGES], bar_empty[G_MAX_STAGES], bar_accum, bar_tmem_free, bar_b, bar_b_free, bar_first;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
     const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
@@ -173,10 +186,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
             mbar_init(&bar_sorted[i], G_SORTERS);
             mbar_init(&bar_empty[i], 1);
         }
-        mbar_init(&bar_accum, 1);
+        mbar_init(&bar_accum, G_ISSUERS);
         mbar_init(&bar_tmem_free, G_SORTERS);
         mbar_init(&bar_b, 1);
-        mbar_init(&bar_b_free, 1);
+        mbar_init(&bar_b_free, G_ISSUERS);
+        mbar_init(&bar_first, 1);
         s_abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -220,6 +234,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
                 __syncwarp();
             }
             if (j >= n_stages && !mbar_wait(&bar_empty[stage], ring ^ 1)) { *abort_flag = 1; break; }
+            G_TRACE(0, j);
             if (elect_one()) {
                 uint8_t *sa = smem + stage * P.stage_bytes;
                 mbar_expect_tx(&bar_full[stage], P.b_resident ? G_TILE_BYTES : G_TILE_BYTES + G_BTILE_BYTES);
@@ -230,37 +245,60 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
             if (++kc == P.k_chunks) { kc = 0; if (++r == my_tiles) { r = 0; qi++; } }
             if (++stage == n_stages) { stage = 0; ring ^= 1; }
         }
-    } else if (warp == G_WARP_MMA) {
-        // ---- MMA issuer: the warp runs the loop convergently, one elected lane issues 10 tcgen05.mma per sorted chunk ----
+    } else if (warp >= G_WARP_MMA) {
+        // ---- MMA issuers: two warps take alternate chunks of a query tile; each runs its loop convergently and one
+        // elected lane issues the 10 tcgen05.mma of a sorted chunk.  Why two: the tensor pipe's queue is shallow (the
+        // issue of an MMA blocks until the previous one is nearly done), so whatever the issuer does between two
+        // chunks -- barrier round trip (~150 clk per try_wait), fence, descriptor arithmetic, commit -- idles the pipe;
+        // with two issuers one prepares while the other issues.  Accumulation is commutative, so the only order that
+        // matters is that the accumulate = 0 MMAs of a query tile's first chunk are issued first (bar_first).
+        const uint32_t me = warp - G_WARP_MMA;
         const uint32_t idesc = umma_idesc_u8(G_TILE_M, G_TILE_N);
+        const uint32_t b_res = P.b_resident, k_chunks = P.k_chunks, stage_bytes = P.stage_bytes;
+        const uint32_t ring_addr = smem_u32(smem), bres_addr = smem_u32(smem_b);
         uint32_t rem = 0, kc = 0, qi = 0, stage = 0, ring = 0;
         for (uint32_t j = 0; j < total; j++) {
-            if (!mbar_wait(&bar_sorted[stage], ring) || !mbar_wait(&bar_full[stage], ring)) { *abort_flag = 2; break; }
-            if (rem == 0) {
-                if (P.b_resident && !mbar_wait(&bar_b, qi & 1)) { *abort_flag = 8; break; }
-                // the epilogue of the previous query tile must have read TMEM out
-                if (qi > 0 && !mbar_wait(&bar_tmem_free, (qi - 1) & 1)) { *abort_flag = 4; break; }
-            }
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_tmem = tmem_base + G_TMEM_A + (j % G_SORT_GROUPS) * 32;
-            const uint32_t b_addr = P.b_resident ? smem_u32(smem_b + kc * G_BTILE_BYTES) : smem_u32(smem + stage * P.stage_bytes) + G_TILE_BYTES;
             const bool last = rem + 1 == per_qt;
-            if (elect_one()) {
-#pragma unroll
-                for (uint32_t a = 0; a < 4; a++)
-#pragma unroll
-                    for (uint32_t b = 0; a + b < 4; b++)   // limb pair (a, b) accumulates into D_{a+b}; the first pair of a shift is a = 0
-                        umma_i8_ts(tmem_base + (a + b) * G_TILE_N, a_tmem + a * 8, umma_desc_sw128(b_addr + b * G_UMMA_K), idesc,
-                                   (rem != 0 || a != 0) ? 1u : 0u);
-                umma_commit(&bar_empty[stage]);   // the stage may be refilled and the A buffer rewritten once these MMAs have read them
-                if (last) {                       // every MMA of this query tile has landed; its B tile may be replaced
-                    umma_commit(&bar_accum);
-                    if (P.b_resident) umma_commit(&bar_b_free);
+            // Both issuers, also one that owns no chunk of this tile: the epilogue of the previous query tile must have
+            // read TMEM out -- which also keeps an idle issuer from arriving on bar_accum a whole tile early.
+            if (rem == 0 && qi > 0 && !mbar_wait(&bar_tmem_free, (qi - 1) & 1)) { *abort_flag = 4; break; }
+            if ((rem & 1u) == me) {
+                if (!mbar_wait(&bar_sorted[stage], ring)) { *abort_flag = 2; break; }
+                if (!b_res && !mbar_wait(&bar_full[stage], ring)) { *abort_flag = 2; break; }   // streamed B tile: observe the TMA barrier itself
+                if (rem == 0) {
+                    if (b_res && !mbar_wait(&bar_b, qi & 1)) { *abort_flag = 8; break; }
+                } else if (rem == 1) {
+                    if (!mbar_wait(&bar_first, qi & 1)) { *abort_flag = 9; break; }   // the other issuer has started this query tile
                 }
+                G_TRACE(4, j);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_tmem = tmem_base + G_TMEM_A + (j % G_ABUFS) * 32;
+                const uint32_t b_addr = b_res ? bres_addr + kc * G_BTILE_BYTES : ring_addr + stage * stage_bytes + G_TILE_BYTES;
+                if (elect_one()) {
+#pragma unroll
+                    for (uint32_t a = 0; a < 4; a++)
+#pragma unroll
+                        for (uint32_t b = 0; a + b < 4; b++)   // limb pair (a, b) accumulates into D_{a+b}; the first pair of a shift is a = 0
+                            umma_i8_ts(tmem_base + (a + b) * G_TILE_N, a_tmem + a * 8, umma_desc_sw128(b_addr + b * G_UMMA_K), idesc,
+                                       (rem != 0 || a != 0) ? 1u : 0u);
+                    umma_commit(&bar_empty[stage]);   // the stage may be refilled and the A buffer rewritten once these MMAs have read them
+                    if (rem == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_first)) : "memory");
+                }
+                __syncwarp();
+                G_TRACE(5, j);
             }
-            __syncwarp();
-            if (++kc == P.k_chunks) kc = 0;
-            if (last) { rem = 0; qi++; } else rem++;
+            if (last) {   // both issuers: every MMA of mine for this query tile has been issued; the tile's B may be replaced after them
+                if (elect_one()) {
+                    umma_commit(&bar_accum);
+                    if (b_res) umma_commit(&bar_b_free);
+                }
+                __syncwarp();
+                rem = 0;
+                qi++;
+            } else {
+                rem++;
+            }
+            if (++kc == k_chunks) kc = 0;
             if (++stage == n_stages) { stage = 0; ring ^= 1; }
         }
     } else {
@@ -269,23 +307,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
         const uint32_t group = warp >> 2, row = threadIdx.x & (G_SORTERS - 1);
         const uint32_t lane_addr = tmem_base + (((warp & 3u) * 32u) << 16);
         uint32_t rem = 0, qi = 0, stage = 0, ring = 0;
-        uint32_t pstage = 0, pring = 0;   // stage / ring of chunk j - G_SORT_GROUPS
+        uint32_t pstage = 0, pring = 0;   // stage / ring of chunk j - G_ABUFS
         for (uint32_t j = 0; j < total; j++) {
             if (j % G_SORT_GROUPS == group) {
                 if (!mbar_wait(&bar_full[stage], ring)) { *abort_flag = 3; break; }
+                if ((warp & 3) == 0) G_TRACE(1, j);
                 uint32_t limbs[32];
                 limb_sort_row(smem + stage * P.stage_bytes, row, limbs);
-                // this group's A buffer in TMEM was last read by the MMAs of chunk j - G_SORT_GROUPS
-                if (j >= (uint32_t)G_SORT_GROUPS) {
+                // A buffer j % G_ABUFS in TMEM was last read by the MMAs of chunk j - G_ABUFS
+                if (j >= (uint32_t)G_ABUFS) {
                     if (!mbar_wait(&bar_empty[pstage], pring)) { *abort_flag = 6; break; }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                tmem_st32(lane_addr + G_TMEM_A + group * 32, limbs);
+                if ((warp & 3) == 0) G_TRACE(2, j);
+                tmem_st32(lane_addr + G_TMEM_A + (j % G_ABUFS) * 32, limbs);
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_sorted[stage])) : "memory");
+                if ((warp & 3) == 0) G_TRACE(3, j);
             }
-            if (j >= (uint32_t)G_SORT_GROUPS && ++pstage == n_stages) { pstage = 0; pring ^= 1; }
+            if (j >= (uint32_t)G_ABUFS && ++pstage == n_stages) { pstage = 0; pring ^= 1; }
             if (++stage == n_stages) { stage = 0; ring ^= 1; }
             if (++rem != per_qt) continue;
             rem = 0;
@@ -377,6 +418,13 @@ int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq
     P.k_chunks = (uint32_t)(kbytes / G_KCHUNK);
     P.checksum = cs_pad;
     P.error_flag = err;
+    P.trace = nullptr;
+#ifdef PM_IPGEMM_TRACE
+    static unsigned long long *d_trace = nullptr;
+    if (!d_trace) PM_CUDA(cudaMalloc(&d_trace, 6 * G_TRACE_N * 8));
+    PM_CUDA(cudaMemsetAsync(d_trace, 0, 6 * G_TRACE_N * 8, st));
+    P.trace = d_trace;
+#endif
     // shared memory: the CTA's query tile resident (all K chunks) + a ring of A tiles, or a ring of A + B tiles
     const size_t smem_avail = 227 * 1024 - 2048;
     const size_t b_all = (size_t)P.k_chunks * G_BTILE_BYTES;
@@ -407,6 +455,20 @@ int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq
     ipgemm_kernel<<<P.q_slots * P.groups, G_THREADS, smem, st>>>(map_a, map_b, P);
     PM_CHECK_LAUNCH();
     count_launch();
+#ifdef PM_IPGEMM_TRACE
+    {
+        static unsigned long long h[6 * G_TRACE_N];
+        PM_CUDA(cudaStreamSynchronize(st));
+        PM_CUDA(cudaMemcpy(h, d_trace, sizeof h, cudaMemcpyDeviceToHost));
+        unsigned long long t0 = h[0];
+        fprintf(stderr, "j,tma_issue,full_seen,st_begin,sorted_arrived,mma_sorted_seen,mma_issued\n");
+        for (int j = 0; j < G_TRACE_N; j++) {
+            fprintf(stderr, "%d", j);
+            for (int r = 0; r < 6; r++) fprintf(stderr, ",%lld", h[r * G_TRACE_N + j] ? (long long)(h[r * G_TRACE_N + j] - t0) : -1ll);
+            fprintf(stderr, "\n");
+        }
+    }
+#endif
     PM_CUDA(cudaMemcpyAsync(checksum, cs_pad, nq * 4, cudaMemcpyDeviceToDevice, st));
     return PM_OK;
 }
