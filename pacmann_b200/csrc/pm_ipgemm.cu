@@ -16,19 +16,30 @@
 // pair (a, b) is then the MMA of A slice a with B slice b of the same 128-byte chunk: 10 MMAs per chunk.
 //
 // Why A lives in TMEM: with both operands in shared memory an M128 N128 K32 MMA reads 8 KB for 64 clk of math, i.e.
-// the whole 128 B/clk of the SM's shared memory, and the TMA fills and the limb sort come on top (measured: 1240 clk
-// per chunk against 640 of math).  With A in TMEM the shared-memory traffic per chunk drops from 144 KB to 62 KB.
-// TMEM budget: 4 accumulators x 96 columns + 4 A buffers x 32 columns = 512, hence the query tile of 96.  Four A
-// buffers because refilling one waits for the MMAs that read it: with two, the chain "MMA done -> sorter wakes ->
-// tcgen05.st -> arrive -> issuer wakes" (~600 clk) was as long as one chunk of MMAs and the tensor pipe idled 35 %.
+// the whole 128 B/clk of the SM's shared memory, with the TMA fills and the limb sort on top.  With A in TMEM the
+// shared-memory traffic per chunk drops from 144 KB to 67 KB, and a stage of the ring is dead as soon as its sorters
+// hold it in registers.  TMEM budget: 4 accumulators x 112 columns + 2 A buffers x 32 columns = 512, hence the query
+// tile of 112.
 //
-// Kernel: one persistent CTA per SM, warp-specialised.  One thread of the TMA warp is the producer of a 6-stage
-// mbarrier ring (16 KB A, + 12 KB B when the query tile is streamed); two groups of four warps sort the limbs of alternate A tiles as they
-// land (thread = row = TMEM lane) and signal `sorted`; two MMA warps take alternate chunks and one thread of each issues the tcgen05.mma (M128 N96
-// K32, kind::i8, B K-major with the 128-byte swizzle the tensor map writes) and commits `empty`, which releases both
-// the stage to the producer and the A buffer to its sorter group.  Warps 0-3 are also the epilogue (warp w reads TMEM
-// lanes 32w..32w+31 = rows of the tile) once per query tile.  Every mbarrier wait is bounded: on a timeout the kernel
-// raises an error flag and drains instead of hanging.
+// Work split: CTA b takes query tile b % q_slots and row tiles b / q_slots (+ groups, ...).  The q_slots CTAs of a
+// group sweep the same row tiles at the same pace, so a row tile comes from HBM once (ncu: 2.5 GB for a 2.46 GB table,
+// L2 hit rate 86 %) and the CTA's query tile stays resident in shared memory for the whole sweep.
+//
+// Kernel: one persistent CTA per SM, warp-specialised (11 warps).  One lane of the TMA warp is the producer of an
+// 8-stage mbarrier ring of 16 KB A tiles (A + B tiles when 4*dim bytes of queries do not fit shared memory); two groups
+// of four warps sort the limbs of alternate A tiles as they land (thread = row = TMEM lane), release the stage, store
+// the limbs to TMEM and signal `sorted`; two MMA warps take alternate chunks and one lane of each issues the
+// tcgen05.mma (M128 N112 K32, kind::i8, B K-major with the 128-byte swizzle the tensor map writes) and commits `empty`,
+// which releases the A buffer in TMEM to its sorters.  Warps 0-3 are also the epilogue (warp w reads TMEM lanes
+// 32w..32w+31 = rows of the tile) once per query tile.  Every mbarrier wait is bounded: on a timeout the kernel raises
+// an error flag and drains instead of hanging.
+//
+// What the measurements said on the way (scripts/trace_ipgemm.py, profiles/): (1) tcgen05.mma issued from a divergent
+// `if (lane == 0)` branch compiles to an ELECT / BRA.U.ANY loop per instruction and the issuer became the bottleneck
+// (1240 clk per chunk for 640 clk of math) -- the issuing warps run convergently and elect one lane instead; (2) the
+// tensor pipe's queue is shallow, so whatever one issuer does between chunks idles the pipe -- hence two issuers;
+// (3) TMA latency under load is ~3000 clk, so the ring must be released by the sorters, not by the MMAs.
+// Q = 1000 over 3 201 821 x 192: 3.31 ms = 1.9e15 int8 MAC/s (84 % of the dense int8 peak), integer-pipe kernel 75 ms.
 #include <cuda.h>
 
 #include <algorithm>
@@ -41,8 +52,8 @@ namespace pm {
 constexpr int G_SORT_GROUPS = 2, G_SORTERS = 128;   // sorter group g = warps 4g..4g+3 takes chunks j = g (mod G_SORT_GROUPS)
 constexpr int G_WARP_TMA = 4 * G_SORT_GROUPS, G_WARP_MMA = G_WARP_TMA + 1, G_ISSUERS = 2, G_THREADS = 32 * (G_WARP_MMA + G_ISSUERS);
 #ifndef PM_G_TILE_N
-#define PM_G_TILE_N 96
-#define PM_G_ABUFS 4
+#define PM_G_TILE_N 112   // measured at Q = 1000: N = 112 with two A buffers 3.31 ms, N = 96 with four 3.76 ms (11 instead of 9
+#define PM_G_ABUFS 2     // readers per row tile: the L2 -> SM traffic, ~7 TB/s, becomes the limit)
 #endif
 constexpr int G_TILE_M = 128, G_TILE_N = PM_G_TILE_N, G_KCHUNK = 128, G_UMMA_K = 32, G_MAX_STAGES = 8, G_ABUFS = PM_G_ABUFS;
 constexpr uint32_t G_TILE_BYTES = G_TILE_M * G_KCHUNK;           // A tile, 16 KB
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem_b = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t *smem = smem_b + P.b_resident;   // the ring
-    __shared__ uint64_t bar_full[G_MAX_STAGES], bar_sorted[G_MAX_STAGES], bar_empty[G_MAX_STAGES], bar_accum, bar_tmem_free, bar_b, bar_b_free, bar_first;
+    __shared__ uint64_t bar_full[G_MAX_STAGES], bar_sorted[G_MAX_STAGES], bar_empty[G_MAX_STAGES], bar_a_read[G_MAX_STAGES], bar_accum, bar_tmem_free, bar_b, bar_b_free, bar_first;
     __shared__ uint32_t s_tmem_base;
     __shared__ int s_abort;
     const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
@@ -185,6 +196,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
             mbar_init(&bar_full[i], 1);
             mbar_init(&bar_sorted[i], G_SORTERS);
             mbar_init(&bar_empty[i], 1);
+            mbar_init(&bar_a_read[i], G_SORTERS);
         }
         mbar_init(&bar_accum, G_ISSUERS);
         mbar_init(&bar_tmem_free, G_SORTERS);
@@ -233,7 +245,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
                 }
                 __syncwarp();
             }
-            if (j >= n_stages && !mbar_wait(&bar_empty[stage], ring ^ 1)) { *abort_flag = 1; break; }
+            // An A tile is dead once its sorters hold it in registers (it reaches the MMA through TMEM), so with the
+            // query tile resident the stage is refilled without waiting for the MMAs -- the ring then covers the TMA
+            // latency (~3000 clk under load) instead of TMA + sort + MMA.  A stage that also carries B waits for the MMAs.
+            if (j >= n_stages && !mbar_wait(P.b_resident ? &bar_a_read[stage] : &bar_empty[stage], ring ^ 1)) { *abort_flag = 1; break; }
             G_TRACE(0, j);
             if (elect_one()) {
                 uint8_t *sa = smem + stage * P.stage_bytes;
@@ -314,6 +329,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) ipgemm_kernel(const __grid_const
                 if ((warp & 3) == 0) G_TRACE(1, j);
                 uint32_t limbs[32];
                 limb_sort_row(smem + stage * P.stage_bytes, row, limbs);
+                asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar_a_read[stage])), "r"(limbs[0]), "r"(limbs[31]) : "memory");
                 // A buffer j % G_ABUFS in TMEM was last read by the MMAs of chunk j - G_ABUFS
                 if (j >= (uint32_t)G_ABUFS) {
                     if (!mbar_wait(&bar_empty[pstage], pring)) { *abort_flag = 6; break; }
