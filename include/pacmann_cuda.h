@@ -158,6 +158,11 @@ int pm_client_query_batch(pm_client *c, const pm_client_query *queries, uint64_t
  * answers (the per-step L2Dist call site of SearchKNN, graphann/search.go:204), saving a second round trip */
 int pm_client_query_batch_l2(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
                              const float *query_vec, uint64_t dim, float *dist_out);
+/* same for a call that carries the sub-queries of several searches (several independent client instances kept as
+ * groups of parts of one pm_client, driven in lock step): dist_out[i] = L2Dist(out[i], query_vecs[vec_id[i]]),
+ * query_vecs = [n_vecs][dim] */
+int pm_client_query_batch_l2m(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
+                              const float *query_vecs, uint64_t n_vecs, const uint32_t *vec_id, uint64_t dim, float *dist_out);
 /* copy one table of one part to the host (tests / checkpointing): 0 primaryShortTag, 1 primaryParity,
  * 2 primaryProgramPoint, 3 replacementIdx, 4 replacementVal, 5 backupShortTag, 6 backupParity, 7 QueryHistogram,
  * 8 FinishedQueryNum */

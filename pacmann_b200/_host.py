@@ -43,6 +43,9 @@ SIG = {
     "pmh_frontend_basic": (vp, [i64, i64, i64, vp, vp]),
     "pmh_frontend_pir": (vp, [i64, i64, i64, vp, vp, C.c_int, C.c_int, u64, C.c_int, C.c_int]),
     "pmh_frontend_pir_shared": (vp, [vp, u64, C.c_int]),
+    "pmh_frontend_set_group_lanes": (C.c_int, [vp, C.c_uint32]),
+    "pmh_frontend_pir_lane": (vp, [vp, u64, C.c_uint32]),
+    "pmh_search_knn_lockstep": (C.c_int, [vp, i64, vp, i64, i64, i64, i64, C.c_int, vp, vp]),
     "pmh_frontend_free": (None, [vp]),
     "pmh_frontend_preprocess": (C.c_int, [vp]),
     "pmh_frontend_start_ids": (i64, [vp, vp, i64]),

@@ -89,7 +89,10 @@ void PIRGraphInfo::Preprocess() {
         std::vector<uint64_t>().swap(rawDB);  // the device copy is the server's DB from here on
     }
     PIR->SetSeeds(Mix64(seed, 1), Mix64(seed, 2));
-    if (residentClient && !NonPrivateMode) PIR->EnableResidentClient();
+    if (residentClient && !NonPrivateMode) {
+        if (laneOf && laneOf->PIR) PIR->AttachResidentClient(laneOf->PIR, lane);   // a further lane of laneOf's client group
+        else PIR->EnableResidentClient(groupLanes);
+    }
     if (skipPrep) PIR->DummyPreprocessing();
     else PIR->Preprocessing();
 }
@@ -123,6 +126,36 @@ int PIRGraphInfo::GetVertexInfoWithDist(const std::vector<int64_t> &ids, const f
     wsIdx.assign(ids.begin(), ids.end());
     wsResp.resize(ids.size() * E);
     if (PIR->QueryFlat(wsIdx.data(), wsIdx.size(), wsResp.data(), query, (uint64_t)Dim, query ? dists->data() : nullptr) != 0) return -1;
+    unpackResponses(ids, out);
+    return 0;
+}
+
+// GetVertexInfoWithDist of several lanes of one resident client group: ONE QueryFlatGroup for all of them
+int PIRGraphInfo::GetVertexInfoWithDistGroup(const std::vector<PIRGraphInfo *> &infos, const std::vector<const std::vector<int64_t> *> &ids,
+                                             const std::vector<const float *> &queries, const std::vector<std::vector<Vertex> *> &outs,
+                                             const std::vector<std::vector<float> *> &dists) {
+    const size_t L = infos.size();
+    std::vector<pianopir::SimpleBatchPianoPIR::GroupCall> calls(L);
+    for (size_t l = 0; l < L; l++) {
+        PIRGraphInfo *g = infos[l];
+        const uint64_t E = g->DBEntryByteNum / 8;
+        const size_t cnt = ids[l]->size();
+        g->totalQueryNum += (int64_t)cnt;
+        outs[l]->resize(cnt);
+        dists[l]->assign(cnt, std::nanf(""));
+        g->wsIdx.assign(ids[l]->begin(), ids[l]->end());
+        g->wsResp.resize(cnt * E);
+        calls[l] = {g->PIR, g->wsIdx.data(), cnt, g->wsResp.data(), queries[l], queries[l] ? dists[l]->data() : nullptr, 0};
+    }
+    if (pianopir::SimpleBatchPianoPIR::QueryFlatGroup(calls, (uint64_t)infos[0]->Dim) != 0) return -1;
+#pragma omp parallel for schedule(static) if (L > 2)
+    for (size_t l = 0; l < L; l++) infos[l]->unpackResponses(*ids[l], outs[l]);
+    return 0;
+}
+
+// Entry2VectorAndNeighbors of every fetched entry + the reference's correctness accounting (private-search.go:480-504)
+void PIRGraphInfo::unpackResponses(const std::vector<int64_t> &ids, std::vector<Vertex> *out) {
+    const uint64_t E = DBEntryByteNum / 8;
     for (size_t i = 0; i < ids.size(); i++) {
         Vertex &v = (*out)[i];
         v.Id = ids[i];
@@ -132,7 +165,6 @@ int PIRGraphInfo::GetVertexInfoWithDist(const std::vector<int64_t> &ids, const f
             if (v.Neighbors[j] != (int64_t)(uint32_t)graph[ids[i] * M + j]) { correctQ = false; break; }
         if (correctQ) succQueryNum++;
     }
-    return 0;
 }
 
 int PIRGraphInfo::GetStartVertex(std::vector<Vertex> *out) {
@@ -175,43 +207,36 @@ GraphANNFrontend::~GraphANNFrontend() {
     if (startDb) pm_db_destroy(startDb);
 }
 
-namespace {
-struct VD { float dist; int64_t id; };
 // container/heap's up/down/Push/Pop with Less = dist < dist (search.go:92-111)
-struct ExploreQueue {
-    std::vector<VD> a;
-    void up(int64_t j) {
-        for (;;) {
-            int64_t i = (j - 1) / 2;
-            if (i == j || j <= 0 || !(a[j].dist < a[i].dist)) break;
-            std::swap(a[i], a[j]);
-            j = i;
-        }
+void ExploreQueue::up(int64_t j) {
+    for (;;) {
+        int64_t i = (j - 1) / 2;
+        if (i == j || j <= 0 || !(a[j].dist < a[i].dist)) break;
+        std::swap(a[i], a[j]);
+        j = i;
     }
-    void down(int64_t i0, int64_t n) {
-        int64_t i = i0;
-        for (;;) {
-            int64_t j1 = 2 * i + 1;
-            if (j1 >= n || j1 < 0) break;
-            int64_t j = j1, j2 = j1 + 1;
-            if (j2 < n && a[j2].dist < a[j1].dist) j = j2;
-            if (!(a[j].dist < a[i].dist)) break;
-            std::swap(a[i], a[j]);
-            i = j;
-        }
+}
+void ExploreQueue::down(int64_t i0, int64_t n) {
+    int64_t i = i0;
+    for (;;) {
+        int64_t j1 = 2 * i + 1;
+        if (j1 >= n || j1 < 0) break;
+        int64_t j = j1, j2 = j1 + 1;
+        if (j2 < n && a[j2].dist < a[j1].dist) j = j2;
+        if (!(a[j].dist < a[i].dist)) break;
+        std::swap(a[i], a[j]);
+        i = j;
     }
-    void Push(VD v) { a.push_back(v); up((int64_t)a.size() - 1); }
-    VD Pop() {
-        int64_t n = (int64_t)a.size() - 1;
-        std::swap(a[0], a[n]);
-        down(0, n);
-        VD v = a.back();
-        a.pop_back();
-        return v;
-    }
-    size_t Len() const { return a.size(); }
-};
-}  // namespace
+}
+void ExploreQueue::Push(VD v) { a.push_back(v); up((int64_t)a.size() - 1); }
+VD ExploreQueue::Pop() {
+    int64_t n = (int64_t)a.size() - 1;
+    std::swap(a[0], a[n]);
+    down(0, n);
+    VD v = a.back();
+    a.pop_back();
+    return v;
+}
 
 // Distances of every start vertex to one query (search.go:131-134).  The start vertices are fixed plaintext copies,
 // so their vectors are uploaded once (Preprocess) and each search only sends the query.
@@ -227,105 +252,123 @@ void GraphANNFrontend::StartDistances(const float *queryVector, int64_t dim, int
     dist_many(ptrs, dim, queryVector, device, out);
 }
 
-int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking,
-                                std::vector<int64_t> *ret, std::vector<int64_t> *stepRet) {
-    int64_t n, dim, m;
-    Graph->GetMetadata(&n, &dim, &m);
-    const int device = Graph->Device();
+// ---- SearchKNN (search.go:114-234) as a resumable state: Begin, then NextBatch / Consume once per step, then Finish ----
+void SearchState::addKnown(const Vertex &v, float dist, int64_t step) {
+    slotOf[v.Id] = (int32_t)knownId.size();
+    knownId.push_back(v.Id);
+    knownDist.push_back(dist);
+    knownStep.push_back(step);
+    nbrPool.insert(nbrPool.end(), v.Neighbors.begin(), v.Neighbors.end());
+}
+
+void SearchState::Begin(GraphANNFrontend *front, const float *q, int64_t k_, int64_t maxStep_, int64_t parallel_, bool benchmarking_) {
+    f = front;
+    queryVector = q;
+    k = k_; maxStep = maxStep_; parallel = parallel_; benchmarking = benchmarking_;
+    f->Graph->GetMetadata(&n, &dim, &m);
+    device = f->Graph->Device();
     // knownVertices / reachStep (search.go:117-118) as a slot table: the reference keeps whole Vertex objects in maps, but
     // only ids, neighbour lists, reach steps and distances are read back.  A vertex's distance is evaluated once, when it
     // becomes known, and reused by the final ranking (search.go:212-218 recomputes L2Dist on the same vector: same bits).
-    std::unordered_map<int64_t, int32_t> slotOf;
+    slotOf.clear();
     slotOf.reserve((size_t)(maxStep * parallel * m * 2 + 64));
-    std::vector<int64_t> knownId, knownStep, nbrPool;
-    std::vector<float> knownDist;
-    auto add_known = [&](const Vertex &v, float dist, int64_t step) {
-        slotOf[v.Id] = (int32_t)knownId.size();
-        knownId.push_back(v.Id);
-        knownDist.push_back(dist);
-        knownStep.push_back(step);
-        nbrPool.insert(nbrPool.end(), v.Neighbors.begin(), v.Neighbors.end());
-    };
-    ExploreQueue toBeExplored;
-    const uint64_t rseed = Mix64(randSeed, queryCounter++);
-    uint64_t rctr = 0;
-    std::vector<float> dists;
-
+    knownId.clear(); knownStep.clear(); nbrPool.clear(); knownDist.clear();
+    toBeExplored.a.clear();
+    rseed = Mix64(f->randSeed, f->queryCounter++);
+    rctr = 0;
+    step = 0;
     if (!benchmarking) {  // search.go:129-148
-        StartDistances(queryVector, dim, device, &dists);
-        std::vector<size_t> order(StartVertices.size());
+        f->StartDistances(queryVector, dim, device, &dists);
+        std::vector<size_t> order(f->StartVertices.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dists[a] < dists[b]; });
         for (size_t i = 0; (int64_t)toBeExplored.Len() < parallel && i < order.size(); i++) {
-            const Vertex &v = StartVertices[order[i]];
+            const Vertex &v = f->StartVertices[order[i]];
             if (slotOf.count(v.Id)) continue;
-            add_known(v, dists[order[i]], 0);
+            addKnown(v, dists[order[i]], 0);
             toBeExplored.Push({dists[order[i]], v.Id});
         }
     }
+}
 
-    std::vector<Vertex> &queryResults = wsResults;
-    std::vector<float> &srcDists = wsSrcDists;
-    std::vector<int64_t> batchQ;
-    std::vector<size_t> fresh, missing;
-    std::vector<const float *> ptrs;
-    for (int64_t step = 0; step < maxStep; step++) {  // search.go:150-208
-        batchQ.clear();
-        for (int64_t rept = 0; rept < parallel; rept++) {
-            if (toBeExplored.Len() == 0 || benchmarking) {
-                for (int64_t i = 0; i < m; i++) batchQ.push_back((int64_t)(Mix64(rseed, rctr++) % (uint64_t)n));
-            } else {
-                VD item = toBeExplored.Pop();
-                const int64_t *nb = &nbrPool[(size_t)slotOf[item.id] * (size_t)m];
-                batchQ.insert(batchQ.end(), nb, nb + m);
-            }
-        }
-        if (Graph->GetVertexInfoWithDist(batchQ, benchmarking ? nullptr : queryVector, &queryResults, &srcDists) != 0) return -1;
-        if (benchmarking) continue;
-        // newly discovered vertices of this step, in batch order (a repeated id is "already known" by its second occurrence)
-        fresh.clear();
-        for (size_t i = 0; i < queryResults.size(); i++) {
-            const Vertex &v = queryResults[i];
-            if (slotOf.count(v.Id)) continue;
-            bool dup = false;
-            for (size_t f : fresh) dup = dup || queryResults[f].Id == v.Id;
-            if (dup) continue;
-            bool ok = false;
-            for (int64_t nb : v.Neighbors) if (nb != 0) { ok = true; break; }   // all-zero list = failed fetch (search.go:192-199)
-            if (ok) fresh.push_back(i);
-        }
-        // their distances (search.go:204): taken from the vertex source when it computed them behind the fetch, one extra
-        // launch only for the ones it did not (e.g. entries served from the local cache)
-        dists.assign(fresh.size(), 0.f);
-        ptrs.clear();
-        missing.clear();
-        for (size_t t = 0; t < fresh.size(); t++) {
-            const float d = srcDists[fresh[t]];
-            if (std::isnan(d)) { missing.push_back(t); ptrs.push_back(queryResults[fresh[t]].Vector.data()); }
-            else dists[t] = d;
-        }
-        if (!missing.empty()) {
-            std::vector<float> md;
-            dist_many(ptrs, dim, queryVector, device, &md);
-            for (size_t j = 0; j < missing.size(); j++) dists[missing[j]] = md[j];
-        }
-        for (size_t t = 0; t < fresh.size(); t++) {
-            const Vertex &v = queryResults[fresh[t]];
-            add_known(v, dists[t], step);
-            toBeExplored.Push({dists[t], v.Id});
+// the ids this step fetches (search.go:150-167); false once maxStep steps have been made
+bool SearchState::NextBatch(std::vector<int64_t> *batchQ) {
+    if (step >= maxStep) return false;
+    batchQ->clear();
+    for (int64_t rept = 0; rept < parallel; rept++) {
+        if (toBeExplored.Len() == 0 || benchmarking) {
+            for (int64_t i = 0; i < m; i++) batchQ->push_back((int64_t)(Mix64(rseed, rctr++) % (uint64_t)n));
+        } else {
+            VD item = toBeExplored.Pop();
+            const int64_t *nb = &nbrPool[(size_t)slotOf[item.id] * (size_t)m];
+            batchQ->insert(batchQ->end(), nb, nb + m);
         }
     }
+    return true;
+}
 
-    // search.go:210-233
+// search.go:169-208 for the fetched vertices of this step
+void SearchState::Consume(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists) {
+    const int64_t thisStep = step++;
+    if (benchmarking) return;
+    // newly discovered vertices of this step, in batch order (a repeated id is "already known" by its second occurrence)
+    fresh.clear();
+    for (size_t i = 0; i < queryResults.size(); i++) {
+        const Vertex &v = queryResults[i];
+        if (slotOf.count(v.Id)) continue;
+        bool dup = false;
+        for (size_t t : fresh) dup = dup || queryResults[t].Id == v.Id;
+        if (dup) continue;
+        bool ok = false;
+        for (int64_t nb : v.Neighbors) if (nb != 0) { ok = true; break; }   // all-zero list = failed fetch (search.go:192-199)
+        if (ok) fresh.push_back(i);
+    }
+    // their distances (search.go:204): taken from the vertex source when it computed them behind the fetch, one extra
+    // launch only for the ones it did not (e.g. entries served from the local cache)
+    dists.assign(fresh.size(), 0.f);
+    ptrs.clear();
+    missing.clear();
+    for (size_t t = 0; t < fresh.size(); t++) {
+        const float d = srcDists[fresh[t]];
+        if (std::isnan(d)) { missing.push_back(t); ptrs.push_back(queryResults[fresh[t]].Vector.data()); }
+        else dists[t] = d;
+    }
+    if (!missing.empty()) {
+        std::vector<float> md;
+        dist_many(ptrs, dim, queryVector, device, &md);
+        for (size_t j = 0; j < missing.size(); j++) dists[missing[j]] = md[j];
+    }
+    for (size_t t = 0; t < fresh.size(); t++) {
+        const Vertex &v = queryResults[fresh[t]];
+        addKnown(v, dists[t], thisStep);
+        toBeExplored.Push({dists[t], v.Id});
+    }
+}
+
+// search.go:210-233
+void SearchState::Finish(int64_t *ret, int64_t *stepRet) {
     std::vector<VD> all(knownId.size());
     for (size_t i = 0; i < all.size(); i++) all[i] = {knownDist[i], knownId[i]};
     std::sort(all.begin(), all.end(), [](const VD &a, const VD &b) { return a.dist < b.dist || (a.dist == b.dist && a.id < b.id); });
-    ret->assign(k, -1);
-    stepRet->assign(k, -1);
+    for (int64_t i = 0; i < k; i++) { ret[i] = -1; stepRet[i] = -1; }
     for (int64_t i = 0; i < k && i < (int64_t)all.size(); i++) {
-        (*ret)[i] = all[i].id;
-        (*stepRet)[i] = knownStep[(size_t)slotOf[all[i].id]];
+        ret[i] = all[i].id;
+        stepRet[i] = knownStep[(size_t)slotOf[all[i].id]];
     }
+}
+
+int GraphANNFrontend::SearchKNN(const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking,
+                                std::vector<int64_t> *ret, std::vector<int64_t> *stepRet) {
+    SearchState &st = wsState;
+    st.Begin(this, queryVector, k, maxStep, parallel, benchmarking);
+    std::vector<int64_t> &batchQ = wsBatch;
+    while (st.NextBatch(&batchQ)) {
+        if (Graph->GetVertexInfoWithDist(batchQ, benchmarking ? nullptr : queryVector, &wsResults, &wsSrcDists) != 0) return -1;
+        st.Consume(wsResults, wsSrcDists);
+    }
+    ret->assign((size_t)k, -1);
+    stepRet->assign((size_t)k, -1);
+    st.Finish(ret->data(), stepRet->data());
     return 0;
 }
 
@@ -340,6 +383,85 @@ int GraphANNFrontend::SearchKNNBatch(const float *queryVectors, int64_t nq, int6
         if (SearchKNN(queryVectors + i * dim, k, maxStep, parallel, benchmarking, &r, &s) != 0) return -1;
         memcpy(&(*ret)[i * k], r.data(), (size_t)k * 8);
         memcpy(&(*stepRet)[i * k], s.data(), (size_t)k * 8);
+    }
+    return 0;
+}
+
+// Lock-step search over several lanes.  Query i goes to lane i % L; every lane runs its queries in
+// order exactly as its own SearchKNNBatch would -- same client state, same results -- but each step fetches the
+// vertices of all lanes together: one GetVertexInfoWithDistGroup (one device call) per step instead of one per lane.
+int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float *queryVectors, int64_t nq, int64_t k, int64_t maxStep,
+                      int64_t parallel, bool benchmarking, std::vector<int64_t> *ret, std::vector<int64_t> *stepRet) {
+    const int64_t L = (int64_t)lanes.size();
+    if (L == 0) return -1;
+    int64_t n, dim, m;
+    lanes[0]->Graph->GetMetadata(&n, &dim, &m);
+    ret->assign((size_t)(nq * k), -1);
+    stepRet->assign((size_t)(nq * k), -1);
+    std::vector<PIRGraphInfo *> infos((size_t)L);
+    bool groupable = true;
+    for (int64_t l = 0; l < L; l++) {
+        infos[(size_t)l] = dynamic_cast<PIRGraphInfo *>(lanes[(size_t)l]->Graph);
+        groupable = groupable && infos[(size_t)l] != nullptr && !infos[(size_t)l]->NonPrivateMode;
+    }
+    std::vector<std::vector<int64_t>> batch((size_t)L);
+    std::vector<std::vector<Vertex>> results((size_t)L);
+    std::vector<std::vector<float>> srcDists((size_t)L);
+    std::vector<const float *> qptr((size_t)L);
+    std::vector<char> more((size_t)L);
+    for (int64_t base = 0; base < nq; base += L) {
+        const int64_t act = std::min(L, nq - base);
+        std::string err;
+#pragma omp parallel for schedule(static) if (act > 2)
+        for (int64_t l = 0; l < act; l++) {
+            try {
+                qptr[(size_t)l] = queryVectors + (base + l) * dim;
+                lanes[(size_t)l]->wsState.Begin(lanes[(size_t)l], qptr[(size_t)l], k, maxStep, parallel, benchmarking);
+            } catch (const std::exception &e) {
+#pragma omp critical
+                err = e.what();
+            }
+        }
+        if (!err.empty()) throw std::runtime_error(err);
+        for (;;) {
+            bool any = false;
+            for (int64_t l = 0; l < act; l++) {
+                more[(size_t)l] = lanes[(size_t)l]->wsState.NextBatch(&batch[(size_t)l]) ? 1 : 0;
+                any = any || more[(size_t)l];
+            }
+            if (!any) break;   // all lanes use the same maxStep, so they finish together
+            if (groupable) {
+                std::vector<PIRGraphInfo *> gi;
+                std::vector<const std::vector<int64_t> *> gb;
+                std::vector<const float *> gq;
+                std::vector<std::vector<Vertex> *> go;
+                std::vector<std::vector<float> *> gd;
+                for (int64_t l = 0; l < act; l++) {
+                    if (!more[(size_t)l]) continue;
+                    gi.push_back(infos[(size_t)l]); gb.push_back(&batch[(size_t)l]); gq.push_back(benchmarking ? nullptr : qptr[(size_t)l]);
+                    go.push_back(&results[(size_t)l]); gd.push_back(&srcDists[(size_t)l]);
+                }
+                if (PIRGraphInfo::GetVertexInfoWithDistGroup(gi, gb, gq, go, gd) != 0) return -1;
+            } else {
+                for (int64_t l = 0; l < act; l++)
+                    if (more[(size_t)l] && lanes[(size_t)l]->Graph->GetVertexInfoWithDist(batch[(size_t)l], benchmarking ? nullptr : qptr[(size_t)l],
+                                                                                          &results[(size_t)l], &srcDists[(size_t)l]) != 0)
+                        return -1;
+            }
+#pragma omp parallel for schedule(static) if (act > 2)
+            for (int64_t l = 0; l < act; l++) {
+                if (!more[(size_t)l]) continue;
+                try {
+                    lanes[(size_t)l]->wsState.Consume(results[(size_t)l], srcDists[(size_t)l]);
+                } catch (const std::exception &e) {
+#pragma omp critical
+                    err = e.what();
+                }
+            }
+            if (!err.empty()) throw std::runtime_error(err);
+        }
+        for (int64_t l = 0; l < act; l++)
+            lanes[(size_t)l]->wsState.Finish(&(*ret)[(size_t)((base + l) * k)], &(*stepRet)[(size_t)((base + l) * k)]);
     }
     return 0;
 }

@@ -6,6 +6,7 @@
 // the final ranking orders by (distance, id).
 #pragma once
 #include <cstdint>
+#include <unordered_map>
 #include <vector>
 
 #include "pianopir.hpp"
@@ -67,6 +68,15 @@ public:
     bool skipPrep, NonPrivateMode;
     bool residentClient = true;  // keep the hint tables on the GPU (pm_client_*)
     PIRGraphInfo *shareDBWith = nullptr;  // another client's graph info whose resident rawDB this one reuses (one per user)
+    // Client groups for lock-step search: the group's first client sets groupLanes = L before Preprocess(); clients
+    // 1..L-1 set laneOf = the first client and lane = their number (they also share its rawDB).  All lanes then live in
+    // one pm_client and GetVertexInfoWithDistGroup fetches for all of them with one device call.
+    uint32_t groupLanes = 1, lane = 0;
+    PIRGraphInfo *laneOf = nullptr;
+    static int GetVertexInfoWithDistGroup(const std::vector<PIRGraphInfo *> &infos, const std::vector<const std::vector<int64_t> *> &ids,
+                                          const std::vector<const float *> &queries, const std::vector<std::vector<Vertex> *> &outs,
+                                          const std::vector<std::vector<float> *> &dists);
+    void unpackResponses(const std::vector<int64_t> &ids, std::vector<Vertex> *out);
     uint64_t DBEntryByteNum = 0, DBTotalSize = 0;
     std::vector<uint64_t> rawDB;
     pianopir::SimpleBatchPianoPIR *PIR = nullptr;
@@ -80,6 +90,42 @@ public:
 void Entry2VectorAndNeighbors(int64_t dim, int64_t m, const uint64_t *entry, std::vector<float> *vector,
                               std::vector<int64_t> *neighbors);
 void PackEntry(int64_t dim, int64_t m, const float *vector, const int32_t *neighbors, uint64_t *entry);
+
+struct VD { float dist; int64_t id; };
+struct ExploreQueue {   // container/heap over (dist, id), search.go:92-111
+    std::vector<VD> a;
+    void up(int64_t j);
+    void down(int64_t i0, int64_t n);
+    void Push(VD v);
+    VD Pop();
+    size_t Len() const { return a.size(); }
+};
+
+class GraphANNFrontend;
+// One SearchKNN in progress (search.go:114-234): Begin, then NextBatch -> fetch -> Consume once per step, then Finish.
+// SearchKNN drives it alone, SearchKNNLockstep drives one per lane with a shared fetch.
+class SearchState {
+public:
+    void Begin(GraphANNFrontend *front, const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking);
+    bool NextBatch(std::vector<int64_t> *batchQ);
+    void Consume(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists);
+    void Finish(int64_t *ret, int64_t *stepRet);   // [k] each, -1 padded
+
+private:
+    void addKnown(const Vertex &v, float dist, int64_t step);
+    GraphANNFrontend *f = nullptr;
+    const float *queryVector = nullptr;
+    int64_t k = 0, maxStep = 0, parallel = 0, n = 0, dim = 0, m = 0, step = 0;
+    bool benchmarking = false;
+    int device = 0;
+    std::unordered_map<int64_t, int32_t> slotOf;
+    std::vector<int64_t> knownId, knownStep, nbrPool;
+    std::vector<float> knownDist, dists;
+    ExploreQueue toBeExplored;
+    uint64_t rseed = 0, rctr = 0;
+    std::vector<size_t> fresh, missing;
+    std::vector<const float *> ptrs;
+};
 
 class GraphANNFrontend {  // search.go:69-245
 public:
@@ -98,12 +144,20 @@ public:
     uint64_t randSeed = 0;   // stands in for Go's global math/rand in the "random query" branch (search.go:155-159)
     uint64_t queryCounter = 0;
 
-private:
     void StartDistances(const float *queryVector, int64_t dim, int device, std::vector<float> *out);
+    SearchState wsState;                 // the search in progress (one at a time per frontend)
+
+private:
+    std::vector<int64_t> wsBatch;
     pm_db *startDb = nullptr;            // start vertices' vectors, resident on the GPU
     std::vector<int64_t> startIds;       // 0..n_start-1
     std::vector<Vertex> wsResults;       // per-step scratch reused across steps and searches
     std::vector<float> wsSrcDists;
 };
+
+// Lock-step SearchKNNBatch over several frontends ("lanes"): query i is searched by lane i % L; results are those of
+// each lane's own SearchKNNBatch over its queries, the per-step fetches of all lanes share one device call.
+int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float *queryVectors, int64_t nq, int64_t k, int64_t maxStep,
+                      int64_t parallel, bool benchmarking, std::vector<int64_t> *ret, std::vector<int64_t> *stepRet);
 
 }  // namespace graphann

@@ -245,6 +245,44 @@ PMH void *pmh_frontend_pir_shared(void *other, uint64_t seed, int resident) {
     return b;
     PMH_CATCH(nullptr)
 }
+// Client groups for lock-step search: call pmh_frontend_set_group_lanes(first, L) before preprocessing the first
+// client, then create clients 1..L-1 with pmh_frontend_pir_lane(first, seed, lane) and preprocess them.
+PMH int pmh_frontend_set_group_lanes(void *h, uint32_t lanes) {
+    PMH_TRY
+    auto *pg = dynamic_cast<graphann::PIRGraphInfo *>(((FrontBox *)h)->g);
+    if (!pg || pg->PIR) throw std::runtime_error("pmh_frontend_set_group_lanes: needs a private frontend that is not preprocessed yet");
+    pg->groupLanes = lanes ? lanes : 1;
+    return 0;
+    PMH_CATCH(-100)
+}
+PMH void *pmh_frontend_pir_lane(void *first, uint64_t seed, uint32_t lane) {
+    PMH_TRY
+    auto *og = dynamic_cast<graphann::PIRGraphInfo *>(((FrontBox *)first)->g);
+    if (!og || !og->PIR || !og->PIR->resident) throw std::runtime_error("pmh_frontend_pir_lane: the first client has no resident client group");
+    auto *b = new FrontBox();
+    auto *pg = new graphann::PIRGraphInfo(og->N, og->Dim, og->M, og->graph, og->vectors, og->skipPrep, false, seed, og->device);
+    pg->residentClient = true;
+    pg->shareDBWith = og;
+    pg->laneOf = og;
+    pg->lane = lane;
+    b->g = pg;
+    b->f = new graphann::GraphANNFrontend(b->g);
+    return b;
+    PMH_CATCH(nullptr)
+}
+PMH int pmh_search_knn_lockstep(void **handles, int64_t n_lanes, const float *queries, int64_t nq, int64_t k, int64_t max_step,
+                                int64_t parallel, int benchmarking, int64_t *ret, int64_t *step_ret) {
+    PMH_TRY
+    std::vector<graphann::GraphANNFrontend *> lanes;
+    for (int64_t i = 0; i < n_lanes; i++) lanes.push_back(((FrontBox *)handles[i])->f);
+    std::vector<int64_t> r, s;
+    int rc = graphann::SearchKNNLockstep(lanes, queries, nq, k, max_step, parallel, benchmarking != 0, &r, &s);
+    if (rc != 0) return rc;
+    memcpy(ret, r.data(), r.size() * 8);
+    memcpy(step_ret, s.data(), s.size() * 8);
+    return 0;
+    PMH_CATCH(-100)
+}
 PMH void pmh_frontend_free(void *h) {
     auto *b = (FrontBox *)h;
     if (!b) return;

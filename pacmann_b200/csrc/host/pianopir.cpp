@@ -421,7 +421,7 @@ SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
     if (getenv("PM_HOST_PROFILE") && profQueryCalls)
         fprintf(stderr, "[host profile] Query calls %llu: %.1f us per call, of which pm_client_query_batch %.1f us\n",
                 (unsigned long long)profQueryCalls, profQueryTotal / profQueryCalls * 1e6, profGpuCall / profQueryCalls * 1e6);
-    if (rclient) pm_client_destroy(rclient);
+    if (rclient && ownsClient) pm_client_destroy(rclient);
     for (auto *p : subPIR) delete p;
     if (ownsDB) delete db;
 }
@@ -614,16 +614,35 @@ int SimpleBatchPianoPIR::Query(const std::vector<uint64_t> &idx, std::vector<std
 // ---------------------------------------------------------------------------------------------
 // GPU-resident client
 // ---------------------------------------------------------------------------------------------
-void SimpleBatchPianoPIR::EnableResidentClient() {
+void SimpleBatchPianoPIR::EnableResidentClient(uint32_t lanes) {
     if (resident) return;
-    std::vector<pm_client_part> parts(config.PartitionNum);
-    for (uint64_t i = 0; i < config.PartitionNum; i++) {
-        PianoPIR *p = subPIR[i];
-        parts[i] = pm_client_part{p->server.row0, p->config.DBSize, p->config.ChunkSize, p->config.SetSize,
-                                  p->client.primaryHintNum, p->client.maxQueryPerChunk, p->client.MaxQueryNum};
-    }
+    if (lanes == 0) lanes = 1;
+    std::vector<pm_client_part> parts((size_t)config.PartitionNum * lanes);
+    for (uint32_t l = 0; l < lanes; l++)
+        for (uint64_t i = 0; i < config.PartitionNum; i++) {
+            PianoPIR *p = subPIR[i];
+            parts[(size_t)l * config.PartitionNum + i] = pm_client_part{p->server.row0, p->config.DBSize, p->config.ChunkSize, p->config.SetSize,
+                                                                        p->client.primaryHintNum, p->client.maxQueryPerChunk, p->client.MaxQueryNum};
+        }
     check(pm_client_create(db->h, parts.data(), parts.size(), &rclient), "pm_client_create");
     resident = true;
+    ownsClient = true;
+    partBase = 0;
+    clientLanes = lanes;
+}
+
+void SimpleBatchPianoPIR::AttachResidentClient(SimpleBatchPianoPIR *owner, uint32_t lane) {
+    if (resident) return;
+    if (!owner || !owner->resident || !owner->ownsClient || lane == 0 || lane >= owner->clientLanes)
+        throw std::runtime_error("AttachResidentClient: the owner has no resident client with that lane");
+    if (owner->config.PartitionNum != config.PartitionNum || owner->config.DBSize != config.DBSize ||
+        owner->config.DBEntrySize != config.DBEntrySize || owner->db != db)
+        throw std::runtime_error("AttachResidentClient: lanes must be clients of the same database with the same geometry");
+    rclient = owner->rclient;
+    resident = true;
+    ownsClient = false;
+    partBase = lane * (uint32_t)config.PartitionNum;
+    clientLanes = owner->clientLanes;
 }
 
 // Initialization + Preprocessing of the listed sub-PIRs on the device (keys and seeds derived as in the host path)
@@ -642,7 +661,9 @@ void SimpleBatchPianoPIR::PreprocessResident(const std::vector<uint32_t> &ids, b
     }
     check(pm_expand_key_batch(keys.data(), ids.size(), rk.data()), "pm_expand_key_batch");  // GetLongKey for every sub-PIR
     for (size_t a = 0; a < ids.size(); a++) subPIR[ids[a]]->client.longKey.assign(rk.begin() + a * 44, rk.begin() + (a + 1) * 44);
-    check(pm_client_preprocess(rclient, ids.data(), ids.size(), rk.data(), seeds.data(), skipPrep ? 1 : 0), "pm_client_preprocess");
+    std::vector<uint32_t> devIds(ids);
+    for (auto &v : devIds) v += partBase;
+    check(pm_client_preprocess(rclient, devIds.data(), devIds.size(), rk.data(), seeds.data(), skipPrep ? 1 : 0), "pm_client_preprocess");
 }
 
 void SimpleBatchPianoPIR::SyncTablesFromDevice(uint64_t i) {
@@ -654,9 +675,9 @@ void SimpleBatchPianoPIR::SyncTablesFromDevice(uint64_t i) {
     c.QueryHistogram.resize(subPIR[i]->config.SetSize);
     std::vector<uint64_t> *tabs[8] = {&c.primaryShortTag, &c.primaryParity, &c.primaryProgramPoint, &c.replacementIdx,
                                       &c.replacementVal, &c.backupShortTag, &c.backupParity, &c.QueryHistogram};
-    for (int t = 0; t < 8; t++) check(pm_client_download(rclient, (uint32_t)i, t, tabs[t]->data(), tabs[t]->size()), "pm_client_download");
+    for (int t = 0; t < 8; t++) check(pm_client_download(rclient, partBase + (uint32_t)i, t, tabs[t]->data(), tabs[t]->size()), "pm_client_download");
     uint64_t fin = 0;
-    check(pm_client_download(rclient, (uint32_t)i, 8, &fin, 1), "pm_client_download");
+    check(pm_client_download(rclient, partBase + (uint32_t)i, 8, &fin, 1), "pm_client_download");
     c.FinishedQueryNum = fin;
 }
 
@@ -670,120 +691,84 @@ int SimpleBatchPianoPIR::QueryResident(const std::vector<uint64_t> &idx, std::ve
     return 0;
 }
 
-// Flat form of Query for the resident client: out is [n][DBEntrySize].  With query_vec != nullptr it also returns
-// dists[i] = L2Dist(vector part of out[i], query_vec) from the same GPU call (NaN where the entry came from the
-// local cache and no distance was computed).  Scratch vectors are members: no allocation on the steady-state path.
-int SimpleBatchPianoPIR::QueryFlat(const uint64_t *idx, size_t n, uint64_t *out, const float *query_vec, uint64_t dim, float *dists) {
+// ---- the pieces of one resident Query call (batch-pir.go:170-248 over pm_client_*) ----
+// bucket the indices by partition (batch-pir.go:177-187) and reset the per-call scratch
+void SimpleBatchPianoPIR::beginCall(const uint64_t *idx, size_t n, bool *bad) {
     const uint64_t PN = config.PartitionNum, PS = config.PartitionSize, E = config.DBEntrySize;
-    const float kNaN = std::nanf("");
-    if (!resident) {
-        std::vector<uint64_t> v(idx, idx + n);
-        std::vector<std::vector<uint64_t>> r;
-        int rc = Query(v, &r);
-        if (rc != 0) return rc;
-        for (size_t i = 0; i < n; i++) memcpy(out + i * E, r[i].data(), E * 8);
-        if (dists) for (size_t i = 0; i < n; i++) dists[i] = kNaN;
-        return 0;
-    }
-    struct Timer {
-        double &acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-        ~Timer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
-    } timer{profQueryTotal};
-    profQueryCalls += 1;
-    const uint64_t queryNumToMake = n / PN;
-    auto &lists = wsLists;
-    lists.resize(PN);
-    for (auto &l : lists) l.clear();
+    *bad = false;
+    wsLists.resize(PN);
+    for (auto &l : wsLists) l.clear();
     for (size_t i = 0; i < n; i++) {
         uint64_t pi = idx[i] / PS;
-        if (pi >= PN) return -1;
-        lists[pi].push_back(idx[i]);
+        if (pi >= PN) { *bad = true; return; }
+        wsLists[pi].push_back(idx[i]);
     }
-    struct Resp { const uint64_t *entry; float dist; };
-    std::unordered_map<uint64_t, Resp> responses;
-    responses.reserve(n * 2);
-    auto &pend = wsPend;
-    auto &ql = wsQueries;
-    pend.clear();
-    ql.clear();
-    wsOut.resize(n * E);
-    wsStatus.resize(n);
-    wsDist.resize(n);
+    const uint64_t queryNumToMake = n / PN;
+    for (auto &l : wsLists) while (l.size() < queryNumToMake) l.push_back(DefaultValue);
+    wsResponses.clear();
+    wsResponses.reserve(n * 2);
+    wsPend.clear();
+    wsQueries.clear();
     wsZero.assign(E, 0);
-    std::vector<uint64_t> pendingReal(PN, 0);
-    size_t qbase = 0, pbase = 0;   // queries / pending records already settled by an earlier flush of this call
+    wsPendingReal.assign(PN, 0);
+}
 
-    auto flush = [&]() {
-        const size_t cnt = ql.size() - qbase;
-        if (cnt) {
-            auto tg = std::chrono::steady_clock::now();
-            if (query_vec)
-                check(pm_client_query_batch_l2(rclient, ql.data() + qbase, cnt, wsOut.data() + qbase * E, wsStatus.data() + qbase,
-                                               query_vec, dim, wsDist.data() + qbase), "pm_client_query_batch_l2");
-            else
-                check(pm_client_query_batch(rclient, ql.data() + qbase, cnt, wsOut.data() + qbase * E, wsStatus.data() + qbase),
-                      "pm_client_query_batch");
-            profGpuCall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
-            serverLaunches += 1;
-        }
-        for (size_t a = pbase; a < pend.size(); a++) {
-            const PendRec &pd = pend[a];
-            PianoPIRClient &c = subPIR[pd.part]->client;
-            if (pd.kind == 0) { serverQueries += 1; continue; }
-            if (pd.kind == 2) {  // served from the local cache (pir.go:381-383); an earlier failure of the same index repeats as zeros
-                auto it = c.localCache.find(pd.local);
-                responses[pd.global] = Resp{it != c.localCache.end() ? it->second.data() : wsZero.data(), kNaN};
-                continue;
-            }
-            const uint64_t *r = wsOut.data() + (size_t)pd.qpos * E;
-            if (wsStatus[pd.qpos] == 0) {
-                serverQueries += 1;
-                c.FinishedQueryNum += 1;
-                c.localCache[pd.local].assign(r, r + E);
-            }
-            for (size_t k = 0; k < c.pendingCached.size(); k++)
-                if (c.pendingCached[k] == pd.local) { c.pendingCached.erase(c.pendingCached.begin() + (long)k); break; }
-            responses[pd.global] = Resp{r, query_vec ? wsDist[pd.qpos] : kNaN};
-        }
-        qbase = ql.size();
-        pbase = pend.size();
-        std::fill(pendingReal.begin(), pendingReal.end(), 0);
-    };
-
-    for (uint64_t i = 0; i < PN; i++) {
-        auto &lst = lists[i];
-        while (lst.size() < queryNumToMake) lst.push_back(DefaultValue);
-        PianoPIR *p = subPIR[i];
-        PianoPIRClient &c = p->client;
-        for (uint64_t j = 0; j < queryNumToMake; j++) {
-            // pir.go:527-530 needs the exact FinishedQueryNum, which is only known after the pending queries ran
-            if (c.FinishedQueryNum + pendingReal[i] >= c.MaxQueryNum) {
-                flush();
-                if (c.FinishedQueryNum == c.MaxQueryNum) PreprocessResident({(uint32_t)i}, c.skipPrep);
-            }
-            if (lst[j] == DefaultValue) {
-                ql.push_back(pm_client_query{(uint32_t)i, 0, 0, c.dummySeed, c.dummyCtr});
-                c.dummyCtr += p->config.SetSize;
-                pend.push_back(PendRec{i, DefaultValue, 0, 0, (int64_t)ql.size() - 1});
-                continue;
-            }
-            const uint64_t local = lst[j] - i * PS;
-            bool cached = c.localCache.count(local) != 0;
-            for (size_t k = 0; !cached && k < c.pendingCached.size(); k++) cached = c.pendingCached[k] == local;
-            if (cached) {
-                pend.push_back(PendRec{i, lst[j], local, 2, -1});
-            } else {
-                ql.push_back(pm_client_query{(uint32_t)i, 1, local, 0, 0});
-                c.pendingCached.push_back(local);
-                pendingReal[i] += 1;
-                pend.push_back(PendRec{i, lst[j], local, 1, (int64_t)ql.size() - 1});
-            }
-        }
+// one sub-query of partition `part` (batch-pir.go:189-216 / pir.go:354-383): a dummy, a local-cache hit, or a record for the GPU
+void SimpleBatchPianoPIR::pushRecord(uint64_t part, uint64_t globalIdx) {
+    PianoPIR *p = subPIR[part];
+    PianoPIRClient &c = p->client;
+    if (globalIdx == DefaultValue) {
+        wsQueries.push_back(pm_client_query{partBase + (uint32_t)part, 0, 0, c.dummySeed, c.dummyCtr});
+        c.dummyCtr += p->config.SetSize;
+        wsPend.push_back(PendRec{part, DefaultValue, 0, 0, (int64_t)wsQueries.size() - 1});
+        return;
     }
-    flush();
+    const uint64_t local = globalIdx - part * config.PartitionSize;
+    bool cached = c.localCache.count(local) != 0;
+    for (size_t k = 0; !cached && k < c.pendingCached.size(); k++) cached = c.pendingCached[k] == local;
+    if (cached) {
+        wsPend.push_back(PendRec{part, globalIdx, local, 2, -1});
+    } else {
+        wsQueries.push_back(pm_client_query{partBase + (uint32_t)part, 1, local, 0, 0});
+        c.pendingCached.push_back(local);
+        wsPendingReal[part] += 1;
+        wsPend.push_back(PendRec{part, globalIdx, local, 1, (int64_t)wsQueries.size() - 1});
+    }
+}
+
+// book the answers of the records wsPend[pbase..]: res / status / dist are indexed by the record's position in wsQueries
+void SimpleBatchPianoPIR::settle(size_t pbase, const uint64_t *res, const int32_t *status, const float *dist) {
+    const uint64_t E = config.DBEntrySize;
+    const float kNaN = std::nanf("");
+    for (size_t a = pbase; a < wsPend.size(); a++) {
+        const PendRec &pd = wsPend[a];
+        PianoPIRClient &c = subPIR[pd.part]->client;
+        if (pd.kind == 0) { serverQueries += 1; continue; }
+        if (pd.kind == 2) {  // served from the local cache (pir.go:381-383); an earlier failure of the same index repeats as zeros
+            auto it = c.localCache.find(pd.local);
+            wsResponses[pd.global] = Resp{it != c.localCache.end() ? it->second.data() : wsZero.data(), kNaN};
+            continue;
+        }
+        const uint64_t *r = res + (size_t)pd.qpos * E;
+        if (status[pd.qpos] == 0) {
+            serverQueries += 1;
+            c.FinishedQueryNum += 1;
+            c.localCache[pd.local].assign(r, r + E);
+        }
+        for (size_t k = 0; k < c.pendingCached.size(); k++)
+            if (c.pendingCached[k] == pd.local) { c.pendingCached.erase(c.pendingCached.begin() + (long)k); break; }
+        wsResponses[pd.global] = Resp{r, dist ? dist[pd.qpos] : kNaN};
+    }
+    std::fill(wsPendingReal.begin(), wsPendingReal.end(), 0);
+}
+
+// responses keyed by global index, zero rows for misses (batch-pir.go:218-237), then the batch accounting (:239-245)
+bool SimpleBatchPianoPIR::finishCall(const uint64_t *idx, size_t n, uint64_t *out, float *dists) {
+    const uint64_t E = config.DBEntrySize;
+    const float kNaN = std::nanf("");
     for (size_t i = 0; i < n; i++) {
-        auto it = responses.find(idx[i]);
-        if (it != responses.end()) {
+        auto it = wsResponses.find(idx[i]);
+        if (it != wsResponses.end()) {
             memcpy(out + i * E, it->second.entry, E * 8);
             if (dists) dists[i] = it->second.dist;
         } else {
@@ -791,12 +776,160 @@ int SimpleBatchPianoPIR::QueryFlat(const uint64_t *idx, size_t n, uint64_t *out,
             if (dists) dists[i] = kNaN;
         }
     }
-    if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) {
-        Preprocessing();
-    } else {
-        FinishedBatchNum += n / config.BatchSize;
-        QueriesMadeInPartition += queryNumToMake;
+    if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) return true;
+    FinishedBatchNum += n / config.BatchSize;
+    QueriesMadeInPartition += n / config.PartitionNum;
+    return false;
+}
+
+// pir.go:527-530 re-preprocesses a sub-PIR whose query budget is used up; that needs the exact FinishedQueryNum, i.e.
+// the pending queries must have run.  True when this call could reach that point for some sub-PIR.
+bool SimpleBatchPianoPIR::mayFlushInside(size_t n) const {
+    const uint64_t per = n / config.PartitionNum;
+    for (auto *p : subPIR)
+        if (p->client.FinishedQueryNum + per >= p->client.MaxQueryNum) return true;
+    return false;
+}
+
+// Flat form of Query for the resident client: out is [n][DBEntrySize].  With query_vec != nullptr it also returns
+// dists[i] = L2Dist(vector part of out[i], query_vec) from the same GPU call (NaN where the entry came from the
+// local cache and no distance was computed).  Scratch vectors are members: no allocation on the steady-state path.
+int SimpleBatchPianoPIR::QueryFlat(const uint64_t *idx, size_t n, uint64_t *out, const float *query_vec, uint64_t dim, float *dists) {
+    const uint64_t PN = config.PartitionNum, E = config.DBEntrySize;
+    if (!resident) {
+        std::vector<uint64_t> v(idx, idx + n);
+        std::vector<std::vector<uint64_t>> r;
+        int rc = Query(v, &r);
+        if (rc != 0) return rc;
+        for (size_t i = 0; i < n; i++) memcpy(out + i * E, r[i].data(), E * 8);
+        if (dists) for (size_t i = 0; i < n; i++) dists[i] = std::nanf("");
+        return 0;
     }
+    struct Timer {
+        double &acc; std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+        ~Timer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+    } timer{profQueryTotal};
+    profQueryCalls += 1;
+    bool bad = false;
+    beginCall(idx, n, &bad);
+    if (bad) return -1;
+    const uint64_t queryNumToMake = n / PN;
+    wsOut.resize(n * E);
+    wsStatus.resize(n);
+    wsDist.resize(n);
+    size_t qbase = 0, pbase = 0;   // queries / pending records already settled by an earlier flush of this call
+
+    auto flush = [&]() {
+        const size_t cnt = wsQueries.size() - qbase;
+        if (cnt) {
+            auto tg = std::chrono::steady_clock::now();
+            if (query_vec)
+                check(pm_client_query_batch_l2(rclient, wsQueries.data() + qbase, cnt, wsOut.data() + qbase * E, wsStatus.data() + qbase,
+                                               query_vec, dim, wsDist.data() + qbase), "pm_client_query_batch_l2");
+            else
+                check(pm_client_query_batch(rclient, wsQueries.data() + qbase, cnt, wsOut.data() + qbase * E, wsStatus.data() + qbase),
+                      "pm_client_query_batch");
+            profGpuCall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
+            serverLaunches += 1;
+        }
+        settle(pbase, wsOut.data(), wsStatus.data(), query_vec ? wsDist.data() : nullptr);
+        qbase = wsQueries.size();
+        pbase = wsPend.size();
+    };
+
+    for (uint64_t i = 0; i < PN; i++) {
+        PianoPIRClient &c = subPIR[i]->client;
+        for (uint64_t j = 0; j < queryNumToMake; j++) {
+            // pir.go:527-530 needs the exact FinishedQueryNum, which is only known after the pending queries ran
+            if (c.FinishedQueryNum + wsPendingReal[i] >= c.MaxQueryNum) {
+                flush();
+                if (c.FinishedQueryNum == c.MaxQueryNum) PreprocessResident({(uint32_t)i}, c.skipPrep);
+            }
+            pushRecord(i, wsLists[i][j]);
+        }
+    }
+    flush();
+    if (finishCall(idx, n, out, dists)) Preprocessing();
+    return 0;
+}
+
+// Several lanes of one pm_client in one device call.  Host work per lane (bucketing, cache checks, booking the answers)
+// runs in parallel over the lanes; the lanes share nothing on the host.
+int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t dim) {
+    if (calls.empty()) return 0;
+    const size_t L = calls.size();
+    pm_client *client = calls[0].pir->rclient;
+    const uint64_t E = calls[0].pir->config.DBEntrySize;
+    std::vector<char> grouped(L, 0);
+    for (size_t l = 0; l < L; l++) {
+        SimpleBatchPianoPIR *p = calls[l].pir;
+        calls[l].rc = 0;
+        grouped[l] = p->resident && p->rclient == client && client != nullptr && !p->mayFlushInside(calls[l].n) && p->config.DBEntrySize == E;
+    }
+    // lanes that cannot take part (not resident, another client, a sub-PIR about to exhaust its budget) run on their own
+    for (size_t l = 0; l < L; l++)
+        if (!grouped[l]) calls[l].rc = calls[l].pir->QueryFlat(calls[l].idx, calls[l].n, calls[l].out, calls[l].query_vec, dim, calls[l].dists);
+    std::vector<size_t> base(L + 1, 0);
+#pragma omp parallel for schedule(static) if (L > 2)
+    for (size_t l = 0; l < L; l++) {
+        if (!grouped[l]) continue;
+        SimpleBatchPianoPIR *p = calls[l].pir;
+        bool bad = false;
+        p->profQueryCalls += 1;
+        p->beginCall(calls[l].idx, calls[l].n, &bad);
+        if (bad) { calls[l].rc = -1; p->wsQueries.clear(); p->wsPend.clear(); continue; }
+        const uint64_t per = calls[l].n / p->config.PartitionNum;
+        for (uint64_t i = 0; i < p->config.PartitionNum; i++)
+            for (uint64_t j = 0; j < per; j++) p->pushRecord(i, p->wsLists[i][j]);
+    }
+    for (size_t l = 0; l < L; l++) base[l + 1] = base[l] + (grouped[l] ? calls[l].pir->wsQueries.size() : 0);
+    const size_t total = base[L];
+    // group scratch lives in the first grouped lane's members
+    SimpleBatchPianoPIR *host = nullptr;
+    for (size_t l = 0; l < L && !host; l++) if (grouped[l]) host = calls[l].pir;
+    if (!host) return 0;
+    static thread_local std::vector<pm_client_query> gq;
+    static thread_local std::vector<uint32_t> gvec;
+    static thread_local std::vector<float> gqv;
+    gq.resize(total);
+    gvec.resize(total);
+    gqv.assign(L * dim, 0.f);
+    bool anyVec = false;
+    for (size_t l = 0; l < L; l++) {
+        if (!grouped[l]) continue;
+        SimpleBatchPianoPIR *p = calls[l].pir;
+        std::copy(p->wsQueries.begin(), p->wsQueries.end(), gq.begin() + (long)base[l]);
+        std::fill(gvec.begin() + (long)base[l], gvec.begin() + (long)base[l + 1], (uint32_t)l);
+        if (calls[l].query_vec) { memcpy(&gqv[l * dim], calls[l].query_vec, dim * 4); anyVec = true; }
+    }
+    host->wsOut.resize(std::max<size_t>(host->wsOut.size(), total * E));
+    host->wsStatus.resize(std::max(host->wsStatus.size(), total));
+    host->wsDist.resize(std::max(host->wsDist.size(), total));
+    if (total) {
+        auto tg = std::chrono::steady_clock::now();
+        if (anyVec && dim)
+            check(pm_client_query_batch_l2m(client, gq.data(), total, host->wsOut.data(), host->wsStatus.data(), gqv.data(), L, gvec.data(), dim,
+                                            host->wsDist.data()), "pm_client_query_batch_l2m");
+        else
+            check(pm_client_query_batch(client, gq.data(), total, host->wsOut.data(), host->wsStatus.data()), "pm_client_query_batch");
+        host->profGpuCall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
+        host->serverLaunches += 1;
+    }
+    const uint64_t *gout = host->wsOut.data();
+    const int32_t *gst = host->wsStatus.data();
+    const float *gdist = host->wsDist.data();
+    std::vector<char> due(L, 0);
+#pragma omp parallel for schedule(static) if (L > 2)
+    for (size_t l = 0; l < L; l++) {
+        if (!grouped[l] || calls[l].rc != 0) continue;
+        SimpleBatchPianoPIR *p = calls[l].pir;
+        p->settle(0, gout + base[l] * E, gst + base[l], (anyVec && dim && calls[l].query_vec) ? gdist + base[l] : nullptr);
+        due[l] = p->finishCall(calls[l].idx, calls[l].n, calls[l].out, calls[l].dists) ? 1 : 0;
+    }
+    for (size_t l = 0; l < L; l++)
+        if (due[l]) calls[l].pir->Preprocessing();   // batch-pir.go:239-245; device calls of one pm_client are serialised anyway
+    for (size_t l = 0; l < L; l++)
+        if (calls[l].rc != 0) return calls[l].rc;
     return 0;
 }
 

@@ -160,10 +160,25 @@ public:
     // GPU-resident client (pm_client_*): hint tables stay in HBM, hint search / refresh run on the GPU.
     // Must be enabled before Preprocessing(); the host-side tables of the sub-PIRs are then only refreshed on
     // request (SyncTablesFromDevice), counters and the local cache stay on the host.
-    void EnableResidentClient();
+    // lanes > 1: the pm_client is created with lanes * PartitionNum parts; lane 0 is this object, further independent
+    // client instances (own keys, hint tables, caches, counters) attach to it as lanes 1.. and can then be driven in
+    // lock step by QueryFlatGroup -- one pm_client_query_batch_l2m call for all of them.
+    void EnableResidentClient(uint32_t lanes = 1);
+    void AttachResidentClient(SimpleBatchPianoPIR *owner, uint32_t lane);
     void SyncTablesFromDevice(uint64_t i);
     int QueryFlat(const uint64_t *idx, size_t n, uint64_t *out, const float *query_vec, uint64_t dim, float *dists);
+    struct GroupCall {
+        SimpleBatchPianoPIR *pir;
+        const uint64_t *idx; size_t n; uint64_t *out;   // as QueryFlat
+        const float *query_vec; float *dists;           // query_vec may be null (then no distances for this lane)
+        int rc;
+    };
+    // QueryFlat of several lanes of one pm_client at once.  Every lane ends in exactly the state its own QueryFlat
+    // would have left (a lane that may exhaust a sub-PIR's budget inside this call is simply run on its own).
+    static int QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t dim);
     bool resident = false;
+    bool ownsClient = true;
+    uint32_t partBase = 0, clientLanes = 1;
     double profQueryTotal = 0, profGpuCall = 0;  // PM_HOST_PROFILE=1 prints them when the object is destroyed
     uint64_t profQueryCalls = 0;
     pm_client *rclient = nullptr;
@@ -177,6 +192,15 @@ private:
     std::vector<uint64_t> wsOut, wsZero;
     std::vector<int32_t> wsStatus;
     std::vector<float> wsDist;
+    struct Resp { const uint64_t *entry; float dist; };
+    std::unordered_map<uint64_t, Resp> wsResponses;
+    std::vector<uint64_t> wsPendingReal;
+    // the three pieces of QueryFlat, shared with QueryFlatGroup
+    void beginCall(const uint64_t *idx, size_t n, bool *bad);
+    void pushRecord(uint64_t part, uint64_t globalIdx);
+    void settle(size_t pbase, const uint64_t *res, const int32_t *status, const float *dist);
+    bool finishCall(const uint64_t *idx, size_t n, uint64_t *out, float *dists);   // true: the batch budget is used up, Preprocessing() is due
+    bool mayFlushInside(size_t n) const;
     void PreprocessResident(const std::vector<uint32_t> &ids, bool skipPrep);
     int QueryResident(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret);
     void Flush(std::vector<PendingQuery> &pend, std::vector<uint64_t> &pend_part, std::vector<uint64_t> &pend_global,

@@ -74,15 +74,16 @@ __global__ void __launch_bounds__(L2_THREADS) l2_batch_kernel(const uint64_t *db
         if (in && half == 0) out[q * k + j] = ok ? d : INFINITY;
     }
 }
+// b row of pair i: b + i*b_stride, or b + b_index[i]*b_stride when b_index is given (several queries in one call)
 __global__ void __launch_bounds__(L2_THREADS) l2_pairs_kernel(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride,
-                                                              uint64_t n, uint32_t dim, float *out) {
+                                                              const uint32_t *b_index, uint64_t n, uint32_t dim, float *out) {
     const int half = threadIdx.x & 1;
     const uint64_t stride = (uint64_t)gridDim.x * (L2_THREADS / 2);
     const uint64_t n_up = (n + 15) & ~15ull;  // keep whole warps in the shuffle
     for (uint64_t i = (uint64_t)blockIdx.x * (L2_THREADS / 2) + (threadIdx.x >> 1); i < n_up; i += stride) {
         const bool ok = i < n;
         const uint64_t r = ok ? i : 0;
-        float d = l2_pair<false>(a + r * a_stride, b + r * b_stride, dim, half);
+        float d = l2_pair<false>(a + r * a_stride, b + (b_index ? (uint64_t)b_index[r] : r) * b_stride, dim, half);
         if (ok && half == 0) out[i] = d;
     }
 }
@@ -165,12 +166,12 @@ __global__ void __launch_bounds__(IP_THREADS, 2) ip_scan_kernel(const uint4 *row
 }
 
 // out[i] = L2Dist(a + i*a_stride, b + i*b_stride) for device-resident rows (strides in floats; b_stride 0 = one query)
-int l2_rows_enqueue(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride, uint64_t n, uint32_t dim, float *out,
-                    cudaStream_t st) {
+int l2_rows_enqueue(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride, const uint32_t *b_index, uint64_t n,
+                    uint32_t dim, float *out, cudaStream_t st) {
     if (n == 0) return PM_OK;
     uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS, 0, st>>>(a, a_stride, b, b_stride, n, dim, out);
+    l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS, 0, st>>>(a, a_stride, b, b_stride, b_index, n, dim, out);
     PM_CHECK_LAUNCH();
     count_launch();
     return PM_OK;
@@ -257,7 +258,7 @@ static int l2_host(const float *a, const float *b, uint64_t b_rows, uint64_t n, 
     PM_CUDA(cudaMemcpyAsync(d_b, b, bb, cudaMemcpyHostToDevice, st));
     uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS, 0, st>>>(d, dim, d_b, b_rows == 1 ? 0 : dim, n, (uint32_t)dim, d_out);
+    l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS, 0, st>>>(d, dim, d_b, b_rows == 1 ? 0 : dim, nullptr, n, (uint32_t)dim, d_out);
     PM_CHECK_LAUNCH();
     count_launch();
     PM_CUDA(cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, st));

@@ -530,18 +530,26 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
 }
 
 static int client_query_impl(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
-                             const float *query_vec, uint64_t dim, float *dist_out);
+                             const float *query_vec, uint64_t n_vecs, const uint32_t *vec_id, uint64_t dim, float *dist_out);
 PM_EXPORT int pm_client_query_batch(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status) {
-    return client_query_impl(c, queries, q, out, status, nullptr, 0, nullptr);
+    return client_query_impl(c, queries, q, out, status, nullptr, 0, nullptr, 0, nullptr);
 }
 PM_EXPORT int pm_client_query_batch_l2(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
                                        const float *query_vec, uint64_t dim, float *dist_out) {
     if (!query_vec || !dist_out || dim == 0) return pm::set_error(PM_ERR_ARG, "pm_client_query_batch_l2: null pointer");
     if (c && dim * 4 > c->E * 8) return pm::set_error(PM_ERR_ARG, "pm_client_query_batch_l2: dim does not fit in an entry");
-    return client_query_impl(c, queries, q, out, status, query_vec, dim, dist_out);
+    return client_query_impl(c, queries, q, out, status, query_vec, 1, nullptr, dim, dist_out);
+}
+PM_EXPORT int pm_client_query_batch_l2m(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
+                                        const float *query_vecs, uint64_t n_vecs, const uint32_t *vec_id, uint64_t dim, float *dist_out) {
+    if (!query_vecs || !vec_id || !dist_out || dim == 0 || n_vecs == 0) return pm::set_error(PM_ERR_ARG, "pm_client_query_batch_l2m: null pointer");
+    if (c && dim * 4 > c->E * 8) return pm::set_error(PM_ERR_ARG, "pm_client_query_batch_l2m: dim does not fit in an entry");
+    for (uint64_t t = 0; t < q; t++)
+        if (vec_id[t] >= n_vecs) return pm::set_error(PM_ERR_ARG, "pm_client_query_batch_l2m: vec_id out of range");
+    return client_query_impl(c, queries, q, out, status, query_vecs, n_vecs, vec_id, dim, dist_out);
 }
 static int client_query_impl(pm_client *c, const pm_client_query *queries, uint64_t q, uint64_t *out, int32_t *status,
-                             const float *query_vec, uint64_t dim, float *dist_out) {
+                             const float *query_vec, uint64_t n_vecs, const uint32_t *vec_id, uint64_t dim, float *dist_out) {
     using namespace pm;
     if (!c || (q && (!queries || !out || !status))) return set_error(PM_ERR_ARG, "pm_client_query_batch: null pointer");
     if (q == 0) return PM_OK;
@@ -563,8 +571,8 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     // staging: queries | meta | offsets | answer descriptors   and   answers | out
     const size_t b_q = q * sizeof(ClientQueryDev), b_meta = q * sizeof(ClientMeta), b_off = q * stride * 4, b_desc = q * 24;
     void *d_in = nullptr, *d_out = nullptr;
-    const size_t b_qv = (dim * 4 + 15) & ~15ull, b_dist = dist_out ? q * 4 : 0;
-    if ((rc = client_scratch(c, 1, b_q + b_off + b_desc + b_qv + 64, &d_in))) return rc;
+    const size_t b_qv = (n_vecs * dim * 4 + 15) & ~15ull, b_vid = vec_id ? q * 4 : 0, b_dist = dist_out ? q * 4 : 0;
+    if ((rc = client_scratch(c, 1, b_q + b_off + b_desc + b_qv + b_vid + 64, &d_in))) return rc;
     if ((rc = client_scratch(c, 0, 2 * q * E * 8 + b_meta + b_dist, &d_out))) return rc;
     ClientQueryDev *d_q = (ClientQueryDev *)d_in;
     uint32_t *d_off = (uint32_t *)((char *)d_in + b_q);
@@ -605,8 +613,10 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     PM_CHECK_LAUNCH();
     count_launch();
     if (dist_out) {  // distances of the answered entries' vectors to the search query, on the same stream (A10 call site)
-        PM_CUDA(cudaMemcpyAsync(d_qv, query_vec, dim * 4, cudaMemcpyHostToDevice, c->stream));
-        if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, 0, q, (uint32_t)dim, d_dist, c->stream))) return rc;
+        uint32_t *d_vid = vec_id ? (uint32_t *)((char *)d_qv + b_qv) : nullptr;
+        PM_CUDA(cudaMemcpyAsync(d_qv, query_vec, n_vecs * dim * 4, cudaMemcpyHostToDevice, c->stream));
+        if (vec_id) PM_CUDA(cudaMemcpyAsync(d_vid, vec_id, b_vid, cudaMemcpyHostToDevice, c->stream));
+        if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, vec_id ? dim : 0, d_vid, q, (uint32_t)dim, d_dist, c->stream))) return rc;
     }
     mark(4);
     PM_CUDA(cudaMemcpyAsync(c->stage, d_res, b_back, cudaMemcpyDeviceToHost, c->stream));

@@ -41,8 +41,8 @@ bool ipgemm_applicable(const pm_db *db, uint64_t dim, uint64_t nq, const uint32_
 size_t ipgemm_scratch_bytes(uint64_t dim, uint64_t nq);
 int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq, uint32_t *checksum, void *scratch_dev, cudaStream_t st);
 int ipgemm_check(void *scratch_dev, uint64_t dim, uint64_t nq);
-int l2_rows_enqueue(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride, uint64_t n, uint32_t dim, float *out,
-                    cudaStream_t st);  // pm_ann.cu  // 4 KB of device zeros, allocated once per device
+int l2_rows_enqueue(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride, const uint32_t *b_index, uint64_t n,
+                    uint32_t dim, float *out, cudaStream_t st);  // pm_ann.cu  // 4 KB of device zeros, allocated once per device
 // grow-only scratch slot on a handle
 int scratch(pm_db *db, int slot, size_t bytes, void **out);
 unsigned int *sync_counter(pm_db *db);  // next barrier counter of the handle's pool

@@ -24,16 +24,20 @@ class GraphANNFrontend:
     """graphann.GraphANNFrontend over BasicGraphInfo (non-private) or PIRGraphInfo (private, private-search.go)."""
 
     def __init__(self, vectors, graph, private=False, skipPrep=False, nonPrivateMode=False, seed=1, device=0, resident=True,
-                 share_db_with=None):
+                 share_db_with=None, group_lanes=1, lane_of=None, lane=0):
         """share_db_with: another private frontend (already preprocessed) whose GPU-resident rawDB this client reuses --
-        one DB replica per GPU, one client (keys, hint tables, search state) per user."""
+        one DB replica per GPU, one client (keys, hint tables, search state) per user.
+        group_lanes / lane_of / lane: client groups for SearchKNNLockstep -- the first client is created with
+        group_lanes=L and preprocessed, clients 1..L-1 with lane_of=first, lane=i (see make_client_group)."""
         self.vectors = np.ascontiguousarray(vectors, np.float32)
         self.graph = np.ascontiguousarray(graph, np.int32)
         self.n, self.dim = self.vectors.shape
         self.m = self.graph.shape[1]
         L = _host.lib()
-        self._shared = share_db_with      # keep the owner of the DB alive
-        if share_db_with is not None:
+        self._shared = share_db_with if share_db_with is not None else lane_of      # keep the owner of the DB / client group alive
+        if lane_of is not None:
+            h = L.pmh_frontend_pir_lane(lane_of.h, seed, lane)
+        elif share_db_with is not None:
             h = L.pmh_frontend_pir_shared(share_db_with.h, seed, int(resident))
         elif private:
             h = L.pmh_frontend_pir(self.n, self.dim, self.m, _p(self.graph), _p(self.vectors), int(skipPrep), int(nonPrivateMode), seed, device, int(resident))
@@ -42,7 +46,9 @@ class GraphANNFrontend:
         if not h:
             raise _host.HostError(L.pmh_last_error().decode())
         self.h = C.c_void_p(h)
-        self.private = private or share_db_with is not None
+        self.private = private or share_db_with is not None or lane_of is not None
+        if group_lanes > 1:
+            _host.check(L.pmh_frontend_set_group_lanes(self.h, group_lanes))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -92,3 +98,31 @@ class GraphANNFrontend:
     @property
     def succQueryNum(self):
         return _host.lib().pmh_frontend_stat(self.h, 1)
+
+
+def make_client_group(vectors, graph, lanes, seeds=None, skipPrep=False, device=0):
+    """L independent private clients (own keys, hint tables, caches, search state) over ONE GPU-resident rawDB whose hint
+    tables live in ONE pm_client, preprocessed and ready for SearchKNNLockstep.  seeds[i] = client i's seed."""
+    seeds = list(seeds) if seeds is not None else [1 + i for i in range(lanes)]
+    first = GraphANNFrontend(vectors, graph, private=True, skipPrep=skipPrep, seed=seeds[0], device=device, group_lanes=lanes)
+    first.Preprocess()
+    group = [first]
+    for i in range(1, lanes):
+        f = GraphANNFrontend(first.vectors, first.graph, seed=seeds[i], lane_of=first, lane=i)
+        f.Preprocess()
+        group.append(f)
+    return group
+
+
+def SearchKNNLockstep(lanes, queryVectors, k, maxStep, parallel, benchmarking=False):
+    """SearchKNNBatch over the clients of a group in lock step: query i is searched by lanes[i % L]; the results equal
+    each client's own SearchKNNBatch over its queries, every step's fetches of all lanes share one device call."""
+    dim = lanes[0].dim
+    q = np.ascontiguousarray(queryVectors, np.float32).reshape(-1, dim)
+    ret = np.zeros((q.shape[0], k), np.int64)
+    step = np.zeros((q.shape[0], k), np.int64)
+    hs = (C.c_void_p * len(lanes))(*[f.h for f in lanes])
+    rc = _host.check(_host.lib().pmh_search_knn_lockstep(hs, len(lanes), _p(q), q.shape[0], k, maxStep, parallel, int(benchmarking), _p(ret), _p(step)))
+    if rc != 0:
+        raise RuntimeError("GetVertexInfo failed")
+    return ret, step

@@ -101,3 +101,29 @@ def test_benchmark_mode_issues_random_queries(oracle):
     # every slot is a server query unless its index repeated (local cache) or no hint matched
     assert 0.9 * 192 <= f.PIR.serverQueries <= 3 * 4 * 2 * m
     assert f.PIR.serverLaunches == 3 * 4
+
+
+@pytest.mark.parametrize("lanes,nq,steps", [(3, 11, 10), (2, 44, 12)])
+def test_lockstep_client_group_matches_oracle(oracle, lanes, nq, steps):
+    """L independent clients whose hint tables live in ONE pm_client, searched in lock step (one device
+    call per step for all lanes).  Query i goes to lane i % L and every lane must return exactly what the CPU oracle
+    returns for a client with that lane's seed running its queries alone -- also across the batch budget
+    (second case: each lane re-preprocesses several times, and the call before that runs outside the group)."""
+    from pacmann_b200 import graphann
+    from pacmann_b200.keys import mix64
+    n, dim, m = 6000, 32, 8
+    vec, graph = make_dataset(n, dim, m, 164)
+    queries = vec[np.random.default_rng(165).integers(0, n, nq)] + np.float32(0.02)
+    seeds = [300 + 7 * i for i in range(lanes)]
+    group = graphann.make_client_group(vec, graph, lanes, seeds=seeds)
+    ret, step = graphann.SearchKNNLockstep(group, queries, 10, steps, 2)
+    raw = oracle.pack_db(vec, graph)
+    for l in range(lanes):
+        o_pir = oracle.SimpleBatchPianoPIR(n, (dim + m) * 4, m, raw, 8)
+        o_pir.preprocessing(key_seed=mix64(seeds[l], 1), repl_seed=mix64(seeds[l], 2), threads=4)
+        o_ret, o_step, stats = oracle.search_knn_private(o_pir, vec, graph, group[l].StartVertexIds(), queries[l::lanes], 10, steps, 2)
+        assert (ret[l::lanes] == o_ret).all() and (step[l::lanes] == o_step).all(), f"lane {l}"
+        assert (group[l].totalQueryNum, group[l].succQueryNum) == (int(stats[0]), int(stats[1]))
+    # a lane keeps working on its own afterwards (same pm_client, its own parts)
+    solo_ret, _ = group[lanes - 1].SearchKNNBatch(queries[:2], 10, steps, 2)
+    assert solo_ret.shape == (2, 10)
