@@ -168,6 +168,11 @@ int pm_client_query_batch_l2m(pm_client *c, const pm_client_query *queries, uint
  * 8 FinishedQueryNum */
 int pm_client_download(pm_client *c, uint32_t part, int table, uint64_t *out, uint64_t cap_words);
 
+/* Page-locked host memory for callers that want result buffers the GPU can write directly (any host pointer works
+ * everywhere; a pm_host_alloc'ed `out` of pm_client_query_batch* just saves one host-side copy of the answers). */
+int pm_host_alloc(void **out, uint64_t bytes);
+int pm_host_free(void *p);
+
 /* A9: squared L2 in the reference's exact fp32 order.  out[i] = L2Dist(a[i], b[i]), rows of `dim` floats. */
 int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device);
 /* out[i] = L2Dist(vecs[i], query): one query against n host vectors (SearchKNN's per-step and re-rank call sites) */

@@ -69,6 +69,8 @@ SIGNATURES = {
     "pm_client_query_batch_l2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_client_query_batch_l2m": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                             C.c_uint64, C.c_void_p]),
+    "pm_host_alloc": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "pm_host_free": (C.c_int, [C.c_void_p]),
     "pm_client_download": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64]),
     "pm_l2_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]),
     "pm_l2_query": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),

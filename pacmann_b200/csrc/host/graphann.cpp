@@ -2,7 +2,10 @@
 #include "graphann.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <unordered_map>
@@ -130,26 +133,36 @@ int PIRGraphInfo::GetVertexInfoWithDist(const std::vector<int64_t> &ids, const f
     return 0;
 }
 
-// GetVertexInfoWithDist of several lanes of one resident client group: ONE QueryFlatGroup for all of them
-int PIRGraphInfo::GetVertexInfoWithDistGroup(const std::vector<PIRGraphInfo *> &infos, const std::vector<const std::vector<int64_t> *> &ids,
-                                             const std::vector<const float *> &queries, const std::vector<std::vector<Vertex> *> &outs,
-                                             const std::vector<std::vector<float> *> &dists) {
+// GetVertexInfoWithDist of several lanes of one resident client group: ONE QueryFlatGroup for all of them.
+// Raw form: entries[l][i] points at the fetched entry of ids[l][i] (wire format of private-search.go:355-439), valid
+// until lane l's next fetch -- the search state reads neighbour lists and vectors in place, no Vertex objects are built.
+int PIRGraphInfo::FetchGroupRaw(const std::vector<PIRGraphInfo *> &infos, const std::vector<const std::vector<int64_t> *> &ids,
+                                const std::vector<const float *> &queries, const std::vector<std::vector<const uint64_t *> *> &entries,
+                                const std::vector<std::vector<float> *> &dists) {
     const size_t L = infos.size();
     std::vector<pianopir::SimpleBatchPianoPIR::GroupCall> calls(L);
     for (size_t l = 0; l < L; l++) {
         PIRGraphInfo *g = infos[l];
-        const uint64_t E = g->DBEntryByteNum / 8;
         const size_t cnt = ids[l]->size();
         g->totalQueryNum += (int64_t)cnt;
-        outs[l]->resize(cnt);
+        entries[l]->assign(cnt, nullptr);
         dists[l]->assign(cnt, std::nanf(""));
         g->wsIdx.assign(ids[l]->begin(), ids[l]->end());
-        g->wsResp.resize(cnt * E);
-        calls[l] = {g->PIR, g->wsIdx.data(), cnt, g->wsResp.data(), queries[l], queries[l] ? dists[l]->data() : nullptr, 0};
+        calls[l] = {g->PIR, g->wsIdx.data(), cnt, nullptr, queries[l], queries[l] ? dists[l]->data() : nullptr, 0, entries[l]->data()};
     }
     if (pianopir::SimpleBatchPianoPIR::QueryFlatGroup(calls, (uint64_t)infos[0]->Dim) != 0) return -1;
 #pragma omp parallel for schedule(static) if (L > 2)
-    for (size_t l = 0; l < L; l++) infos[l]->unpackResponses(*ids[l], outs[l]);
+    for (size_t l = 0; l < L; l++) {   // the reference's correctness accounting (private-search.go:480-504)
+        PIRGraphInfo *g = infos[l];
+        for (size_t i = 0; i < ids[l]->size(); i++) {
+            const uint32_t *nb = (const uint32_t *)((const uint8_t *)(*entries[l])[i] + g->Dim * 4);
+            const int32_t *want = g->graph + (*ids[l])[i] * g->M;
+            bool correctQ = true;
+            for (int64_t j = 0; j < g->M; j++)
+                if (nb[j] != (uint32_t)want[j]) { correctQ = false; break; }
+            if (correctQ) g->succQueryNum++;
+        }
+    }
     return 0;
 }
 
@@ -307,42 +320,96 @@ bool SearchState::NextBatch(std::vector<int64_t> *batchQ) {
     return true;
 }
 
-// search.go:169-208 for the fetched vertices of this step
-void SearchState::Consume(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists) {
-    const int64_t thisStep = step++;
-    if (benchmarking) return;
-    // newly discovered vertices of this step, in batch order (a repeated id is "already known" by its second occurrence)
-    fresh.clear();
-    for (size_t i = 0; i < queryResults.size(); i++) {
-        const Vertex &v = queryResults[i];
-        if (slotOf.count(v.Id)) continue;
-        bool dup = false;
-        for (size_t t : fresh) dup = dup || queryResults[t].Id == v.Id;
-        if (dup) continue;
-        bool ok = false;
-        for (int64_t nb : v.Neighbors) if (nb != 0) { ok = true; break; }   // all-zero list = failed fetch (search.go:192-199)
-        if (ok) fresh.push_back(i);
+// The fetched vertices of a step as the search reads them: Vertex objects (GetGraphInfo interface) or entries in the
+// wire format of private-search.go:355-439 read in place.
+struct VertexAccess {
+    const std::vector<Vertex> &v;
+    size_t size() const { return v.size(); }
+    int64_t id(size_t i) const { return v[i].Id; }
+    int64_t neighbor(size_t i, int64_t j) const { return v[i].Neighbors[(size_t)j]; }
+    int64_t degree(size_t i) const { return (int64_t)v[i].Neighbors.size(); }
+    const float *vector(size_t i) const { return v[i].Vector.data(); }
+};
+struct RawAccess {
+    const std::vector<int64_t> &ids;
+    const std::vector<const uint64_t *> &e;
+    int64_t dim, m;
+    size_t size() const { return ids.size(); }
+    int64_t id(size_t i) const { return ids[i]; }
+    int64_t neighbor(size_t i, int64_t j) const {
+        uint32_t v;
+        memcpy(&v, (const uint8_t *)e[i] + dim * 4 + j * 4, 4);
+        return (int64_t)v;
     }
-    // their distances (search.go:204): taken from the vertex source when it computed them behind the fetch, one extra
-    // launch only for the ones it did not (e.g. entries served from the local cache)
-    dists.assign(fresh.size(), 0.f);
+    int64_t degree(size_t) const { return m; }
+    const float *vector(size_t i) const { return (const float *)e[i]; }
+};
+
+// search.go:169-208 for the fetched vertices of this step, in three parts so that a lock-step driver can evaluate the
+// distances the vertex source did not provide for ALL lanes with one launch:
+//   collect -> (L2Dist of MissingVectors() to the query) -> apply
+template <class A>
+void SearchState::collect(const A &res, const std::vector<float> &srcDists) {
+    fresh.clear();
     ptrs.clear();
     missing.clear();
+    if (benchmarking) return;
+    // newly discovered vertices of this step, in batch order (a repeated id is "already known" by its second occurrence)
+    for (size_t i = 0; i < res.size(); i++) {
+        const int64_t id = res.id(i);
+        if (slotOf.count(id)) continue;
+        bool dup = false;
+        for (size_t t : fresh) dup = dup || res.id(t) == id;
+        if (dup) continue;
+        bool ok = false;
+        for (int64_t j = 0, d = res.degree(i); j < d; j++) if (res.neighbor(i, j) != 0) { ok = true; break; }   // all-zero list = failed fetch (search.go:192-199)
+        if (ok) fresh.push_back(i);
+    }
+    // their distances (search.go:204): taken from the vertex source when it computed them behind the fetch; the others
+    // (e.g. entries served from the local cache) are listed for one extra launch
+    dists.assign(fresh.size(), 0.f);
     for (size_t t = 0; t < fresh.size(); t++) {
         const float d = srcDists[fresh[t]];
-        if (std::isnan(d)) { missing.push_back(t); ptrs.push_back(queryResults[fresh[t]].Vector.data()); }
+        if (std::isnan(d)) { missing.push_back(t); ptrs.push_back(res.vector(fresh[t])); }
         else dists[t] = d;
     }
-    if (!missing.empty()) {
-        std::vector<float> md;
-        dist_many(ptrs, dim, queryVector, device, &md);
-        for (size_t j = 0; j < missing.size(); j++) dists[missing[j]] = md[j];
-    }
+}
+
+template <class A>
+void SearchState::apply(const A &res, const float *missingDists) {
+    const int64_t thisStep = step++;
+    if (benchmarking) return;
+    for (size_t j = 0; j < missing.size(); j++) dists[missing[j]] = missingDists[j];
     for (size_t t = 0; t < fresh.size(); t++) {
-        const Vertex &v = queryResults[fresh[t]];
-        addKnown(v, dists[t], thisStep);
-        toBeExplored.Push({dists[t], v.Id});
+        const size_t i = fresh[t];
+        const int64_t id = res.id(i);
+        slotOf[id] = (int32_t)knownId.size();
+        knownId.push_back(id);
+        knownDist.push_back(dists[t]);
+        knownStep.push_back(thisStep);
+        for (int64_t j = 0, d = res.degree(i); j < d; j++) nbrPool.push_back(res.neighbor(i, j));
+        toBeExplored.Push({dists[t], id});
     }
+}
+
+void SearchState::CollectFresh(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists) {
+    collect(VertexAccess{queryResults}, srcDists);
+}
+void SearchState::ApplyFresh(const std::vector<Vertex> &queryResults, const float *missingDists) {
+    apply(VertexAccess{queryResults}, missingDists);
+}
+void SearchState::CollectFreshRaw(const std::vector<int64_t> &ids, const std::vector<const uint64_t *> &entries, const std::vector<float> &srcDists) {
+    collect(RawAccess{ids, entries, dim, m}, srcDists);
+}
+void SearchState::ApplyFreshRaw(const std::vector<int64_t> &ids, const std::vector<const uint64_t *> &entries, const float *missingDists) {
+    apply(RawAccess{ids, entries, dim, m}, missingDists);
+}
+
+void SearchState::Consume(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists) {
+    CollectFresh(queryResults, srcDists);
+    std::vector<float> md;
+    if (!ptrs.empty()) dist_many(ptrs, dim, queryVector, device, &md);
+    ApplyFresh(queryResults, md.data());
 }
 
 // search.go:210-233
@@ -389,7 +456,7 @@ int GraphANNFrontend::SearchKNNBatch(const float *queryVectors, int64_t nq, int6
 
 // Lock-step search over several lanes.  Query i goes to lane i % L; every lane runs its queries in
 // order exactly as its own SearchKNNBatch would -- same client state, same results -- but each step fetches the
-// vertices of all lanes together: one GetVertexInfoWithDistGroup (one device call) per step instead of one per lane.
+// vertices of all lanes together: one FetchGroupRaw (one device call) per step instead of one per lane.
 int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float *queryVectors, int64_t nq, int64_t k, int64_t maxStep,
                       int64_t parallel, bool benchmarking, std::vector<int64_t> *ret, std::vector<int64_t> *stepRet) {
     const int64_t L = (int64_t)lanes.size();
@@ -406,12 +473,22 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
     }
     std::vector<std::vector<int64_t>> batch((size_t)L);
     std::vector<std::vector<Vertex>> results((size_t)L);
+    std::vector<std::vector<const uint64_t *>> rawEntries((size_t)L);
     std::vector<std::vector<float>> srcDists((size_t)L);
     std::vector<const float *> qptr((size_t)L);
     std::vector<char> more((size_t)L);
+    std::vector<size_t> missBase((size_t)L);
+    std::vector<float> missA, missB, missDist;
+    // PM_HOST_PROFILE=1: where a lock-step step spends its time (printed once per call)
+    static const bool prof = getenv("PM_HOST_PROFILE") != nullptr;
+    double tBegin = 0, tNext = 0, tFetch = 0, tCollect = 0, tMiss = 0, tApply = 0;
+    uint64_t nSteps = 0, nMissTotal = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     for (int64_t base = 0; base < nq; base += L) {
         const int64_t act = std::min(L, nq - base);
         std::string err;
+        auto t0 = now();
 #pragma omp parallel for schedule(static) if (act > 2)
         for (int64_t l = 0; l < act; l++) {
             try {
@@ -423,46 +500,84 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
             }
         }
         if (!err.empty()) throw std::runtime_error(err);
+        tBegin += since(t0);
         for (;;) {
+            t0 = now();
             bool any = false;
             for (int64_t l = 0; l < act; l++) {
                 more[(size_t)l] = lanes[(size_t)l]->wsState.NextBatch(&batch[(size_t)l]) ? 1 : 0;
                 any = any || more[(size_t)l];
             }
             if (!any) break;   // all lanes use the same maxStep, so they finish together
+            tNext += since(t0);
+            t0 = now();
+            nSteps++;
             if (groupable) {
                 std::vector<PIRGraphInfo *> gi;
                 std::vector<const std::vector<int64_t> *> gb;
                 std::vector<const float *> gq;
-                std::vector<std::vector<Vertex> *> go;
+                std::vector<std::vector<const uint64_t *> *> ge;
                 std::vector<std::vector<float> *> gd;
                 for (int64_t l = 0; l < act; l++) {
                     if (!more[(size_t)l]) continue;
                     gi.push_back(infos[(size_t)l]); gb.push_back(&batch[(size_t)l]); gq.push_back(benchmarking ? nullptr : qptr[(size_t)l]);
-                    go.push_back(&results[(size_t)l]); gd.push_back(&srcDists[(size_t)l]);
+                    ge.push_back(&rawEntries[(size_t)l]); gd.push_back(&srcDists[(size_t)l]);
                 }
-                if (PIRGraphInfo::GetVertexInfoWithDistGroup(gi, gb, gq, go, gd) != 0) return -1;
+                if (PIRGraphInfo::FetchGroupRaw(gi, gb, gq, ge, gd) != 0) return -1;
             } else {
                 for (int64_t l = 0; l < act; l++)
                     if (more[(size_t)l] && lanes[(size_t)l]->Graph->GetVertexInfoWithDist(batch[(size_t)l], benchmarking ? nullptr : qptr[(size_t)l],
                                                                                           &results[(size_t)l], &srcDists[(size_t)l]) != 0)
                         return -1;
             }
+            tFetch += since(t0);
+            t0 = now();
 #pragma omp parallel for schedule(static) if (act > 2)
-            for (int64_t l = 0; l < act; l++) {
-                if (!more[(size_t)l]) continue;
-                try {
-                    lanes[(size_t)l]->wsState.Consume(results[(size_t)l], srcDists[(size_t)l]);
-                } catch (const std::exception &e) {
-#pragma omp critical
-                    err = e.what();
+            for (int64_t l = 0; l < act; l++)
+                if (more[(size_t)l]) {
+                    if (groupable) lanes[(size_t)l]->wsState.CollectFreshRaw(batch[(size_t)l], rawEntries[(size_t)l], srcDists[(size_t)l]);
+                    else lanes[(size_t)l]->wsState.CollectFresh(results[(size_t)l], srcDists[(size_t)l]);
                 }
+            tCollect += since(t0);
+            t0 = now();
+            // distances the fetch did not provide (entries served from a lane's local cache): one launch for all lanes
+            size_t nMissing = 0;
+            for (int64_t l = 0; l < act; l++) {
+                missBase[(size_t)l] = nMissing;
+                if (more[(size_t)l]) nMissing += lanes[(size_t)l]->wsState.MissingVectors().size();
             }
-            if (!err.empty()) throw std::runtime_error(err);
+            missDist.assign(nMissing, 0.f);
+            if (nMissing) {
+                missA.resize(nMissing * (size_t)dim);
+                missB.resize(nMissing * (size_t)dim);
+                for (int64_t l = 0; l < act; l++) {
+                    if (!more[(size_t)l]) continue;
+                    const auto &mv = lanes[(size_t)l]->wsState.MissingVectors();
+                    for (size_t j = 0; j < mv.size(); j++) {
+                        memcpy(&missA[(missBase[(size_t)l] + j) * (size_t)dim], mv[j], (size_t)dim * 4);
+                        memcpy(&missB[(missBase[(size_t)l] + j) * (size_t)dim], qptr[(size_t)l], (size_t)dim * 4);
+                    }
+                }
+                check(pm_l2_pairs(missA.data(), missB.data(), nMissing, (uint64_t)dim, missDist.data(), lanes[0]->Graph->Device()), "pm_l2_pairs");
+            }
+            tMiss += since(t0);
+            nMissTotal += nMissing;
+            t0 = now();
+#pragma omp parallel for schedule(static) if (act > 2)
+            for (int64_t l = 0; l < act; l++)
+                if (more[(size_t)l]) {
+                    if (groupable) lanes[(size_t)l]->wsState.ApplyFreshRaw(batch[(size_t)l], rawEntries[(size_t)l], missDist.data() + missBase[(size_t)l]);
+                    else lanes[(size_t)l]->wsState.ApplyFresh(results[(size_t)l], missDist.data() + missBase[(size_t)l]);
+                }
+            tApply += since(t0);
         }
         for (int64_t l = 0; l < act; l++)
             lanes[(size_t)l]->wsState.Finish(&(*ret)[(size_t)((base + l) * k)], &(*stepRet)[(size_t)((base + l) * k)]);
     }
+    if (prof && nSteps)
+        fprintf(stderr, "[lockstep profile] %lld lanes, %llu steps, us per step: next %.1f | fetch %.1f | collect %.1f | missing-dist %.1f (%.1f per step) | "
+                        "apply %.1f ; begin %.1f us per round\n", (long long)L, (unsigned long long)nSteps, tNext / nSteps * 1e6, tFetch / nSteps * 1e6,
+                tCollect / nSteps * 1e6, tMiss / nSteps * 1e6, (double)nMissTotal / nSteps, tApply / nSteps * 1e6, tBegin / ((nq + L - 1) / L) * 1e6);
     return 0;
 }
 

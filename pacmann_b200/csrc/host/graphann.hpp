@@ -70,12 +70,12 @@ public:
     PIRGraphInfo *shareDBWith = nullptr;  // another client's graph info whose resident rawDB this one reuses (one per user)
     // Client groups for lock-step search: the group's first client sets groupLanes = L before Preprocess(); clients
     // 1..L-1 set laneOf = the first client and lane = their number (they also share its rawDB).  All lanes then live in
-    // one pm_client and GetVertexInfoWithDistGroup fetches for all of them with one device call.
+    // one pm_client and FetchGroupRaw fetches for all of them with one device call.
     uint32_t groupLanes = 1, lane = 0;
     PIRGraphInfo *laneOf = nullptr;
-    static int GetVertexInfoWithDistGroup(const std::vector<PIRGraphInfo *> &infos, const std::vector<const std::vector<int64_t> *> &ids,
-                                          const std::vector<const float *> &queries, const std::vector<std::vector<Vertex> *> &outs,
-                                          const std::vector<std::vector<float> *> &dists);
+    static int FetchGroupRaw(const std::vector<PIRGraphInfo *> &infos, const std::vector<const std::vector<int64_t> *> &ids,
+                             const std::vector<const float *> &queries, const std::vector<std::vector<const uint64_t *> *> &entries,
+                             const std::vector<std::vector<float> *> &dists);
     void unpackResponses(const std::vector<int64_t> &ids, std::vector<Vertex> *out);
     uint64_t DBEntryByteNum = 0, DBTotalSize = 0;
     std::vector<uint64_t> rawDB;
@@ -109,10 +109,19 @@ public:
     void Begin(GraphANNFrontend *front, const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking);
     bool NextBatch(std::vector<int64_t> *batchQ);
     void Consume(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists);
+    // Consume in parts: CollectFresh, then L2Dist(MissingVectors()[j], query) for every j, then ApplyFresh
+    void CollectFresh(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists);
+    const std::vector<const float *> &MissingVectors() const { return ptrs; }
+    void ApplyFresh(const std::vector<Vertex> &queryResults, const float *missingDists);
+    // the same over entries in the wire format of private-search.go:355-439, read in place
+    void CollectFreshRaw(const std::vector<int64_t> &ids, const std::vector<const uint64_t *> &entries, const std::vector<float> &srcDists);
+    void ApplyFreshRaw(const std::vector<int64_t> &ids, const std::vector<const uint64_t *> &entries, const float *missingDists);
     void Finish(int64_t *ret, int64_t *stepRet);   // [k] each, -1 padded
 
 private:
     void addKnown(const Vertex &v, float dist, int64_t step);
+    template <class A> void collect(const A &res, const std::vector<float> &srcDists);
+    template <class A> void apply(const A &res, const float *missingDists);
     GraphANNFrontend *f = nullptr;
     const float *queryVector = nullptr;
     int64_t k = 0, maxStep = 0, parallel = 0, n = 0, dim = 0, m = 0, step = 0;

@@ -207,7 +207,7 @@ void PianoPIRClient::Initialization() {
     backupShortTag.resize(S * M);
     backupParity.assign(S * M * E, 0);
     for (uint64_t i = 0; i < S * M; i++) backupShortTag[i] = shortTagCount++;
-    localCache.clear();
+    localCache.Init(E);
     pendingCached.clear();
 }
 
@@ -273,7 +273,7 @@ void PianoPIRClient::PrepareQuery(uint64_t idx, bool realQuery, PendingQuery *pq
         pq->err = QueryError::OutOfRange;
         return;
     }
-    bool cached = localCache.count(idx) != 0;
+    bool cached = localCache.has(idx);
     for (size_t i = 0; !cached && i < pendingCached.size(); i++) cached = pendingCached[i] == idx;
     if (cached) {  // pir.go:381-383
         pq->kind = PendingQuery::Cached;
@@ -326,7 +326,11 @@ void PianoPIRClient::FinishQuery(const PendingQuery &pq, const uint64_t *respons
     case PendingQuery::Failed:
         return;
     case PendingQuery::Cached:
-        *ret = localCache.at(pq.idx);
+        {
+            const uint64_t *e = localCache.find(pq.idx);
+            if (!e) throw std::runtime_error("local cache entry vanished");
+            ret->assign(e, e + E);
+        }
         return;
     case PendingQuery::Real:
         break;
@@ -337,7 +341,7 @@ void PianoPIRClient::FinishQuery(const PendingQuery &pq, const uint64_t *respons
     EntryXor(ret->data(), &primaryParity[pq.hitId * E], E);          // pir.go:453
     memcpy(&primaryParity[pq.hitId * E], &backupParity[slot * E], E * 8);  // pir.go:461
     EntryXor(&primaryParity[pq.hitId * E], ret->data(), E);          // pir.go:463
-    localCache[pq.idx] = *ret;                                       // pir.go:468
+    localCache.put(pq.idx, ret->data());                             // pir.go:468
     for (size_t i = 0; i < pendingCached.size(); i++)
         if (pendingCached[i] == pq.idx) { pendingCached.erase(pendingCached.begin() + (long)i); break; }
 }
@@ -422,6 +426,7 @@ SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
         fprintf(stderr, "[host profile] Query calls %llu: %.1f us per call, of which pm_client_query_batch %.1f us\n",
                 (unsigned long long)profQueryCalls, profQueryTotal / profQueryCalls * 1e6, profGpuCall / profQueryCalls * 1e6);
     if (rclient && ownsClient) pm_client_destroy(rclient);
+    if (groupBuf) pm_host_free(groupBuf);
     for (auto *p : subPIR) delete p;
     if (ownsDB) delete db;
 }
@@ -611,6 +616,24 @@ int SimpleBatchPianoPIR::Query(const std::vector<uint64_t> &idx, std::vector<std
     return 0;
 }
 
+void EntryCache::Reserve(uint64_t entries) {
+    while (slabs.size() * kPerSlab < entries) slabs.emplace_back(new uint64_t[kPerSlab * E]());   // value-initialised: pages touched now
+}
+const uint64_t *EntryCache::put(uint64_t idx, const uint64_t *entry) {
+    auto it = slot.find(idx);
+    uint64_t s;
+    if (it != slot.end()) {
+        s = it->second;
+    } else {
+        s = used++;
+        if (s / kPerSlab >= slabs.size()) slabs.emplace_back(new uint64_t[kPerSlab * E]);
+        slot.emplace(idx, s);
+    }
+    uint64_t *dst = slabs[s / kPerSlab].get() + (s % kPerSlab) * E;
+    memcpy(dst, entry, E * 8);
+    return dst;
+}
+
 // ---------------------------------------------------------------------------------------------
 // GPU-resident client
 // ---------------------------------------------------------------------------------------------
@@ -629,6 +652,7 @@ void SimpleBatchPianoPIR::EnableResidentClient(uint32_t lanes) {
     ownsClient = true;
     partBase = 0;
     clientLanes = lanes;
+    reserveCaches();
 }
 
 void SimpleBatchPianoPIR::AttachResidentClient(SimpleBatchPianoPIR *owner, uint32_t lane) {
@@ -643,6 +667,15 @@ void SimpleBatchPianoPIR::AttachResidentClient(SimpleBatchPianoPIR *owner, uint3
     ownsClient = false;
     partBase = lane * (uint32_t)config.PartitionNum;
     clientLanes = owner->clientLanes;
+    reserveCaches();
+}
+
+// a sub-PIR caches at most MaxQueryNum entries between two preprocessings (pir.go:468 runs once per successful query)
+void SimpleBatchPianoPIR::reserveCaches() {
+    for (auto *p : subPIR) {
+        p->client.localCache.Init(config.DBEntrySize);
+        p->client.localCache.Reserve(p->client.MaxQueryNum);
+    }
 }
 
 // Initialization + Preprocessing of the listed sub-PIRs on the device (keys and seeds derived as in the host path)
@@ -655,7 +688,7 @@ void SimpleBatchPianoPIR::PreprocessResident(const std::vector<uint32_t> &ids, b
         c.FinishedQueryNum = 0;
         c.masterKey = DeriveKey(c.keySeed, c.keyEpoch, c.keyParts, c.keyIndex);
         memcpy(&keys[a * 16], c.masterKey.b, 16);
-        c.localCache.clear();
+        c.localCache.Init(config.DBEntrySize);
         c.pendingCached.clear();
         seeds[a] = Mix64(c.replSeed, c.keyEpoch * c.keyParts + c.keyIndex);
     }
@@ -724,7 +757,7 @@ void SimpleBatchPianoPIR::pushRecord(uint64_t part, uint64_t globalIdx) {
         return;
     }
     const uint64_t local = globalIdx - part * config.PartitionSize;
-    bool cached = c.localCache.count(local) != 0;
+    bool cached = c.localCache.has(local);
     for (size_t k = 0; !cached && k < c.pendingCached.size(); k++) cached = c.pendingCached[k] == local;
     if (cached) {
         wsPend.push_back(PendRec{part, globalIdx, local, 2, -1});
@@ -745,15 +778,15 @@ void SimpleBatchPianoPIR::settle(size_t pbase, const uint64_t *res, const int32_
         PianoPIRClient &c = subPIR[pd.part]->client;
         if (pd.kind == 0) { serverQueries += 1; continue; }
         if (pd.kind == 2) {  // served from the local cache (pir.go:381-383); an earlier failure of the same index repeats as zeros
-            auto it = c.localCache.find(pd.local);
-            wsResponses[pd.global] = Resp{it != c.localCache.end() ? it->second.data() : wsZero.data(), kNaN};
+            const uint64_t *e = c.localCache.find(pd.local);
+            wsResponses[pd.global] = Resp{e ? e : wsZero.data(), kNaN};
             continue;
         }
         const uint64_t *r = res + (size_t)pd.qpos * E;
         if (status[pd.qpos] == 0) {
             serverQueries += 1;
             c.FinishedQueryNum += 1;
-            c.localCache[pd.local].assign(r, r + E);
+            c.localCache.put(pd.local, r);
         }
         for (size_t k = 0; k < c.pendingCached.size(); k++)
             if (c.pendingCached[k] == pd.local) { c.pendingCached.erase(c.pendingCached.begin() + (long)k); break; }
@@ -763,18 +796,16 @@ void SimpleBatchPianoPIR::settle(size_t pbase, const uint64_t *res, const int32_
 }
 
 // responses keyed by global index, zero rows for misses (batch-pir.go:218-237), then the batch accounting (:239-245)
-bool SimpleBatchPianoPIR::finishCall(const uint64_t *idx, size_t n, uint64_t *out, float *dists) {
+bool SimpleBatchPianoPIR::finishCall(const uint64_t *idx, size_t n, uint64_t *out, const uint64_t **out_ptrs, float *dists) {
     const uint64_t E = config.DBEntrySize;
     const float kNaN = std::nanf("");
     for (size_t i = 0; i < n; i++) {
         auto it = wsResponses.find(idx[i]);
-        if (it != wsResponses.end()) {
-            memcpy(out + i * E, it->second.entry, E * 8);
-            if (dists) dists[i] = it->second.dist;
-        } else {
-            memset(out + i * E, 0, E * 8);
-            if (dists) dists[i] = kNaN;
-        }
+        const bool have = it != wsResponses.end();
+        if (out_ptrs) out_ptrs[i] = have ? it->second.entry : wsZero.data();
+        else if (have) memcpy(out + i * E, it->second.entry, E * 8);
+        else memset(out + i * E, 0, E * 8);
+        if (dists) dists[i] = have ? it->second.dist : kNaN;
     }
     if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) return true;
     FinishedBatchNum += n / config.BatchSize;
@@ -849,7 +880,7 @@ int SimpleBatchPianoPIR::QueryFlat(const uint64_t *idx, size_t n, uint64_t *out,
         }
     }
     flush();
-    if (finishCall(idx, n, out, dists)) Preprocessing();
+    if (finishCall(idx, n, out, nullptr, dists)) Preprocessing();
     return 0;
 }
 
@@ -857,6 +888,15 @@ int SimpleBatchPianoPIR::QueryFlat(const uint64_t *idx, size_t n, uint64_t *out,
 // runs in parallel over the lanes; the lanes share nothing on the host.
 int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t dim) {
     if (calls.empty()) return 0;
+    static const bool prof = getenv("PM_HOST_PROFILE") != nullptr;
+    static thread_local double tBuild = 0, tDev = 0, tSettle = 0;
+    static thread_local uint64_t nCalls = 0;
+    auto tp0 = std::chrono::steady_clock::now();
+    auto lap = [&](double &acc) {
+        auto t = std::chrono::steady_clock::now();
+        acc += std::chrono::duration<double>(t - tp0).count();
+        tp0 = t;
+    };
     const size_t L = calls.size();
     pm_client *client = calls[0].pir->rclient;
     const uint64_t E = calls[0].pir->config.DBEntrySize;
@@ -867,8 +907,17 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
         grouped[l] = p->resident && p->rclient == client && client != nullptr && !p->mayFlushInside(calls[l].n) && p->config.DBEntrySize == E;
     }
     // lanes that cannot take part (not resident, another client, a sub-PIR about to exhaust its budget) run on their own
-    for (size_t l = 0; l < L; l++)
-        if (!grouped[l]) calls[l].rc = calls[l].pir->QueryFlat(calls[l].idx, calls[l].n, calls[l].out, calls[l].query_vec, dim, calls[l].dists);
+    for (size_t l = 0; l < L; l++) {
+        if (grouped[l]) continue;
+        GroupCall &gc = calls[l];
+        uint64_t *dst = gc.out;
+        if (!dst) {   // pointer form: the lane's own scratch holds the copies
+            gc.pir->wsSolo.resize(gc.n * E);
+            dst = gc.pir->wsSolo.data();
+            for (size_t i = 0; i < gc.n; i++) gc.out_ptrs[i] = dst + i * E;
+        }
+        gc.rc = gc.pir->QueryFlat(gc.idx, gc.n, dst, gc.query_vec, dim, gc.dists);
+    }
     std::vector<size_t> base(L + 1, 0);
 #pragma omp parallel for schedule(static) if (L > 2)
     for (size_t l = 0; l < L; l++) {
@@ -902,20 +951,30 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
         std::fill(gvec.begin() + (long)base[l], gvec.begin() + (long)base[l + 1], (uint32_t)l);
         if (calls[l].query_vec) { memcpy(&gqv[l * dim], calls[l].query_vec, dim * 4); anyVec = true; }
     }
-    host->wsOut.resize(std::max<size_t>(host->wsOut.size(), total * E));
+    lap(tBuild);
+    if (host->groupBufWords < total * E) {   // page-locked: the answers arrive by DMA, no host-side copy in the C-ABI
+        if (host->groupBuf) pm_host_free(host->groupBuf);
+        host->groupBuf = nullptr;
+        host->groupBufWords = 0;
+        void *pbuf = nullptr;
+        check(pm_host_alloc(&pbuf, (total * E + total * E / 2) * 8), "pm_host_alloc");
+        host->groupBuf = (uint64_t *)pbuf;
+        host->groupBufWords = total * E + total * E / 2;
+    }
     host->wsStatus.resize(std::max(host->wsStatus.size(), total));
     host->wsDist.resize(std::max(host->wsDist.size(), total));
     if (total) {
         auto tg = std::chrono::steady_clock::now();
         if (anyVec && dim)
-            check(pm_client_query_batch_l2m(client, gq.data(), total, host->wsOut.data(), host->wsStatus.data(), gqv.data(), L, gvec.data(), dim,
+            check(pm_client_query_batch_l2m(client, gq.data(), total, host->groupBuf, host->wsStatus.data(), gqv.data(), L, gvec.data(), dim,
                                             host->wsDist.data()), "pm_client_query_batch_l2m");
         else
-            check(pm_client_query_batch(client, gq.data(), total, host->wsOut.data(), host->wsStatus.data()), "pm_client_query_batch");
+            check(pm_client_query_batch(client, gq.data(), total, host->groupBuf, host->wsStatus.data()), "pm_client_query_batch");
         host->profGpuCall += std::chrono::duration<double>(std::chrono::steady_clock::now() - tg).count();
         host->serverLaunches += 1;
     }
-    const uint64_t *gout = host->wsOut.data();
+    lap(tDev);
+    const uint64_t *gout = host->groupBuf;
     const int32_t *gst = host->wsStatus.data();
     const float *gdist = host->wsDist.data();
     std::vector<char> due(L, 0);
@@ -924,8 +983,12 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
         if (!grouped[l] || calls[l].rc != 0) continue;
         SimpleBatchPianoPIR *p = calls[l].pir;
         p->settle(0, gout + base[l] * E, gst + base[l], (anyVec && dim && calls[l].query_vec) ? gdist + base[l] : nullptr);
-        due[l] = p->finishCall(calls[l].idx, calls[l].n, calls[l].out, calls[l].dists) ? 1 : 0;
+        due[l] = p->finishCall(calls[l].idx, calls[l].n, calls[l].out, calls[l].out ? nullptr : calls[l].out_ptrs, calls[l].dists) ? 1 : 0;
     }
+    lap(tSettle);
+    if (prof && (++nCalls % 200) == 0)
+        fprintf(stderr, "[group profile] %llu calls, us per call: build %.1f | device call %.1f | settle %.1f\n", (unsigned long long)nCalls,
+                tBuild / nCalls * 1e6, tDev / nCalls * 1e6, tSettle / nCalls * 1e6);
     for (size_t l = 0; l < L; l++)
         if (due[l]) calls[l].pir->Preprocessing();   // batch-pir.go:239-245; device calls of one pm_client are serialised anyway
     for (size_t l = 0; l < L; l++)

@@ -14,6 +14,7 @@
 // "next" in SURVEY.md 8f), caches and statistics.  This file only includes the public C header.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -79,6 +80,31 @@ struct PendingQuery {
     std::vector<uint32_t> offsets;  // what goes to the server (Dummy, Real)
 };
 
+// localCache (pir.go:127, :381-383, :468): idx -> entry.  Entries live in fixed-size slabs (stable addresses, reused after
+// clear()) instead of one heap vector per entry: a search step inserts ~100 entries per client and with many clients in
+// lock step the per-entry allocations (first-touch page faults under the process-wide mm lock) were the largest host
+// cost of a step.  Reserve() allocates and touches the slabs up front.
+class EntryCache {
+public:
+    void Init(uint64_t entryWords) { E = entryWords; clear(); }
+    void Reserve(uint64_t entries);
+    void clear() { slot.clear(); used = 0; }
+    bool has(uint64_t idx) const { return slot.find(idx) != slot.end(); }
+    const uint64_t *find(uint64_t idx) const {
+        auto it = slot.find(idx);
+        return it == slot.end() ? nullptr : at(it->second);
+    }
+    const uint64_t *put(uint64_t idx, const uint64_t *entry);
+    size_t size() const { return slot.size(); }
+
+private:
+    static constexpr uint64_t kPerSlab = 512;
+    const uint64_t *at(uint64_t s) const { return slabs[s / kPerSlab].get() + (s % kPerSlab) * E; }
+    uint64_t E = 0, used = 0;
+    std::vector<std::unique_ptr<uint64_t[]>> slabs;
+    std::unordered_map<uint64_t, uint64_t> slot;
+};
+
 class PianoPIRClient {  // pir.go:91-471
 public:
     explicit PianoPIRClient(const PianoPIRConfig *config);
@@ -103,7 +129,7 @@ public:
     std::vector<uint64_t> primaryShortTag, primaryParity, primaryProgramPoint;
     // [SetSize][maxQueryPerChunk(*E)] flattened (the Go code uses slices of slices, pir.go:113-118)
     std::vector<uint64_t> replacementIdx, replacementVal, backupShortTag, backupParity;
-    std::unordered_map<uint64_t, std::vector<uint64_t>> localCache;
+    EntryCache localCache;
     // deterministic randomness (injected; the reference uses time-seeded rngs)
     uint64_t keySeed = 1, keyEpoch = 0, keyIndex = 0, keyParts = 1, replSeed = 0, dummySeed = 0xD00D, dummyCtr = 0;
     uint64_t replEpoch = 0;
@@ -172,6 +198,9 @@ public:
         const uint64_t *idx; size_t n; uint64_t *out;   // as QueryFlat
         const float *query_vec; float *dists;           // query_vec may be null (then no distances for this lane)
         int rc;
+        // out == nullptr: no copy of the answers; out_ptrs[i] points at the entry of idx[i] instead (into the group's
+        // result buffer, the lane's local cache or a zero row), valid until the lane's next Query call
+        const uint64_t **out_ptrs = nullptr;
     };
     // QueryFlat of several lanes of one pm_client at once.  Every lane ends in exactly the state its own QueryFlat
     // would have left (a lane that may exhaust a sub-PIR's budget inside this call is simply run on its own).
@@ -189,7 +218,7 @@ private:
     std::vector<std::vector<uint64_t>> wsLists;   // per-call scratch, kept to avoid reallocation
     std::vector<PendRec> wsPend;
     std::vector<pm_client_query> wsQueries;
-    std::vector<uint64_t> wsOut, wsZero;
+    std::vector<uint64_t> wsOut, wsZero, wsSolo;
     std::vector<int32_t> wsStatus;
     std::vector<float> wsDist;
     struct Resp { const uint64_t *entry; float dist; };
@@ -199,8 +228,12 @@ private:
     void beginCall(const uint64_t *idx, size_t n, bool *bad);
     void pushRecord(uint64_t part, uint64_t globalIdx);
     void settle(size_t pbase, const uint64_t *res, const int32_t *status, const float *dist);
-    bool finishCall(const uint64_t *idx, size_t n, uint64_t *out, float *dists);   // true: the batch budget is used up, Preprocessing() is due
+    // true: the batch budget is used up, Preprocessing() is due
+    bool finishCall(const uint64_t *idx, size_t n, uint64_t *out, const uint64_t **out_ptrs, float *dists);
+    uint64_t *groupBuf = nullptr;   // page-locked result buffer of QueryFlatGroup calls hosted by this object (pm_host_alloc)
+    size_t groupBufWords = 0;
     bool mayFlushInside(size_t n) const;
+    void reserveCaches();
     void PreprocessResident(const std::vector<uint32_t> &ids, bool skipPrep);
     int QueryResident(const std::vector<uint64_t> &idx, std::vector<std::vector<uint64_t>> *ret);
     void Flush(std::vector<PendingQuery> &pend, std::vector<uint64_t> &pend_part, std::vector<uint64_t> &pend_global,

@@ -582,7 +582,14 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     ClientMeta *d_meta = (ClientMeta *)(d_res + q * E);  // results and their status records leave in ONE copy
     // pinned staging (grow-only): the D2H lands at PCIe speed instead of going through the pageable path
     float *d_qv = (float *)((((uintptr_t)(d_set + q)) + 15) & ~(uintptr_t)15), *d_dist = (float *)(d_meta + q);
-    const size_t b_back = q * E * 8 + b_meta + b_dist;
+    // a page-locked `out` (pm_host_alloc) receives the answers straight from the GPU; only meta + distances are staged
+    bool direct = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, out) == cudaSuccess) direct = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+    }
+    const size_t b_back = (direct ? 0 : q * E * 8) + b_meta + b_dist;
     if (c->stage_bytes < b_back) {
         if (c->stage) cudaFreeHost(c->stage);
         c->stage = nullptr;
@@ -619,12 +626,18 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
         if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, vec_id ? dim : 0, d_vid, q, (uint32_t)dim, d_dist, c->stream))) return rc;
     }
     mark(4);
-    PM_CUDA(cudaMemcpyAsync(c->stage, d_res, b_back, cudaMemcpyDeviceToHost, c->stream));
+    if (direct) {
+        PM_CUDA(cudaMemcpyAsync(out, d_res, q * E * 8, cudaMemcpyDeviceToHost, c->stream));
+        PM_CUDA(cudaMemcpyAsync(c->stage, d_meta, b_back, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        PM_CUDA(cudaMemcpyAsync(c->stage, d_res, b_back, cudaMemcpyDeviceToHost, c->stream));
+    }
     mark(5);
     PM_CUDA(cudaStreamSynchronize(c->stream));
-    memcpy(out, c->stage, q * E * 8);
-    const ClientMeta *meta = (const ClientMeta *)((const char *)c->stage + q * E * 8);
-    if (dist_out) memcpy(dist_out, (const char *)c->stage + q * E * 8 + b_meta, q * 4);
+    const size_t res_in_stage = direct ? 0 : q * E * 8;
+    if (!direct) memcpy(out, c->stage, q * E * 8);
+    const ClientMeta *meta = (const ClientMeta *)((const char *)c->stage + res_in_stage);
+    if (dist_out) memcpy(dist_out, (const char *)c->stage + res_in_stage + b_meta, q * 4);
     if (prof) {
         for (int i = 0; i < 5; i++) {
             float ms = 0;
@@ -634,6 +647,19 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
         c->prof_calls++;
     }
     for (uint64_t t = 0; t < q; t++) status[t] = meta[t].status < 0 ? 0 : meta[t].status;
+    return PM_OK;
+}
+
+PM_EXPORT int pm_host_alloc(void **out, uint64_t bytes) {
+    if (!out) return pm::set_error(PM_ERR_ARG, "pm_host_alloc: null pointer");
+    *out = nullptr;
+    if (bytes == 0) return PM_OK;
+    cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return pm::set_error(PM_ERR_NOMEM, "pm_host_alloc: cudaHostAlloc(%llu) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e)); }
+    return PM_OK;
+}
+PM_EXPORT int pm_host_free(void *p) {
+    if (p) PM_CUDA(cudaFreeHost(p));
     return PM_OK;
 }
 

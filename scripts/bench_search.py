@@ -33,7 +33,9 @@ def main():
     ap.add_argument("--step", type=int, default=20)
     ap.add_argument("--parallel", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--clients", type=int, default=1, help="concurrent clients (one per user) sharing the resident DB")
+    ap.add_argument("--clients", type=int, default=1, help="concurrent clients (one per user) sharing the resident DB, one host thread each")
+    ap.add_argument("--lanes", type=int, default=1, help="clients of one lock-step group (graphann.SearchKNNLockstep)")
+    ap.add_argument("--lane-q", type=int, default=4, help="queries per lane in the lock-step measurement")
     a = ap.parse_args()
     n = a.n or (1000000 if a.shape == "sift" else 3201821)
     dim = 128 if a.shape == "sift" else 192
@@ -45,7 +47,7 @@ def main():
     from pacmann_b200 import cabi, graphann
     from pacmann_b200.keys import mix64
     seed = 7
-    f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed)
+    f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed, group_lanes=max(1, a.lanes))
     t0 = time.perf_counter()
     f.Preprocess()
     prep_s = time.perf_counter() - t0
@@ -80,6 +82,22 @@ def main():
             t.join()
         mdt = time.perf_counter() - t0
         res.update(clients=a.clients, multi_client_qps=a.clients * per / mdt, multi_client_s_per_query_per_client=mdt / per)
+    if a.lanes > 1:
+        t0 = time.perf_counter()
+        group = [f]
+        for i in range(1, a.lanes):
+            g = graphann.GraphANNFrontend(vec, graph, seed=seed + 1000 + i, lane_of=f, lane=i)
+            g.Preprocess()
+            group.append(g)
+        res["lockstep_group_setup_s"] = time.perf_counter() - t0
+        lq = vec[np.random.default_rng(70).integers(0, n, a.lanes * a.lane_q)] + np.float32(0.5)
+        graphann.SearchKNNLockstep(group, lq[:a.lanes], k, a.step, a.parallel)      # warm-up: one query per lane
+        l0 = cabi.launch_count()
+        t0 = time.perf_counter()
+        graphann.SearchKNNLockstep(group, lq, k, a.step, a.parallel)
+        ldt = time.perf_counter() - t0
+        res.update(lanes=a.lanes, lockstep_queries=len(lq), lockstep_qps=len(lq) / ldt, lockstep_ms_per_step=ldt / (a.lane_q * a.step) * 1e3,
+                   lockstep_gpu_launches=cabi.launch_count() - l0)
     if not a.no_cpu:
         from oracle import oracle as o
         raw = o.pack_db(vec, graph)
