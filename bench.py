@@ -192,7 +192,9 @@ def main():
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="N > 1: how parities reach rank 0")
     ap.add_argument("--no-search", action="store_true", help="skip the private-ANN queries/s part")
     ap.add_argument("--search-queries", type=int, default=96, help="private ANN queries per GPU")
-    ap.add_argument("--search-clients", type=int, default=8, help="concurrent clients per GPU in the serving measurement")
+    ap.add_argument("--search-clients", type=int, default=0, help="serving measurement, thread form: concurrent clients per GPU, one host thread each (0 = skip)")
+    ap.add_argument("--search-lanes", type=int, default=16, help="serving measurement, lock-step form: clients per lock-step group (graphann.SearchKNNLockstep); 0 = skip")
+    ap.add_argument("--search-groups", type=int, default=4, help="lock-step groups per GPU, one host thread each")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -465,7 +467,8 @@ def private_search(args, rank, world, local_rank, dist, dev):
     qall = vec[np.random.default_rng(SEED + 1).integers(0, n, nq * world)] + np.float32(0.25)
     queries = qall[rank * nq:(rank + 1) * nq]
     seed = SEED + 2
-    f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed, device=local_rank)
+    lanes, ngroups = max(0, args.search_lanes), max(1, args.search_groups)
+    f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed, device=local_rank, group_lanes=max(1, lanes))
     t0 = time.perf_counter()
     f.Preprocess()
     setup_s = time.perf_counter() - t0
@@ -524,6 +527,48 @@ def private_search(args, rank, world, local_rank, dist, dev):
         out["multi_client"] = {"clients_per_gpu": K, "queries": K * per * world, "queries_per_s": K * per * world / float(tm[0]),
                                "s_per_query_per_client": mdt / per}
         del fs
+    # serving form, lock step: groups of `lanes` independent clients whose hint tables live in one
+    # pm_client; every search step of a group is ONE device call for all its lanes.  Each client still answers its own
+    # queries sequentially and returns exactly what it would return alone (tests/test_graphann_gpu.py).  Several groups
+    # run from host threads so that the host work of one overlaps the GPU work of another.
+    if lanes > 1:
+        import threading
+        t0 = time.perf_counter()
+        groups = []
+        for gi in range(ngroups):
+            lead = f if gi == 0 else graphann.GraphANNFrontend(vec, graph, seed=seed + 5000 * gi, share_db_with=f, group_lanes=lanes)
+            if gi:
+                lead.Preprocess()
+            grp = [lead]
+            for i in range(1, lanes):
+                g = graphann.GraphANNFrontend(vec, graph, seed=seed + 5000 * gi + 1000 + i, lane_of=lead, lane=i)
+                g.Preprocess()
+                grp.append(g)
+            groups.append(grp)
+        gsetup = time.perf_counter() - t0
+        per = max(4, nq // 16)
+        lqs = [vec[np.random.default_rng(SEED + 50 + rank * ngroups + gi).integers(0, n, lanes * per)] + np.float32(0.25) for gi in range(ngroups)]
+        for gi in range(ngroups):
+            graphann.SearchKNNLockstep(groups[gi], lqs[gi][:lanes], k, step, par)
+        th = [threading.Thread(target=graphann.SearchKNNLockstep, args=(groups[gi], lqs[gi], k, step, par)) for gi in range(ngroups)]
+        if dist is not None:
+            dist.barrier()
+        l1 = cabi.launch_count()
+        t0 = time.perf_counter()
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        ldt = time.perf_counter() - t0
+        tl = torch.tensor([ldt], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        nlq = ngroups * lanes * per
+        out["lockstep"] = {"clients_per_gpu": ngroups * lanes, "groups_per_gpu": ngroups, "lanes_per_group": lanes, "queries": nlq * world,
+                           "queries_per_s": nlq * world / float(tl[0]), "ms_per_step_per_group": ldt / (per * step) * 1e3,
+                           "gpu_launches": int(cabi.launch_count() - l1), "group_setup_s": gsetup,
+                           "note": "every client keeps its own keys, hint tables, cache and search state; results identical to each client searching alone"}
+        del groups
     if rank == 0 and not args.no_cpu_baseline:
         from oracle import oracle as o
         raw = o.pack_db(vec, graph)

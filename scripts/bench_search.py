@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--clients", type=int, default=1, help="concurrent clients (one per user) sharing the resident DB, one host thread each")
     ap.add_argument("--lanes", type=int, default=1, help="clients of one lock-step group (graphann.SearchKNNLockstep)")
     ap.add_argument("--lane-q", type=int, default=4, help="queries per lane in the lock-step measurement")
+    ap.add_argument("--groups", type=int, default=1, help="lock-step groups, one host thread each (host work of one overlaps the GPU work of another)")
     a = ap.parse_args()
     n = a.n or (1000000 if a.shape == "sift" else 3201821)
     dim = 128 if a.shape == "sift" else 192
@@ -83,20 +84,33 @@ def main():
         mdt = time.perf_counter() - t0
         res.update(clients=a.clients, multi_client_qps=a.clients * per / mdt, multi_client_s_per_query_per_client=mdt / per)
     if a.lanes > 1:
+        import threading
         t0 = time.perf_counter()
-        group = [f]
-        for i in range(1, a.lanes):
-            g = graphann.GraphANNFrontend(vec, graph, seed=seed + 1000 + i, lane_of=f, lane=i)
-            g.Preprocess()
-            group.append(g)
+        groups = []
+        for gi in range(a.groups):
+            lead = f if gi == 0 else graphann.GraphANNFrontend(vec, graph, seed=seed + 5000 * gi, share_db_with=f, group_lanes=a.lanes)
+            if gi:
+                lead.Preprocess()
+            group = [lead]
+            for i in range(1, a.lanes):
+                g = graphann.GraphANNFrontend(vec, graph, seed=seed + 5000 * gi + 1000 + i, lane_of=lead, lane=i)
+                g.Preprocess()
+                group.append(g)
+            groups.append(group)
         res["lockstep_group_setup_s"] = time.perf_counter() - t0
-        lq = vec[np.random.default_rng(70).integers(0, n, a.lanes * a.lane_q)] + np.float32(0.5)
-        graphann.SearchKNNLockstep(group, lq[:a.lanes], k, a.step, a.parallel)      # warm-up: one query per lane
+        lqs = [vec[np.random.default_rng(70 + gi).integers(0, n, a.lanes * a.lane_q)] + np.float32(0.5) for gi in range(a.groups)]
+        for gi in range(a.groups):
+            graphann.SearchKNNLockstep(groups[gi], lqs[gi][:a.lanes], k, a.step, a.parallel)      # warm-up: one query per lane
         l0 = cabi.launch_count()
+        th = [threading.Thread(target=graphann.SearchKNNLockstep, args=(groups[gi], lqs[gi], k, a.step, a.parallel)) for gi in range(a.groups)]
         t0 = time.perf_counter()
-        graphann.SearchKNNLockstep(group, lq, k, a.step, a.parallel)
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
         ldt = time.perf_counter() - t0
-        res.update(lanes=a.lanes, lockstep_queries=len(lq), lockstep_qps=len(lq) / ldt, lockstep_ms_per_step=ldt / (a.lane_q * a.step) * 1e3,
+        nlq = a.groups * a.lanes * a.lane_q
+        res.update(lanes=a.lanes, groups=a.groups, lockstep_queries=nlq, lockstep_qps=nlq / ldt, lockstep_ms_per_step=ldt / (a.lane_q * a.step) * 1e3,
                    lockstep_gpu_launches=cabi.launch_count() - l0)
     if not a.no_cpu:
         from oracle import oracle as o
