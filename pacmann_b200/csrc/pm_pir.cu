@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(256) prf_batch_kernel(const __grid_constant__ 
 // lines for G = 8).  Parities are written once.  CTAs walk tiles in a static round-robin so that
 // all resident CTAs sweep the same DB slice chunk 0..S-1 at the same pace: each chunk is pulled
 // from HBM once and re-hit in L2 by the other ~H'/ChunkSize hints that select rows of it.
-constexpr int HG_THREADS = 512;
+constexpr int HG_THREADS = 512;        // default CTA width (16 warps); the width is chosen per launch: 12..16 warps
+constexpr int HG_MAX_THREADS = 512;    // wider CTAs would cap the kernel below the 128 registers it needs (spills)
 constexpr int HG_MAX_JOBS = 16;
 
 struct HintJobDev {
@@ -117,6 +118,7 @@ struct HintParams {
     HintJobDev jobs[HG_MAX_JOBS];
     const void *db;
     uint32_t n_jobs, n_tiles;
+    uint32_t threads;   // CTA width of this launch
     uint32_t ev, evx;  // vectors per row (incl. un-xored tail), vectors that are xored
     unsigned int *sync;  // round barrier counter (cooperative launch) or nullptr
 };
@@ -189,7 +191,7 @@ __device__ __forceinline__ void hg_phase(const AesTab<NTAB> &T, const RK &R, con
 }
 
 template <typename VT, int G, int NV, int NTAB, int NB, int U, bool FULL>
-__global__ void __launch_bounds__(HG_THREADS, 1) hintgen_kernel(const __grid_constant__ HintParams P) {
+__global__ void __launch_bounds__(HG_MAX_THREADS, 1) hintgen_kernel(const __grid_constant__ HintParams P) {
     extern __shared__ uint32_t smem[];
     aes_tab_fill<NTAB>(smem, c_te0);
     __syncthreads();
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(HG_THREADS, 1) hintgen_kernel(const __grid_con
     const AesTab<NTAB> T{smem + lane};
     constexpr int GPW = 32 / G, NPH = G / U;
     const int gl = lane & (G - 1), gbase = lane & ~(G - 1), gw = lane / G;
-    const uint32_t hints_per_tile = (HG_THREADS / 32) * GPW;
+    const uint32_t hints_per_tile = (blockDim.x / 32) * GPW;
     const uint32_t ev = P.ev, evx = P.evx;
 
     // Rounds: in round r the CTAs process tiles r*grid .. r*grid+grid-1, i.e. one contiguous range of hints of
@@ -367,11 +369,11 @@ static int launch_hg(KERN kern, int smem, const HintParams &P, int sm, cudaStrea
         // round barrier needs every CTA resident: cooperative launch (one 512-thread CTA per SM always fits)
         PM_CUDA(cudaMemsetAsync(P.sync, 0, sizeof(unsigned int), st));
         void *args[] = {(void *)&P};
-        PM_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(HG_THREADS), args, (size_t)smem, st));
+        PM_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(P.threads), args, (size_t)smem, st));
     } else {
         HintParams Q = P;
         Q.sync = nullptr;
-        kern<<<grid, HG_THREADS, smem, st>>>(Q);
+        kern<<<grid, Q.threads, smem, st>>>(Q);
     }
     PM_CHECK_LAUNCH();
     count_launch();
@@ -411,7 +413,7 @@ static int launch_hintgen_g(uint32_t evx, const HintParams &P, int sm, cudaStrea
     const uint32_t x = evx ? evx : 1;
     int G = x >= 8 ? 8 : x >= 4 ? 4 : x >= 2 ? 2 : 1;
     int nv = (int)((x + G - 1) / G);
-    *hints_per_tile = (HG_THREADS / 32) * (32 / G);
+    *hints_per_tile = (32 / G);   // hints per warp; the caller multiplies by the warps of the CTA width it picks
     if (query_only) return nv <= 8 ? PM_OK : set_error(PM_ERR_UNSUPPORTED, "hintgen: entry_u64 too large");
     switch (G) {
     case 8: return launch_hintgen_nv<VT, 8, NB>(nv, P, sm, st);
@@ -452,9 +454,33 @@ int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStr
         P.sync = use_sync ? sync_counter(db) : nullptr;
         P.ev = ev;
         P.evx = evx;
-        uint32_t hpt = 0;
-        int rc = wide ? launch_hintgen_g<uint4, 2>(evx, P, 0, st, &hpt, true) : launch_hintgen_g<uint2, 2>(evx, P, 0, st, &hpt, true);
+        uint32_t hpw = 0;   // hints per warp
+        int rc = wide ? launch_hintgen_g<uint4, 2>(evx, P, 0, st, &hpw, true) : launch_hintgen_g<uint2, 2>(evx, P, 0, st, &hpw, true);
         if (rc != PM_OK) return rc;
+        // CTA width.  Every lane group keeps one hint for a whole sweep, so a tile costs one sweep whatever it holds and
+        // the CTAs run ceil(tiles / SMs) rounds.  A round gets cheaper with fewer warps, but less than proportionally
+        // (measured on B200, MS-MARCO rows: 16 -> 14 warps = -5 % per round, i.e. round time ~ warps + 24), so a
+        // narrower CTA only pays when it saves nothing in rounds: 1/8 of the hints (8 GPUs) is 5.2 -> 6 rounds at 16
+        // warps and 5.95 -> 6 at 14 (-4.3 %); at 1, 2 and 4 GPUs 16 warps stay best.  PM_HG_WARPS forces a width.
+        static const int force_warps = env_int("PM_HG_WARPS", 0);
+        uint32_t warps = HG_THREADS / 32;
+        {
+            uint64_t best = ~0ull;
+            for (uint32_t w = 12; w <= (uint32_t)HG_MAX_THREADS / 32; w++) {
+                uint64_t t = 0, nj2 = 0;
+                for (uint64_t b = a; b < n_jobs && nj2 < HG_MAX_JOBS; b++) {
+                    if (jobs[b].n_hints == 0 || jobs[b].n_rows == 0) continue;
+                    nj2++;
+                    t += (jobs[b].n_hints + (uint64_t)w * hpw - 1) / ((uint64_t)w * hpw);
+                }
+                const uint64_t g = std::max<uint64_t>(1, std::min<uint64_t>(t, (uint64_t)db->sm_count));
+                const uint64_t cost = ((t + g - 1) / g) * (w + 24);
+                if (cost <= best) { best = cost; warps = w; }
+            }
+            if (force_warps >= 1 && force_warps <= HG_MAX_THREADS / 32) warps = (uint32_t)force_warps;
+        }
+        const uint32_t hpt = hpw * warps;
+        P.threads = warps * 32;
         uint32_t tiles = 0;
         uint32_t nj = 0;
         for (; a < n_jobs && nj < HG_MAX_JOBS; a++) {
@@ -478,10 +504,11 @@ int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStr
         if (nj == 0) break;
         P.n_jobs = nj;
         P.n_tiles = tiles;
-        if (wide) rc = need4 ? launch_hintgen_g<uint4, 4>(evx, P, db->sm_count, st, &hpt, false)
-                             : launch_hintgen_g<uint4, 2>(evx, P, db->sm_count, st, &hpt, false);
+        uint32_t unused = 0;
+        if (wide) rc = need4 ? launch_hintgen_g<uint4, 4>(evx, P, db->sm_count, st, &unused, false)
+                             : launch_hintgen_g<uint4, 2>(evx, P, db->sm_count, st, &unused, false);
         else if (need4) rc = set_error(PM_ERR_UNSUPPORTED, "hintgen: odd entry_u64 with chunk_size > 65536 is not built");
-        else rc = launch_hintgen_g<uint2, 2>(evx, P, db->sm_count, st, &hpt, false);
+        else rc = launch_hintgen_g<uint2, 2>(evx, P, db->sm_count, st, &unused, false);
         if (rc != PM_OK) return rc;
     }
     return PM_OK;

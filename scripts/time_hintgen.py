@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--fail", type=int, default=8)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--shard", default="0/1", help="r/N: time rank r's share of the hints of an N-GPU run")
     a = ap.parse_args()
     torch.cuda.init()
     E = a.entry_u64
@@ -50,9 +51,11 @@ def main():
         H = p + s * mq
         out = torch.empty(H * E, dtype=torch.int64, device="cuda")
         outs.append(out)
-        jobs.append(cabi.make_job(i * ps, n_i, c, s, rk.astype(np.uint32), 0, H, p, mq, parity_out=out.data_ptr()))
-        total_h += H
-        prf += s * H
+        r_, n_ = (int(x) for x in a.shard.split("/"))
+        hb, he = H * r_ // n_, H * (r_ + 1) // n_
+        jobs.append(cabi.make_job(i * ps, n_i, c, s, rk.astype(np.uint32), hb, he - hb, p, mq, parity_out=out.data_ptr()))
+        total_h += he - hb
+        prf += s * (he - hb)
     print(f"parts={parts} chunk={c} set={s} primary={p} mqpc={mq} hints/part={H} prf={prf} xor_bytes={prf*E*8/1e9:.3f} GB db={nbytes/1e9:.3f} GB")
     stream = torch.cuda.Stream()
     st = stream.cuda_stream
