@@ -548,18 +548,28 @@ def private_search(args, rank, world, local_rank, dist, dev):
         gsetup = time.perf_counter() - t0
         per = max(4, nq // 16)
         lqs = [vec[np.random.default_rng(SEED + 50 + rank * ngroups + gi).integers(0, n, lanes * per)] + np.float32(0.25) for gi in range(ngroups)]
-        for gi in range(ngroups):
+        # one host thread per group; each warms up in its own thread (one query per lane: OpenMP team, allocator arena)
+        # and then waits for the common start
+        start_b, done_b = threading.Barrier(ngroups + 1), threading.Barrier(ngroups + 1)
+
+        def drive(gi):
             graphann.SearchKNNLockstep(groups[gi], lqs[gi][:lanes], k, step, par)
-        th = [threading.Thread(target=graphann.SearchKNNLockstep, args=(groups[gi], lqs[gi], k, step, par)) for gi in range(ngroups)]
-        if dist is not None:
-            dist.barrier()
-        l1 = cabi.launch_count()
-        t0 = time.perf_counter()
+            start_b.wait()
+            graphann.SearchKNNLockstep(groups[gi], lqs[gi], k, step, par)
+            done_b.wait()
+
+        th = [threading.Thread(target=drive, args=(gi,)) for gi in range(ngroups)]
         for t_ in th:
             t_.start()
+        if dist is not None:
+            dist.barrier()
+        start_b.wait()
+        l1 = cabi.launch_count()
+        t0 = time.perf_counter()
+        done_b.wait()
+        ldt = time.perf_counter() - t0
         for t_ in th:
             t_.join()
-        ldt = time.perf_counter() - t0
         tl = torch.tensor([ldt], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(tl, op=dist.ReduceOp.MAX)

@@ -20,32 +20,36 @@ __device__ __forceinline__ uint32_t rotl8(uint32_t v) { return __byte_perm(v, v,
 __device__ __forceinline__ uint32_t rotl16(uint32_t v) { return __byte_perm(v, v, 0x1032); }
 __device__ __forceinline__ uint32_t rotl24(uint32_t v) { return __byte_perm(v, v, 0x0321); }
 
-// Lane-private view of the replicated tables.  `base` points at shared word [0*32 + lane].
+// Lane-private view of the replicated tables.  `base` points at shared word [0*REP + lane % REP].
+// NTAB = 1: Te0 replicated 32x (conflict-free);  NTAB = 4: Te0..Te3 replicated 32x;  NTAB = 8: "compact", Te0 replicated
+// 4x only (4 KB instead of 32 KB: for kernels that evaluate few PRFs and need the shared memory for occupancy).
 template <int NTAB>
 struct AesTab {
+    static constexpr int REP = NTAB == 8 ? 4 : 32;
     const uint32_t *base;
-    __device__ __forceinline__ uint32_t t0(uint32_t b) const { return base[b * 32]; }
+    __device__ __forceinline__ uint32_t t0(uint32_t b) const { return base[b * REP]; }
     __device__ __forceinline__ uint32_t t1(uint32_t b) const {
-        return NTAB == 4 ? base[8192 + b * 32] : rotl8(base[b * 32]);
+        return NTAB == 4 ? base[8192 + b * 32] : rotl8(base[b * REP]);
     }
     __device__ __forceinline__ uint32_t t2(uint32_t b) const {
-        return NTAB == 4 ? base[2 * 8192 + b * 32] : rotl16(base[b * 32]);
+        return NTAB == 4 ? base[2 * 8192 + b * 32] : rotl16(base[b * REP]);
     }
     __device__ __forceinline__ uint32_t t3(uint32_t b) const {
-        return NTAB == 4 ? base[3 * 8192 + b * 32] : rotl24(base[b * 32]);
+        return NTAB == 4 ? base[3 * 8192 + b * 32] : rotl24(base[b * REP]);
     }
-    __device__ __forceinline__ uint32_t sbox(uint32_t b) const { return byte_of(base[b * 32], 1); }
+    __device__ __forceinline__ uint32_t sbox(uint32_t b) const { return byte_of(base[b * REP], 1); }
 };
 
 // shared words needed by AesTab<NTAB>
 template <int NTAB>
-__host__ __device__ constexpr int aes_tab_words() { return NTAB * 256 * 32; }
+__host__ __device__ constexpr int aes_tab_words() { return NTAB == 8 ? 256 * 4 : NTAB * 256 * 32; }
 
 // Fill the replicated tables from the 256-entry Te0 in constant memory.  Whole CTA participates.
 template <int NTAB>
 __device__ __forceinline__ void aes_tab_fill(uint32_t *smem, const uint32_t *te0_const) {
-    for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
-        uint32_t v = te0_const[i >> 5];  // warp-uniform index
+    constexpr int REP = AesTab<NTAB>::REP;
+    for (int i = threadIdx.x; i < 256 * REP; i += blockDim.x) {
+        uint32_t v = te0_const[i / REP];  // warp-uniform index when REP = 32
         smem[i] = v;
         if (NTAB == 4) {
             smem[8192 + i] = rotl8(v);

@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
                                                                     ClientMeta *meta, uint64_t *a_row0, uint64_t *a_nrows,
                                                                     uint32_t *a_chunk, uint32_t *a_set) {
     extern __shared__ uint32_t smem[];
-    uint32_t *s_tab = smem;                           // replicated Te0
-    uint32_t *s_rk = smem + aes_tab_words<1>();       // 44 round-key words
+    uint32_t *s_tab = smem;                           // compact Te0 (4 KB): few PRFs here, the shared memory buys occupancy
+    uint32_t *s_rk = smem + aes_tab_words<8>();       // 44 round-key words
     uint32_t *s_offs = s_rk + 64;                     // [stride]
     uint32_t *s_list = s_offs + stride;               // [CL_MAX_LIST]
     uint32_t *s_pp = s_list + CL_MAX_LIST;            // [P] program points (only when the offset index is in use)
@@ -145,13 +145,13 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
     const uint32_t n_mine = client_build_list(reinterpret_cast<const uint32_t *>(queries), q, part, s_list);
     if (n_mine == 0) return;
-    aes_tab_fill<1>(s_tab, c_te0);
+    aes_tab_fill<8>(s_tab, c_te0);
     if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
     const bool indexed = D.poff != nullptr;
     if (indexed)
         for (uint64_t i = threadIdx.x; i < P; i += CL_THREADS) s_pp[i] = (uint32_t)D.pp[i];   // values < 2^31 or 0x7fffffff
     __syncthreads();
-    const AesTab<1> T{s_tab + (threadIdx.x & 31)};
+    const AesTab<8> T{s_tab + (threadIdx.x & 3)};
     const RkOfPtr R{s_rk};
 
     for (uint32_t k = 0; k < n_mine; k++) {
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
                 const uint64_t i = base + threadIdx.x;
                 if (i < P) {
                     const PrfTagPart g = prf_tag_part(T, R, D.tags[i]);
-                    const uint32_t ho = prf_low<1, 4>(T, R, g, (uint32_t)chunkId) & cmask;
+                    const uint32_t ho = prf_low<8, 4>(T, R, g, (uint32_t)chunkId) & cmask;
                     if (ho == (uint32_t)offset) {
                         const uint64_t pp = D.pp[i];
                         if (pp == kDefaultProgramPoint || pp / C != chunkId) atomicMin(&s_hit, (uint32_t)i);
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) s_offs[c] = __ldcg(D.poff + (uint64_t)c * P + hit);
         } else {
             const PrfTagPart g = prf_tag_part(T, R, D.tags[hit]);
-            for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) s_offs[c] = prf_low<1, 4>(T, R, g, c) & cmask;
+            for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS) s_offs[c] = prf_low<8, 4>(T, R, g, c) & cmask;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         if (indexed) {
             const PrfTagPart g = prf_tag_part(T, R, s_newtag);
             for (uint32_t c = threadIdx.x; c < S; c += CL_THREADS)
-                D.poff[(uint64_t)c * P + hit] = (uint16_t)(prf_low<1, 2>(T, R, g, c) & cmask);
+                D.poff[(uint64_t)c * P + hit] = (uint16_t)(prf_low<8, 2>(T, R, g, c) & cmask);
         }
         __threadfence_block();
         __syncthreads();
@@ -606,7 +606,7 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     mark(1);
     uint64_t max_p = 0;
     for (uint64_t i = 0; i < c->n_parts; i++) if (c->host_parts[i].poff) max_p = std::max<uint64_t>(max_p, c->host_parts[i].n_primary);
-    const size_t smem = (aes_tab_words<1>() + 64 + stride + CL_MAX_LIST + max_p) * 4;
+    const size_t smem = (aes_tab_words<8>() + 64 + stride + CL_MAX_LIST + max_p) * 4;
     if (smem > 200 * 1024) return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: primaryHintNum too large for the shared-memory mirror");
     PM_CUDA(cudaFuncSetAttribute(client_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     client_prepare_kernel<<<(unsigned)c->n_parts, CL_THREADS, smem, c->stream>>>(c->d_parts, d_q, (uint32_t)q, (uint32_t)stride, d_off,

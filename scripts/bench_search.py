@@ -99,16 +99,25 @@ def main():
             groups.append(group)
         res["lockstep_group_setup_s"] = time.perf_counter() - t0
         lqs = [vec[np.random.default_rng(70 + gi).integers(0, n, a.lanes * a.lane_q)] + np.float32(0.5) for gi in range(a.groups)]
-        for gi in range(a.groups):
-            graphann.SearchKNNLockstep(groups[gi], lqs[gi][:a.lanes], k, a.step, a.parallel)      # warm-up: one query per lane
-        l0 = cabi.launch_count()
-        th = [threading.Thread(target=graphann.SearchKNNLockstep, args=(groups[gi], lqs[gi], k, a.step, a.parallel)) for gi in range(a.groups)]
-        t0 = time.perf_counter()
+        # one host thread per group; each warms up (one query per lane) and then waits for the common start
+        start, done = threading.Barrier(a.groups + 1), threading.Barrier(a.groups + 1)
+
+        def drive(gi):
+            graphann.SearchKNNLockstep(groups[gi], lqs[gi][:a.lanes], k, a.step, a.parallel)
+            start.wait()
+            graphann.SearchKNNLockstep(groups[gi], lqs[gi], k, a.step, a.parallel)
+            done.wait()
+
+        th = [threading.Thread(target=drive, args=(gi,)) for gi in range(a.groups)]
         for t in th:
             t.start()
+        start.wait()
+        l0 = cabi.launch_count()
+        t0 = time.perf_counter()
+        done.wait()
+        ldt = time.perf_counter() - t0
         for t in th:
             t.join()
-        ldt = time.perf_counter() - t0
         nlq = a.groups * a.lanes * a.lane_q
         res.update(lanes=a.lanes, groups=a.groups, lockstep_queries=nlq, lockstep_qps=nlq / ldt, lockstep_ms_per_step=ldt / (a.lane_q * a.step) * 1e3,
                    lockstep_gpu_launches=cabi.launch_count() - l0)
