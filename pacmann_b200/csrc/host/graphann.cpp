@@ -151,7 +151,7 @@ int PIRGraphInfo::FetchGroupRaw(const std::vector<PIRGraphInfo *> &infos, const 
         calls[l] = {g->PIR, g->wsIdx.data(), cnt, nullptr, queries[l], queries[l] ? dists[l]->data() : nullptr, 0, entries[l]->data()};
     }
     if (pianopir::SimpleBatchPianoPIR::QueryFlatGroup(calls, (uint64_t)infos[0]->Dim) != 0) return -1;
-#pragma omp parallel for schedule(static) if (L > 2)
+#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (L > 2)
     for (size_t l = 0; l < L; l++) {   // the reference's correctness accounting (private-search.go:480-504)
         PIRGraphInfo *g = infos[l];
         for (size_t i = 0; i < ids[l]->size(); i++) {
@@ -489,7 +489,7 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
         const int64_t act = std::min(L, nq - base);
         std::string err;
         auto t0 = now();
-#pragma omp parallel for schedule(static) if (act > 2)
+#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (act > 2)
         for (int64_t l = 0; l < act; l++) {
             try {
                 qptr[(size_t)l] = queryVectors + (base + l) * dim;
@@ -532,7 +532,7 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
             }
             tFetch += since(t0);
             t0 = now();
-#pragma omp parallel for schedule(static) if (act > 2)
+#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (act > 2)
             for (int64_t l = 0; l < act; l++)
                 if (more[(size_t)l]) {
                     if (groupable) lanes[(size_t)l]->wsState.CollectFreshRaw(batch[(size_t)l], rawEntries[(size_t)l], srcDists[(size_t)l]);
@@ -563,7 +563,7 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
             tMiss += since(t0);
             nMissTotal += nMissing;
             t0 = now();
-#pragma omp parallel for schedule(static) if (act > 2)
+#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (act > 2)
             for (int64_t l = 0; l < act; l++)
                 if (more[(size_t)l]) {
                     if (groupable) lanes[(size_t)l]->wsState.ApplyFreshRaw(batch[(size_t)l], rawEntries[(size_t)l], missDist.data() + missBase[(size_t)l]);

@@ -2,6 +2,7 @@
 #include "pianopir.hpp"
 
 #include <immintrin.h>
+#include <omp.h>
 
 #include <chrono>
 #include <cmath>
@@ -616,6 +617,16 @@ int SimpleBatchPianoPIR::Query(const std::vector<uint64_t> &idx, std::vector<std
     return 0;
 }
 
+int HostThreads() {
+    static const int n = [] {
+        const char *v = getenv("PM_HOST_THREADS");
+        int t = v && *v ? atoi(v) : 0;
+        if (t <= 0) t = std::min(8, std::max(1, omp_get_num_procs()));
+        return t;
+    }();
+    return n;
+}
+
 void EntryCache::Reserve(uint64_t entries) {
     while (slabs.size() * kPerSlab < entries) slabs.emplace_back(new uint64_t[kPerSlab * E]());   // value-initialised: pages touched now
 }
@@ -919,7 +930,7 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
         gc.rc = gc.pir->QueryFlat(gc.idx, gc.n, dst, gc.query_vec, dim, gc.dists);
     }
     std::vector<size_t> base(L + 1, 0);
-#pragma omp parallel for schedule(static) if (L > 2)
+#pragma omp parallel for schedule(static) num_threads(HostThreads()) if (L > 2)
     for (size_t l = 0; l < L; l++) {
         if (!grouped[l]) continue;
         SimpleBatchPianoPIR *p = calls[l].pir;
@@ -978,7 +989,7 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
     const int32_t *gst = host->wsStatus.data();
     const float *gdist = host->wsDist.data();
     std::vector<char> due(L, 0);
-#pragma omp parallel for schedule(static) if (L > 2)
+#pragma omp parallel for schedule(static) num_threads(HostThreads()) if (L > 2)
     for (size_t l = 0; l < L; l++) {
         if (!grouped[l] || calls[l].rc != 0) continue;
         SimpleBatchPianoPIR *p = calls[l].pir;

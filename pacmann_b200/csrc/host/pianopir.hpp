@@ -80,6 +80,10 @@ struct PendingQuery {
     std::vector<uint32_t> offsets;  // what goes to the server (Dummy, Real)
 };
 
+// Threads a lock-step group uses for its per-lane host work (OpenMP team size): PM_HOST_THREADS, default min(8, cores).
+// Several groups (and several ranks) run side by side, so a team must not grab the whole machine.
+int HostThreads();
+
 // localCache (pir.go:127, :381-383, :468): idx -> entry.  Entries live in fixed-size slabs (stable addresses, reused after
 // clear()) instead of one heap vector per entry: a search step inserts ~100 entries per client and with many clients in
 // lock step the per-entry allocations (first-touch page faults under the process-wide mm lock) were the largest host
