@@ -30,6 +30,8 @@ struct ClientPartDev {
     uint64_t *hist;                            // [S]
     uint64_t *finished;                        // [1]
     uint16_t *poff;                            // [S][P] offset index of the primary hints (nullptr if chunk_size > 65536)
+    uint32_t *pp32;                            // [P] program points once more as u32 (all values < 2^31), 16-byte aligned: the
+                                               // prepare kernel mirrors them in shared memory with a few vector loads
 };
 
 __device__ __forceinline__ uint64_t mix64_dev(uint64_t seed, uint64_t ctr) {
@@ -48,6 +50,7 @@ __global__ void client_init_kernel(const ClientPartDev *parts, const uint32_t *p
         if (i < P) {
             D.tags[i] = i;
             D.pp[i] = kDefaultProgramPoint;
+            D.pp32[i] = (uint32_t)kDefaultProgramPoint;
         }
         if (i < B) {
             D.btags[i] = P + i;
@@ -149,8 +152,12 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     aes_tab_fill<8>(s_tab, c_te0);
     if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
     const bool indexed = D.poff != nullptr;
-    if (indexed)
-        for (uint64_t i = threadIdx.x; i < P; i += NT) s_pp[i] = (uint32_t)D.pp[i];   // values < 2^31 or 0x7fffffff
+    if (indexed) {   // values < 2^31 or 0x7fffffff; s_pp is 16-byte aligned (every region before it is a multiple of 4 words)
+        const uint4 *src = reinterpret_cast<const uint4 *>(D.pp32);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_pp);
+        for (uint64_t i = threadIdx.x; i < P / 4; i += NT) dst[i] = __ldcg(src + i);
+        for (uint64_t i = (P & ~3ull) + threadIdx.x; i < P; i += NT) s_pp[i] = D.pp32[i];
+    }
     __syncthreads();
     const AesTab<8> T{s_tab + (threadIdx.x & 3)};
     const RkOfPtr R{s_rk};
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             // response-independent half of the refresh (pir.go:460-467)
             D.tags[hit] = btag;
             D.pp[hit] = Q.idx;
+            D.pp32[hit] = (uint32_t)Q.idx;
             if (indexed) s_pp[hit] = (uint32_t)Q.idx;
             *D.finished = s_fin + 1;
             D.hist[chunkId] = inGroup + 1;
@@ -376,7 +384,7 @@ static int client_scratch(pm_client *c, int slot, size_t bytes, void **out) {
             c->wbuf[slot] = nullptr;
             c->wbytes[slot] = 0;
         }
-        const size_t want = bytes + bytes / 4 + 4096;
+        const size_t want = std::max<size_t>(bytes + bytes / 2, (size_t)1 << 20);   // re-growing costs a cudaFree (device-wide sync)
         cudaError_t e = cudaMalloc(&c->wbuf[slot], want);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -404,6 +412,7 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
         const uint64_t P = p.n_primary, B = p.set_size * p.backup_group;
         words += 2 * P + P * E + 2 * B + 2 * B * E + p.set_size + 2;
         if (p.chunk_size <= 65536) words += (p.set_size * P * 2 + 7) / 8 + 2;   // offset index
+        words += (P * 4 + 7) / 8 + 2;                                           // u32 program points
         words = (words + 3) & ~1ull;
         if (p.set_size > max_set) max_set = p.set_size;
     }
@@ -440,6 +449,9 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
             cur += (p.set_size * P * 2 + 7) / 8;
             if ((uintptr_t)cur & 15) cur += 1;
         }
+        D.pp32 = (uint32_t *)cur;
+        cur += (P * 4 + 7) / 8;
+        if ((uintptr_t)cur & 15) cur += 1;
     }
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { cudaFree(c->arena); cudaFree(c->d_parts); delete c; return set_error(PM_ERR_CUDA, "pm_client_create: stream creation failed"); }

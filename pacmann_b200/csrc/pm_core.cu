@@ -2,6 +2,8 @@
 #include <cstring>
 #include <new>
 
+#include <algorithm>
+
 #include "pm_common.cuh"
 
 namespace pm {
@@ -77,7 +79,9 @@ int dev_work(int device, size_t bytes, void **ptr, cudaStream_t *stream, std::un
             w.buf = nullptr;
             w.bytes = 0;
         }
-        size_t want = bytes + bytes / 4 + 4096;
+        // grow-only, geometrically and from 8 MB: re-growing means cudaFree + cudaMalloc (milliseconds, device-wide
+        // synchronisation), and callers such as the per-step distance calls of a search ask for slowly creeping sizes
+        size_t want = std::max<size_t>(2 * bytes, (size_t)8 << 20);
         cudaError_t e = cudaMalloc(&w.buf, want);
         if (e != cudaSuccess) {
             cudaGetLastError();

@@ -53,7 +53,8 @@ def main():
     f.Preprocess()
     prep_s = time.perf_counter() - t0
     pir = f.PIR
-    f.SearchKNNBatch(queries[:2], k, a.step, a.parallel)          # warm-up
+    wq = vec[np.random.default_rng(3).integers(0, n, 2)] + np.float32(0.5)
+    f.SearchKNNBatch(wq, k, a.step, a.parallel)          # warm-up on queries of its own (a repeated query is served from the local cache)
     l0, s0 = cabi.launch_count(), pir.serverQueries
     t0 = time.perf_counter()
     ret, _ = f.SearchKNNBatch(queries, k, a.step, a.parallel)
@@ -67,7 +68,7 @@ def main():
         fs = [f] + [graphann.GraphANNFrontend(vec, graph, seed=seed + 100 + i, share_db_with=f) for i in range(a.clients - 1)]
         for g in fs[1:]:
             g.Preprocess()
-            g.SearchKNNBatch(queries[:1], k, a.step, a.parallel)
+            g.SearchKNNBatch(wq[:1], k, a.step, a.parallel)
         per = max(1, a.q // 2)
         qs = [vec[np.random.default_rng(50 + i).integers(0, n, per)] + np.float32(0.5) for i in range(a.clients)]
         outs = [None] * a.clients
@@ -102,8 +103,10 @@ def main():
         # one host thread per group; each warms up (one query per lane) and then waits for the common start
         start, done = threading.Barrier(a.groups + 1), threading.Barrier(a.groups + 1)
 
+        wqs = [vec[np.random.default_rng(170 + gi).integers(0, n, a.lanes)] + np.float32(0.5) for gi in range(a.groups)]
+
         def drive(gi):
-            graphann.SearchKNNLockstep(groups[gi], lqs[gi][:a.lanes], k, a.step, a.parallel)
+            graphann.SearchKNNLockstep(groups[gi], wqs[gi], k, a.step, a.parallel)
             start.wait()
             graphann.SearchKNNLockstep(groups[gi], lqs[gi], k, a.step, a.parallel)
             done.wait()
