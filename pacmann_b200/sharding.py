@@ -1,7 +1,9 @@
 """Hint-set sharding of PianoPIR preprocessing across GPUs: every hint's parity depends only on
 (key, tag, DB), so rank r of N computes hints [H*r/N, H*(r+1)/N) of every sub-PIR over its own replica of the DB,
-with no data-path exchange; the parities are then gathered on the consumer.  Pure index arithmetic, shared by
-bench.py and the multi-process tests."""
+with no data-path exchange; the parities are then gathered on the consumer.  The linear-scan baseline (A11) is the one
+piece with a real exchange step: rows are sharded, every rank scans its rows and the per-query checksums -- sums mod
+2^32 -- are all-reduced.  Pure index arithmetic, shared by bench.py, scripts/scan_multi_gpu.py and the multi-process
+tests."""
 
 
 def shard_range(n_hints, rank, world):
@@ -32,3 +34,18 @@ def assemble(gathered, hints_per_part, world, entry_u64):
             out[i][a:b] = buf[off:off + (b - a)]
             off += b - a
     return out
+
+
+def row_shard(n_rows, rank, world):
+    """half-open row range owned by `rank` in the sharded linear scan"""
+    return n_rows * rank // world, n_rows * (rank + 1) // world
+
+
+def allreduce_checksums(dist, checksums_u32):
+    """Combine per-rank partial checksums (uint32, wrapping sums over the rank's rows) into the checksums of the whole
+    table.  `checksums_u32` is a torch tensor holding values in [0, 2^32) as int64 (torch has no uint32 collectives):
+    an int64 sum over at most 2^31 ranks cannot overflow, the result is reduced mod 2^32 afterwards -- exactly the
+    wrap-around of the reference's uint32 accumulator (graphann_test.go:268-273)."""
+    dist.all_reduce(checksums_u32, op=dist.ReduceOp.SUM)
+    checksums_u32 &= 0xFFFFFFFF
+    return checksums_u32

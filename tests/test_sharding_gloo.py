@@ -73,3 +73,36 @@ def test_shard_ranges_partition_the_hints():
             assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
             sizes = [b - a for a, b in r]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _scan_worker(rank, world, port, result_file):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as o
+    from pacmann_b200 import sharding
+
+    n, d, nq = 10007, 32, 9
+    rng = np.random.default_rng(5)
+    rows = rng.integers(0, 2**32, (n, d), dtype=np.uint32)       # every rank draws the same table
+    rows[::3] = 0xFFFFFFFF                                        # partial sums far beyond 2^32: the wrap must survive the all-reduce
+    qs = rng.integers(0, 2**32, (nq, d), dtype=np.uint32)
+    a, b = sharding.row_shard(n, rank, world)
+    part = np.asarray(o.ip_scan(rows[a:b], qs), dtype=np.uint32)  # per-shard compute: the CPU oracle here, pm_ip_u32_scan on the GPU box
+    t = torch.from_numpy(part.astype(np.int64))
+    sharding.allreduce_checksums(dist, t)
+    if rank == 0:
+        want = np.asarray(o.ip_scan(rows, qs), dtype=np.uint32)
+        open(result_file, "w").write("ok" if (t.numpy().astype(np.uint32) == want).all() else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_sharded_scan_allreduces_to_the_unsharded_checksums(world, tmp_path):
+    """SURVEY 8e, linear scan: rows sharded over ranks, per-rank partial checksums, all-reduce mod 2^32."""
+    result = tmp_path / "scan_result.txt"
+    port = 29650 + world
+    mp.spawn(_scan_worker, args=(world, port, str(result)), nprocs=world, join=True)
+    assert result.read_text() == "ok"
