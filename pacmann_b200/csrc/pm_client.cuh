@@ -63,28 +63,16 @@ __global__ void client_init_kernel(const ClientPartDev *parts, const uint32_t *p
     }
 }
 
-// Ordered list (array order = processing order) of the queries that belong to sub-PIR `part`, built by warp 0 with
-// coalesced reads; replaces a serial scan of the whole query array (one dependent global load per query).
-constexpr uint32_t CL_MAX_LIST = 2048;
-__device__ __forceinline__ uint32_t client_build_list(const uint32_t *query_words /* ClientQueryDev as 8 u32 */, uint32_t q,
-                                                       uint32_t part, uint32_t *s_list) {
-    __shared__ uint32_t s_count;
-    if (threadIdx.x < 32) {
-        uint32_t n = 0;
-        for (uint32_t base = 0; base < q; base += 32) {
-            const uint32_t t = base + threadIdx.x;
-            const bool mine = t < q && query_words[(uint64_t)t * 8] == part;
-            const uint32_t m = __ballot_sync(0xffffffffu, mine);
-            if (mine) {
-                const uint32_t pos = n + __popc(m & ((1u << threadIdx.x) - 1));
-                if (pos < CL_MAX_LIST) s_list[pos] = t;
-            }
-            n += __popc(m);
-        }
-        if (threadIdx.x == 0) s_count = n;
-    }
+// The queries of sub-PIR `part`, in array order (= processing order): positions part_start[part] .. part_start[part+1]
+// of part_items.  The host builds these lists (a counting sort of q records) -- an earlier version let every CTA scan
+// the whole query array for its own entries, which at 3072 queries and 512 CTAs was most of the kernels' time.
+constexpr uint32_t CL_MAX_LIST = 2048;   // queries of one sub-PIR per call
+__device__ __forceinline__ uint32_t client_load_list(const uint32_t *part_start, const uint32_t *part_items, uint32_t part,
+                                                      uint32_t *s_list, uint32_t cap) {
+    const uint32_t b = part_start[part], n = min(part_start[part + 1] - b, cap);
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_list[i] = part_items[b + i];
     __syncthreads();
-    return s_count;
+    return n;
 }
 
 struct RkOfPtr {
@@ -130,6 +118,7 @@ struct ClientMeta {
 // phase C rewrites the promoted backup hint's row.  Program points are mirrored in shared memory (u32) so the
 // not-programmed-in-this-chunk test needs no dependent load.
 __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const ClientPartDev *parts, const ClientQueryDev *queries,
+                                                                    const uint32_t *part_start, const uint32_t *part_items,
                                                                     uint32_t q, uint32_t stride, uint32_t *offsets,
                                                                     ClientMeta *meta, uint64_t *a_row0, uint64_t *a_nrows,
                                                                     uint32_t *a_chunk, uint32_t *a_set) {
@@ -147,8 +136,8 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     const ClientPartDev &D = parts[part];
     const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
     const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
-    const uint32_t n_mine = client_build_list(reinterpret_cast<const uint32_t *>(queries), q, part, s_list);
-    if (n_mine == 0) return;
+    if (part_start[part] == part_start[part + 1]) return;
+    const uint32_t n_mine = client_load_list(part_start, part_items, part, s_list, CL_MAX_LIST);
     aes_tab_fill<8>(s_tab, c_te0);
     if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
     const bool indexed = D.poff != nullptr;
@@ -302,8 +291,8 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
 // Thread w owns word w of every entry, so the only cross-query dependency -- two queries of a part refreshing
 // the same hint slot -- is a read-after-write inside one thread: no barrier is needed, and the operands that do not
 // depend on earlier queries (answer, replacement value, backup parity) are fetched four queries ahead.
-__global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev *parts, const ClientQueryDev *queries,
-                                                            const ClientMeta *meta, uint32_t q, uint32_t E,
+__global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev *parts, const uint32_t *part_start,
+                                                            const uint32_t *part_items, const ClientMeta *meta, uint32_t E,
                                                             const uint64_t *__restrict__ answers, uint64_t *__restrict__ out) {
     const uint32_t part = blockIdx.x;
     const ClientPartDev &D = parts[part];
@@ -311,7 +300,8 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
     __shared__ uint32_t s_list[CL_MAX_LIST];
     struct FinMeta { uint32_t hit, slot; int32_t status; };
     __shared__ FinMeta s_meta[CL_MAX_LIST];
-    const uint32_t n_mine = client_build_list(reinterpret_cast<const uint32_t *>(queries), q, part, s_list);
+    if (part_start[part] == part_start[part + 1]) return;
+    const uint32_t n_mine = client_load_list(part_start, part_items, part, s_list, CL_MAX_LIST);
     for (uint32_t k = threadIdx.x; k < n_mine; k += blockDim.x) {
         const ClientMeta m = meta[s_list[k]];
         s_meta[k] = FinMeta{(uint32_t)m.hit, (uint32_t)m.slot, m.status};
@@ -369,6 +359,7 @@ struct pm_client {
     cudaStream_t stream = nullptr;          // every client owns its stream, scratch and lock, so several clients that
     void *wbuf[2] = {nullptr, nullptr};     // share one pm_db (one per user) can be driven from different host threads
     size_t wbytes[2] = {0, 0};
+    std::vector<uint32_t> csr;   // per-part query lists of the current call (host copy)
     void *stage = nullptr;   // pinned host staging for results
     size_t stage_bytes = 0;
     cudaEvent_t ev[6] = {};
@@ -585,7 +576,8 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     const size_t b_q = q * sizeof(ClientQueryDev), b_meta = q * sizeof(ClientMeta), b_off = q * stride * 4, b_desc = q * 24;
     void *d_in = nullptr, *d_out = nullptr;
     const size_t b_qv = (n_vecs * dim * 4 + 15) & ~15ull, b_vid = vec_id ? q * 4 : 0, b_dist = dist_out ? q * 4 : 0;
-    if ((rc = client_scratch(c, 1, b_q + b_off + b_desc + b_qv + b_vid + 64, &d_in))) return rc;
+    const size_t b_csr = ((c->n_parts + 1 + q) * 4 + 15) & ~15ull;
+    if ((rc = client_scratch(c, 1, b_q + b_off + b_desc + b_qv + b_vid + b_csr + 64, &d_in))) return rc;
     if ((rc = client_scratch(c, 0, 2 * q * E * 8 + b_meta + b_dist, &d_out))) return rc;
     ClientQueryDev *d_q = (ClientQueryDev *)d_in;
     uint32_t *d_off = (uint32_t *)((char *)d_in + b_q);
@@ -614,8 +606,22 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     static const bool prof = getenv("PM_CLIENT_PROFILE") != nullptr;
     if (prof && !c->ev[0]) for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
     auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], c->stream); };
+    // per-part query lists (counting sort; array order within a part is the processing order)
+    c->csr.resize(c->n_parts + 1 + q);
+    {
+        uint32_t *start = c->csr.data(), *items = start + c->n_parts + 1;
+        uint32_t acc = 0;
+        for (uint64_t i = 0; i < c->n_parts; i++) { start[i] = acc; acc += per_part[i]; }
+        start[c->n_parts] = acc;
+        std::vector<uint32_t> &cur = per_part;   // reuse as running positions
+        for (uint64_t i = 0; i < c->n_parts; i++) cur[i] = start[i];
+        for (uint64_t t = 0; t < q; t++) items[cur[queries[t].part]++] = (uint32_t)t;
+        for (uint64_t i = 0; i < c->n_parts; i++) cur[i] -= start[i];   // back to counts
+    }
+    uint32_t *d_start = (uint32_t *)(((uintptr_t)((char *)d_qv + b_qv + b_vid) + 15) & ~(uintptr_t)15), *d_items = d_start + c->n_parts + 1;
     mark(0);
     PM_CUDA(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, c->stream));
+    PM_CUDA(cudaMemcpyAsync(d_start, c->csr.data(), (c->n_parts + 1 + q) * 4, cudaMemcpyHostToDevice, c->stream));
     mark(1);
     uint64_t max_p = 0;
     for (uint64_t i = 0; i < c->n_parts; i++) if (c->host_parts[i].poff) max_p = std::max<uint64_t>(max_p, c->host_parts[i].n_primary);
@@ -626,14 +632,14 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     // that carry a lock-step group run 256-thread CTAs (4 per SM): more parts -- of this call and of the other groups'
     // concurrent calls -- are resident at once (measured: one 32-lane group 139 -> 116 us, 4 x 16 lanes +5 % queries/s)
     const unsigned prep_threads = c->n_parts <= 64 ? CL_THREADS : CL_THREADS / 2;
-    client_prepare_kernel<<<(unsigned)c->n_parts, prep_threads, smem, c->stream>>>(c->d_parts, d_q, (uint32_t)q, (uint32_t)stride, d_off,
-                                                                                  d_meta, d_row0, d_nrows, d_chunk, d_set);
+    client_prepare_kernel<<<(unsigned)c->n_parts, prep_threads, smem, c->stream>>>(c->d_parts, d_q, d_start, d_items, (uint32_t)q, (uint32_t)stride,
+                                                                                  d_off, d_meta, d_row0, d_nrows, d_chunk, d_set);
     PM_CHECK_LAUNCH();
     count_launch();
     mark(2);
     if ((rc = answer_enqueue(db, d_row0, d_nrows, d_chunk, d_set, d_off, stride, q, (uint32_t)stride, d_ans, c->stream))) return rc;
     mark(3);
-    client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, c->stream>>>(c->d_parts, d_q, d_meta, (uint32_t)q, (uint32_t)E, d_ans, d_res);
+    client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, c->stream>>>(c->d_parts, d_start, d_items, d_meta, (uint32_t)E, d_ans, d_res);
     PM_CHECK_LAUNCH();
     count_launch();
     if (dist_out) {  // distances of the answered entries' vectors to the search query, on the same stream (A10 call site)
