@@ -182,6 +182,10 @@ int pm_l2_batch(pm_db *db, uint64_t dim, const float *queries, uint64_t n_querie
                 float *out);
 int pm_l2_batch_dev(pm_db *db, uint64_t dim, const float *queries, uint64_t n_queries, const int64_t *ids, uint64_t k,
                     float *out, void *stream);
+/* out[p] = L2Dist(first `dim` fp32 of row ids_a[p], of row ids_b[p]); a row id outside [0, n_rows) gives +inf.  The
+ * distance matrices of graph construction (robustPrune, graphann/build_graph.go:169-236) in one launch. */
+int pm_l2_idpairs(pm_db *db, uint64_t dim, const int64_t *ids_a, const int64_t *ids_b, uint64_t n, float *out);
+int pm_l2_idpairs_dev(pm_db *db, uint64_t dim, const int64_t *ids_a, const int64_t *ids_b, uint64_t n, float *out, void *stream);
 
 /* A11: db viewed as rows[n_rows][dim] uint32 (dim = 2*entry_u64, dim % 16 == 0 as the reference requires).
  * checksum_out[t] = sum_i InnerProduct(row_i, queries[t]) mod 2^32.  If ip_out != NULL it also receives

@@ -44,6 +44,7 @@ def lib():
             "orc_l2_distance_simd": (C.c_float, [f32p, f32p, C.c_int64]),
             "orc_l2dist": (C.c_float, [f32p, f32p, C.c_int64]),
             "orc_l2dist_batch": (None, [f32p, C.c_int64, C.c_int64, f32p, i64p, C.c_int64, C.c_int64, f32p]),
+            "orc_robust_prune": (C.c_int64, [f32p, C.c_int64, C.c_int64, i64p, C.c_int64, C.c_int64, C.c_float, i64p]),
             "orc_inner_product": (C.c_uint32, [u32p, u32p, C.c_int64]),
             "orc_ip_scan": (None, [u32p, C.c_int64, C.c_int64, u32p, C.c_int64, u32p, C.c_int]),
             "orc_gen_params": (None, [C.c_uint64, u64p, u64p]),
@@ -151,6 +152,15 @@ def l2dist_batch(vecs, dim, queries, ids):
     out = np.zeros(ids.shape, np.float32)
     lib().orc_l2dist_batch(_p(vecs, f32p), vecs.shape[1], dim, _p(queries, f32p), _p(ids, i64p), ids.shape[0], ids.shape[1], _p(out, f32p))
     return out
+
+
+def robust_prune(vectors, u, candidates, m, alpha):
+    """robustPrune (build_graph.go:169-236); ties in the distance to u keep candidate order."""
+    vectors = np.ascontiguousarray(vectors, np.float32)
+    cand = np.ascontiguousarray(candidates, np.int64)
+    out = np.zeros(max(cand.size, 1), np.int64)
+    n = lib().orc_robust_prune(_p(vectors, f32p), vectors.shape[1], int(u), _p(cand, i64p), cand.size, int(m), float(alpha), _p(out, i64p))
+    return out[:n].copy()
 
 
 def inner_product(a, b):

@@ -1068,3 +1068,51 @@ ORC_API int orc_search_knn_private(orc_batch *pir, const float *vectors, const i
     free(sv); free(sn);
     return rc;
 }
+
+
+/* robustPrune (graphann/build_graph.go:169-236): prune the candidates of vertex u to at most m out-neighbours.
+ * vectors [n][dim].  sort.Slice is unstable in Go: candidates at equal distance from u may come out in any order; this
+ * restatement (and the GPU path) keeps them in candidate order (a stable sort).  Returns the number of ids written. */
+typedef struct { int64_t id; float dist; int64_t pos; } orc_idd;
+static int orc_idd_cmp(const void *a, const void *b) {
+    const orc_idd *x = (const orc_idd *)a, *y = (const orc_idd *)b;
+    if (x->dist < y->dist) return -1;
+    if (x->dist > y->dist) return 1;
+    return x->pos < y->pos ? -1 : (x->pos > y->pos ? 1 : 0);
+}
+ORC_API int64_t orc_robust_prune(const float *vectors, int64_t dim, int64_t u, const int64_t *candidates, int64_t n_cand, int64_t m,
+                                 float alpha, int64_t *out) {
+    if (n_cand <= m) {                                   /* :170-172 */
+        for (int64_t i = 0; i < n_cand; i++) out[i] = candidates[i];
+        return n_cand;
+    }
+    orc_idd *d = (orc_idd *)malloc((size_t)n_cand * sizeof(orc_idd));
+    orc_idd *acc = (orc_idd *)malloc((size_t)n_cand * sizeof(orc_idd)), *dis = (orc_idd *)malloc((size_t)n_cand * sizeof(orc_idd));
+    for (int64_t i = 0; i < n_cand; i++) {               /* :175-181 */
+        d[i].id = candidates[i];
+        d[i].dist = orc_l2dist(vectors + u * dim, vectors + candidates[i] * dim, dim);
+        d[i].pos = i;
+    }
+    qsort(d, (size_t)n_cand, sizeof(orc_idd), orc_idd_cmp);   /* :183-185 */
+    int64_t na = 0, nd = 0;
+    for (int64_t i = 0; i < n_cand; i++) {               /* :187-208 */
+        const int64_t v = d[i].id;
+        const float dist_uv = d[i].dist;
+        int ok = 1;
+        for (int64_t j = 0; j < na; j++) {
+            const float dj = orc_l2dist(vectors + acc[j].id * dim, vectors + v * dim, dim);
+            if (dj * alpha < dist_uv) { ok = 0; break; }
+        }
+        if (ok) {
+            acc[na++] = d[i];
+            if (na == m) break;
+        } else {
+            dis[nd++] = d[i];
+        }
+    }
+    if (na < m)                                          /* :213-226 */
+        for (int64_t i = 0; i < nd && na < m; i++) acc[na++] = dis[i];
+    for (int64_t i = 0; i < na; i++) out[i] = acc[i].id;
+    free(d); free(acc); free(dis);
+    return na;
+}

@@ -76,6 +76,8 @@ SIGNATURES = {
     "pm_l2_query": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int]),
     "pm_l2_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_l2_batch_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "pm_l2_idpairs": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "pm_l2_idpairs_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pm_ip_u32_scan": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
     "pm_ip_u32_scan_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
@@ -294,6 +296,15 @@ def l2_batch(db, dim, queries, ids):
     assert queries.shape == (nq, dim)
     out = np.zeros((nq, k), np.float32)
     check(lib().pm_l2_batch(db.h, dim, _ptr(queries), nq, _ptr(ids), k, _ptr(out)))
+    return out
+
+
+def l2_idpairs(db, dim, ids_a, ids_b):
+    """out[p] = L2Dist(row ids_a[p], row ids_b[p]) over the resident table"""
+    ids_a, ids_b = _arr(ids_a, np.int64).reshape(-1), _arr(ids_b, np.int64).reshape(-1)
+    assert ids_a.size == ids_b.size
+    out = np.zeros(ids_a.size, np.float32)
+    check(lib().pm_l2_idpairs(db.h, dim, _ptr(ids_a), _ptr(ids_b), ids_a.size, _ptr(out)))
     return out
 
 

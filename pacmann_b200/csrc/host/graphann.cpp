@@ -581,4 +581,56 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
     return 0;
 }
 
+void RobustPruneBatch(pm_db *vecDb, int64_t dim, const std::vector<int64_t> &us, const std::vector<std::vector<int64_t>> &candidates,
+                      int64_t m, float alpha, std::vector<std::vector<int64_t>> *out) {
+    const size_t B = us.size();
+    out->assign(B, {});
+    // pair list: per vertex with more than m candidates, K pairs (u, c_i) then K(K-1)/2 pairs (c_i, c_j), i < j
+    std::vector<int64_t> ia, ib;
+    std::vector<size_t> base(B, 0);
+    for (size_t b = 0; b < B; b++) {
+        const auto &c = candidates[b];
+        const size_t K = c.size();
+        if ((int64_t)K <= m) continue;
+        base[b] = ia.size();
+        for (size_t i = 0; i < K; i++) { ia.push_back(us[b]); ib.push_back(c[i]); }
+        for (size_t i = 0; i < K; i++)
+            for (size_t j = i + 1; j < K; j++) { ia.push_back(c[i]); ib.push_back(c[j]); }
+    }
+    std::vector<float> d(ia.size());
+    if (!ia.empty()) check(pm_l2_idpairs(vecDb, (uint64_t)dim, ia.data(), ib.data(), ia.size(), d.data()), "pm_l2_idpairs");
+    struct IdWithDist { int64_t id; float dist; size_t pos; };
+    for (size_t b = 0; b < B; b++) {
+        const auto &c = candidates[b];
+        const size_t K = c.size();
+        if ((int64_t)K <= m) { (*out)[b] = c; continue; }                       // build_graph.go:170-172
+        const float *du = d.data() + base[b], *dm = du + K;
+        auto pair_dist = [&](size_t i, size_t j) {                              // candidate positions, any order
+            if (i > j) std::swap(i, j);
+            return dm[i * K - i * (i + 1) / 2 + (j - i - 1)];
+        };
+        std::vector<IdWithDist> dist2u(K);
+        for (size_t i = 0; i < K; i++) dist2u[i] = {c[i], du[i], i};             // :175-181
+        std::stable_sort(dist2u.begin(), dist2u.end(), [](const IdWithDist &x, const IdWithDist &y) { return x.dist < y.dist; });  // :183-185
+        std::vector<IdWithDist> accept, discarded;
+        for (size_t i = 0; i < K; i++) {                                        // :187-208
+            const float dist_uv = dist2u[i].dist;
+            bool ok = true;
+            for (size_t j = 0; j < accept.size(); j++) {
+                const float dj = accept[j].pos == dist2u[i].pos ? 0.f : pair_dist(accept[j].pos, dist2u[i].pos);
+                if (dj * alpha < dist_uv) { ok = false; break; }
+            }
+            if (ok) {
+                accept.push_back(dist2u[i]);
+                if ((int64_t)accept.size() == m) break;
+            } else {
+                discarded.push_back(dist2u[i]);
+            }
+        }
+        if ((int64_t)accept.size() < m)                                         // :213-226
+            for (size_t i = 0; i < discarded.size() && (int64_t)accept.size() < m; i++) accept.push_back(discarded[i]);
+        for (auto &a : accept) (*out)[b].push_back(a.id);
+    }
+}
+
 }  // namespace graphann

@@ -164,6 +164,14 @@ private:
     std::vector<float> wsSrcDists;
 };
 
+// robustPrune (build_graph.go:169-236) for a batch of vertices over vectors resident on the GPU (`vecDb`: rows of dim
+// fp32 viewed as dim/2 uint64).  All distances the reference evaluates one L2Dist call at a time -- u to each candidate
+// and candidate to candidate -- come from ONE pm_l2_idpairs launch for the whole batch; the greedy selection then runs
+// on the host over that matrix, with the same comparisons in the same order.  Candidates at equal distance from u keep
+// candidate order (Go's sort.Slice leaves that order unspecified).  out[b] = pruned neighbour list of us[b].
+void RobustPruneBatch(pm_db *vecDb, int64_t dim, const std::vector<int64_t> &us, const std::vector<std::vector<int64_t>> &candidates,
+                      int64_t m, float alpha, std::vector<std::vector<int64_t>> *out);
+
 // Lock-step SearchKNNBatch over several frontends ("lanes"): query i is searched by lane i % L; results are those of
 // each lane's own SearchKNNBatch over its queries, the per-step fetches of all lanes share one device call.
 int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float *queryVectors, int64_t nq, int64_t k, int64_t maxStep,

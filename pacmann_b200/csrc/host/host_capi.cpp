@@ -1,5 +1,6 @@
 // Flat C handles over the C++ host mirror (pianopir:: / graphann::) so the Python tests and benchmarks
 // can drive it through ctypes.  Not part of the drop-in boundary (that is include/pacmann_cuda.h).
+#include <algorithm>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -280,6 +281,33 @@ PMH int pmh_search_knn_lockstep(void **handles, int64_t n_lanes, const float *qu
     if (rc != 0) return rc;
     memcpy(ret, r.data(), r.size() * 8);
     memcpy(step_ret, s.data(), s.size() * 8);
+    return 0;
+    PMH_CATCH(-100)
+}
+// robustPrune for a batch of vertices: candidates = [n][k] (every vertex k candidates), out = [n][m] padded with -1,
+// out_len[n].  vectors are uploaded for the call (rows of dim fp32; dim must be even).
+PMH int pmh_robust_prune_batch(const float *vectors, int64_t n_vectors, int64_t dim, const int64_t *us, int64_t n, const int64_t *candidates,
+                               int64_t k, int64_t m, float alpha, int device, int64_t *out, int64_t *out_len) {
+    PMH_TRY
+    if (dim & 1) throw std::runtime_error("pmh_robust_prune_batch: dim must be even");
+    pm_db *db = nullptr;
+    if (pm_db_create((const uint64_t *)vectors, (uint64_t)n_vectors, (uint64_t)(dim / 2), device, &db) != PM_OK)
+        throw std::runtime_error(std::string("pm_db_create: ") + pm_last_error());
+    std::vector<int64_t> u(us, us + n);
+    std::vector<std::vector<int64_t>> cand((size_t)n), res;
+    for (int64_t i = 0; i < n; i++) cand[(size_t)i].assign(candidates + i * k, candidates + (i + 1) * k);
+    try {
+        graphann::RobustPruneBatch(db, dim, u, cand, m, alpha, &res);
+    } catch (...) {
+        pm_db_destroy(db);
+        throw;
+    }
+    pm_db_destroy(db);
+    const int64_t w = std::max<int64_t>(m, 1);
+    for (int64_t i = 0; i < n; i++) {
+        out_len[i] = (int64_t)res[(size_t)i].size();
+        for (int64_t j = 0; j < w; j++) out[i * w + j] = j < out_len[i] ? res[(size_t)i][(size_t)j] : -1;
+    }
     return 0;
     PMH_CATCH(-100)
 }

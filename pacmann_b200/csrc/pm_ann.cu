@@ -88,6 +88,25 @@ __global__ void __launch_bounds__(L2_THREADS) l2_pairs_kernel(const float *a, ui
     }
 }
 
+// out[p] = L2Dist(vector of row ids_a[p], vector of row ids_b[p]) over the resident table: the distance matrices of
+// graph construction (robustPrune, build_graph.go:169-236: u -> candidates and candidate x candidate)
+template <bool ALIGNED16>
+__global__ void __launch_bounds__(L2_THREADS) l2_idpairs_kernel(const uint64_t *db, uint64_t n_rows, uint64_t entry_u64, uint32_t dim,
+                                                                const int64_t *ids_a, const int64_t *ids_b, uint64_t n, float *out) {
+    const int half = threadIdx.x & 1;
+    const uint64_t stride = (uint64_t)gridDim.x * (L2_THREADS / 2);
+    const uint64_t n_up = (n + 15) & ~15ull;  // keep whole warps in the shuffle
+    for (uint64_t i = (uint64_t)blockIdx.x * (L2_THREADS / 2) + (threadIdx.x >> 1); i < n_up; i += stride) {
+        const bool in = i < n;
+        const int64_t a = in ? ids_a[i] : -1, b = in ? ids_b[i] : -1;
+        const bool ok = in && a >= 0 && b >= 0 && (uint64_t)a < n_rows && (uint64_t)b < n_rows;
+        const float *ra = reinterpret_cast<const float *>(db + (ok ? (uint64_t)a : 0) * entry_u64);
+        const float *rb = reinterpret_cast<const float *>(db + (ok ? (uint64_t)b : 0) * entry_u64);
+        float d = l2_pair<ALIGNED16>(ra, rb, dim, half);
+        if (in && half == 0) out[i] = ok ? d : INFINITY;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // A11: uint32 wrapping inner-product scan (graphann/l2_distance_amd64.s:39-68, graphann_test.go:268-273)
 // Tiles of IP_ROWS consecutive rows are contiguous in memory: they are staged into shared memory with fully
@@ -297,6 +316,44 @@ PM_EXPORT int pm_l2_batch(pm_db *db, uint64_t dim, const float *queries, uint64_
     PM_CUDA(cudaMemcpyAsync(d_q, queries, qb, cudaMemcpyHostToDevice, db->stream));
     if ((rc = l2_batch_enqueue(db, dim, d_q, n_queries, d_ids, k, (float *)d_out, db->stream))) return rc;
     PM_CUDA(cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, db->stream));
+    PM_CUDA(cudaStreamSynchronize(db->stream));
+    return PM_OK;
+}
+
+static int l2_idpairs_enqueue(pm_db *db, uint64_t dim, const int64_t *ids_a, const int64_t *ids_b, uint64_t n, float *out, cudaStream_t st) {
+    if (n == 0) return PM_OK;
+    if (dim * 4 > db->entry_u64 * 8) return set_error(PM_ERR_ARG, "l2: dim %llu does not fit in a row", (unsigned long long)dim);
+    if (dim > 8192) return set_error(PM_ERR_UNSUPPORTED, "l2: dim too large");
+    uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (db->entry_u64 % 2 == 0)
+        l2_idpairs_kernel<true><<<(unsigned)blocks, L2_THREADS, 0, st>>>(db->d_rows, db->n_rows, db->entry_u64, (uint32_t)dim, ids_a, ids_b, n, out);
+    else
+        l2_idpairs_kernel<false><<<(unsigned)blocks, L2_THREADS, 0, st>>>(db->d_rows, db->n_rows, db->entry_u64, (uint32_t)dim, ids_a, ids_b, n, out);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    return PM_OK;
+}
+PM_EXPORT int pm_l2_idpairs_dev(pm_db *db, uint64_t dim, const int64_t *ids_a, const int64_t *ids_b, uint64_t n, float *out, void *stream) {
+    if (!db || (n && (!ids_a || !ids_b || !out))) return set_error(PM_ERR_ARG, "pm_l2_idpairs_dev: null pointer");
+    int rc = ensure_device(db->device);
+    if (rc) return rc;
+    return l2_idpairs_enqueue(db, dim, ids_a, ids_b, n, out, stream ? (cudaStream_t)stream : db->stream);
+}
+PM_EXPORT int pm_l2_idpairs(pm_db *db, uint64_t dim, const int64_t *ids_a, const int64_t *ids_b, uint64_t n, float *out) {
+    if (!db || (n && (!ids_a || !ids_b || !out))) return set_error(PM_ERR_ARG, "pm_l2_idpairs: null pointer");
+    if (n == 0) return PM_OK;
+    int rc = ensure_device(db->device);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    void *d_in = nullptr, *d_out = nullptr;
+    if ((rc = scratch(db, 1, 2 * n * 8, &d_in))) return rc;
+    if ((rc = scratch(db, 0, n * 4, &d_out))) return rc;
+    int64_t *d_a = (int64_t *)d_in, *d_b = d_a + n;
+    PM_CUDA(cudaMemcpyAsync(d_a, ids_a, n * 8, cudaMemcpyHostToDevice, db->stream));
+    PM_CUDA(cudaMemcpyAsync(d_b, ids_b, n * 8, cudaMemcpyHostToDevice, db->stream));
+    if ((rc = l2_idpairs_enqueue(db, dim, d_a, d_b, n, (float *)d_out, db->stream))) return rc;
+    PM_CUDA(cudaMemcpyAsync(out, d_out, n * 4, cudaMemcpyDeviceToHost, db->stream));
     PM_CUDA(cudaStreamSynchronize(db->stream));
     return PM_OK;
 }

@@ -126,3 +126,32 @@ def SearchKNNLockstep(lanes, queryVectors, k, maxStep, parallel, benchmarking=Fa
     if rc != 0:
         raise RuntimeError("GetVertexInfo failed")
     return ret, step
+
+
+def RobustPruneBatch(vectors, us, candidates, m, alpha, device=0):
+    """robustPrune (build_graph.go:169-236) for many vertices at once: candidates[i] are the candidates of vertex us[i]
+    (an [n][k] array; k <= m returns them unchanged as the reference does).  Every distance the reference evaluates --
+    u to candidate, candidate to candidate -- comes from one GPU launch; returns a list of neighbour-id arrays."""
+    v = np.ascontiguousarray(vectors, np.float32)
+    us = np.ascontiguousarray(us, np.int64).reshape(-1)
+    cand = np.ascontiguousarray(candidates, np.int64).reshape(us.size, -1)
+    k = cand.shape[1]
+    if k <= m:                     # the reference returns the candidates unchanged (build_graph.go:170-172)
+        return [cand[i].copy() for i in range(us.size)]
+    out = np.zeros((us.size, max(m, 1)), np.int64)
+    lens = np.zeros(us.size, np.int64)
+    _host.check(_host.lib().pmh_robust_prune_batch(_p(v), v.shape[0], v.shape[1], _p(us), us.size, _p(cand), k, m, float(alpha), device, _p(out), _p(lens)))
+    return [out[i, :lens[i]].copy() for i in range(us.size)]
+
+
+def EvaluateGraphQuality(vectors, graph, numQueries=100, seed=0):
+    """EvaluateGraphQuality (build_graph.go:776-817): search numQueries random dataset vertices (k 20, step 20, parallel 2,
+    non-private) and report (hit rate, average step at which a hit target was reached)."""
+    f = GraphANNFrontend(vectors, graph)
+    f.Preprocess()
+    n = f.n
+    targets = np.random.default_rng(seed).integers(0, n, numQueries)
+    ret, steps = f.SearchKNNBatch(f.vectors[targets], 20, 20, 2)
+    hit = ret[:, 0] == targets
+    avg = float(steps[hit, 0].mean()) if hit.any() else float("nan")
+    return float(hit.mean()), avg

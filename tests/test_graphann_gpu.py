@@ -127,3 +127,60 @@ def test_lockstep_client_group_matches_oracle(oracle, lanes, nq, steps):
     # a lane keeps working on its own afterwards (same pm_client, its own parts)
     solo_ret, _ = group[lanes - 1].SearchKNNBatch(queries[:2], 10, steps, 2)
     assert solo_ret.shape == (2, 10)
+
+
+def test_l2_idpairs_matches_oracle(oracle):
+    """pm_l2_idpairs: distances between rows of the resident table addressed by id pairs, bit-identical to L2Dist."""
+    from pacmann_b200 import cabi
+    rng = np.random.default_rng(171)
+    n, dim = 500, 40
+    vec = (rng.standard_normal((n, dim)) * 3).astype(np.float32)
+    db = cabi.DB(vec.view(np.uint64).reshape(n, dim // 2))
+    a, b = rng.integers(0, n, 777), rng.integers(0, n, 777)
+    a[5], b[9] = -1, n                                        # out of range -> +inf
+    got = cabi.l2_idpairs(db, dim, a, b)
+    for p in range(777):
+        if a[p] < 0 or b[p] >= n:
+            assert np.isinf(got[p])
+        else:
+            assert got[p].view(np.uint32) == oracle.l2dist(vec[a[p]], vec[b[p]]).view(np.uint32)
+    db.close()
+
+
+@pytest.mark.parametrize("integer", [False, True])
+def test_robust_prune_batch_matches_oracle(oracle, integer):
+    """robustPrune (build_graph.go:169-236) with all its L2Dist calls served by one launch.  Same
+    neighbour lists as the oracle restatement, vertex by vertex -- on integer (SIFT-shaped) data with many equal
+    distances too, where the stated tie rule (candidate order) matters."""
+    from pacmann_b200 import graphann
+    rng = np.random.default_rng(172)
+    n, dim, m, k = 3000, 32, 16, 40
+    vec, _ = make_dataset(n, dim, 8, 173, integer=integer)
+    if integer:
+        vec = np.floor(vec / 64).astype(np.float32)           # few distinct values: ties everywhere
+    us = rng.integers(0, n, 200)
+    cand = np.stack([rng.choice(n, k, replace=False) for _ in us])
+    cand[3, 7] = cand[3, 2]                                   # a duplicated candidate
+    for alpha in (1.0, 1.2):
+        got = graphann.RobustPruneBatch(vec, us, cand, m, alpha)
+        for i, u in enumerate(us):
+            want = oracle.robust_prune(vec, u, cand[i], m, alpha)
+            assert len(got[i]) == len(want) and (got[i] == want).all(), (i, alpha)
+    few = graphann.RobustPruneBatch(vec, us[:5], cand[:5, :m], m, 1.2)      # len(candidates) <= m: returned unchanged
+    assert all((few[i] == cand[i, :m]).all() for i in range(5))
+
+
+def test_evaluate_graph_quality(oracle):
+    """EvaluateGraphQuality (build_graph.go:776-817): random dataset vertices searched in their own graph."""
+    from pacmann_b200 import graphann
+    n, dim, m = 4000, 32, 16
+    vec, graph = make_dataset(n, dim, m, 174)
+    hit_rate, avg_steps = graphann.EvaluateGraphQuality(vec, graph, numQueries=50, seed=1)
+    targets = np.random.default_rng(1).integers(0, n, 50)
+    f_start = graphann.GraphANNFrontend(vec, graph)
+    f_start.Preprocess()
+    o_ret, o_step = oracle.search_knn_basic(vec, graph, f_start.StartVertexIds(), vec[targets], 20, 20, 2)
+    o_hit = o_ret[:, 0] == targets
+    assert abs(hit_rate - o_hit.mean()) < 1e-12
+    if o_hit.any():
+        assert abs(avg_steps - o_step[o_hit, 0].mean()) < 1e-9

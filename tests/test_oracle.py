@@ -220,3 +220,22 @@ def test_search_knn_oracle_finds_neighbours(oracle):
     exact = np.argmin(((vec[None, :, :] - queries[:, None, :]) ** 2).sum(-1), axis=1)
     assert (ret[:, 0] == exact).mean() > 0.5          # the chain graph is navigable; sanity only
     assert ((ret >= -1) & (ret < n)).all() and (step >= -1).all()
+
+
+def test_robust_prune_restatement_properties(oracle):
+    """orc_robust_prune follows build_graph.go:169-236: <= m candidates come back unchanged; otherwise the nearest
+    candidate is always kept, every kept id is a candidate, exactly m come back (discarded ones refill), and with
+    alpha large enough nothing is pruned, so the m nearest come back in distance order."""
+    rng = np.random.default_rng(301)
+    n, dim, m = 400, 16, 8
+    vec = rng.standard_normal((n, dim)).astype(np.float32)
+    for u in range(20):
+        cand = rng.choice(n, 30, replace=False)
+        cand = cand[cand != u]
+        assert (oracle.robust_prune(vec, u, cand[:m], m, 1.2) == cand[:m]).all()
+        got = oracle.robust_prune(vec, u, cand, m, 1.2)
+        d = np.array([oracle.l2dist(vec[u], vec[c]) for c in cand])
+        assert len(got) == m and set(got.tolist()) <= set(cand.tolist())
+        assert got[0] == cand[np.argmin(d)]
+        loose = oracle.robust_prune(vec, u, cand, m, 1e9)
+        assert (loose == cand[np.argsort(d, kind="stable")[:m]]).all()
