@@ -16,6 +16,7 @@
  *   pm_client_*        PianoPIRClient.{Initialization,    pianopir/pir.go:203-255, 267-352, 354-471
  *                      Preprocessing,Query} resident form
  *   pm_l2_pairs/_batch L2Dist / L2DistanceSIMD            graphann/build_graph.go:119-134, l2_distance_amd64.s:4-36
+ *   pm_l2_idpairs      the L2Dist calls of robustPrune     graphann/build_graph.go:169-236
  *   pm_ip_u32_scan     InnerProduct + scan loop           graphann/l2_distance_amd64.s:39-68, graphann_test.go:268-273
  *
  * Conventions
