@@ -108,3 +108,43 @@ func (d *DB) IPScan(dim uint64, queries []uint32, nq uint64, checksum []uint32) 
 	must(C.pm_ip_u32_scan(d.h, C.uint64_t(dim), (*C.uint32_t)(unsafe.Pointer(&queries[0])), C.uint64_t(nq),
 		(*C.uint32_t)(unsafe.Pointer(&checksum[0])), nil), "pm_ip_u32_scan")
 }
+
+// L2IDPairs: out[p] = L2Dist(vector of row a[p], vector of row b[p]) over the resident table -- every L2Dist call of
+// robustPrune (graphann/build_graph.go:169-236) for a batch of vertices in one launch.
+func (d *DB) L2IDPairs(dim uint64, a, b []int64, out []float32) {
+	must(C.pm_l2_idpairs(d.h, C.uint64_t(dim), (*C.int64_t)(unsafe.Pointer(&a[0])), (*C.int64_t)(unsafe.Pointer(&b[0])),
+		C.uint64_t(len(a)), (*C.float)(unsafe.Pointer(&out[0]))), "pm_l2_idpairs")
+}
+
+// Client is the GPU-resident form of the PianoPIR client(s) of one SimpleBatchPianoPIR -- or of several of them
+// (lanes x PartitionNum parts) when many users are served in lock step (INTEGRATION.md, steps 7 and 8).
+type Client struct{ h *C.pm_client }
+
+type ClientPart = C.pm_client_part
+type ClientQuery = C.pm_client_query
+
+func (d *DB) NewClient(parts []ClientPart) *Client {
+	var h *C.pm_client
+	must(C.pm_client_create(d.h, &parts[0], C.uint64_t(len(parts)), &h), "pm_client_create")
+	return &Client{h}
+}
+func (c *Client) Close() { C.pm_client_destroy(c.h); c.h = nil }
+
+// Preprocess = Initialization + Preprocessing of the listed parts on the device (pir.go:203-255, 267-352).
+func (c *Client) Preprocess(partIDs []uint32, longKeys []uint32, replSeeds []uint64, skipPrep bool) {
+	sp := C.int(0)
+	if skipPrep {
+		sp = 1
+	}
+	must(C.pm_client_preprocess(c.h, (*C.uint32_t)(unsafe.Pointer(&partIDs[0])), C.uint64_t(len(partIDs)),
+		(*C.uint32_t)(unsafe.Pointer(&longKeys[0])), (*C.uint64_t)(unsafe.Pointer(&replSeeds[0])), sp), "pm_client_preprocess")
+}
+
+// QueryBatchL2M answers the sub-queries of one search step of all lanes: entries, status codes and the distance of
+// every answered vector to its own lane's query vector (queryVecs[vecID[i]]).
+func (c *Client) QueryBatchL2M(q []ClientQuery, out []uint64, status []int32, queryVecs []float32, nVecs uint64, vecID []uint32,
+	dim uint64, dist []float32) {
+	must(C.pm_client_query_batch_l2m(c.h, &q[0], C.uint64_t(len(q)), (*C.uint64_t)(unsafe.Pointer(&out[0])),
+		(*C.int32_t)(unsafe.Pointer(&status[0])), (*C.float)(unsafe.Pointer(&queryVecs[0])), C.uint64_t(nVecs),
+		(*C.uint32_t)(unsafe.Pointer(&vecID[0])), C.uint64_t(dim), (*C.float)(unsafe.Pointer(&dist[0]))), "pm_client_query_batch_l2m")
+}
