@@ -468,6 +468,11 @@ def private_search(args, rank, world, local_rank, dist, dev):
     queries = qall[rank * nq:(rank + 1) * nq]
     seed = SEED + 2
     lanes, ngroups = max(0, args.search_lanes), max(1, args.search_groups)
+    # host threads: the ranks of a node share its cores; a lock-step group = one driver thread + an OpenMP team for the
+    # per-lane host work.  Oversubscribing the cores with spinning teams is ruinous, so both are sized to the share.
+    cores_per_rank = max(1, (os.cpu_count() or 1) // max(1, world))
+    ngroups = max(1, min(ngroups, cores_per_rank))
+    os.environ["PM_HOST_THREADS"] = str(max(1, min(8, cores_per_rank // ngroups)))
     f = graphann.GraphANNFrontend(vec, graph, private=True, seed=seed, device=local_rank, group_lanes=max(1, lanes))
     t0 = time.perf_counter()
     f.Preprocess()
@@ -581,6 +586,7 @@ def private_search(args, rank, world, local_rank, dist, dev):
         out["lockstep"] = {"clients_per_gpu": ngroups * lanes, "groups_per_gpu": ngroups, "lanes_per_group": lanes, "queries": nlq * world,
                            "queries_per_s": nlq * world / float(tl[0]), "ms_per_step_per_group": ldt / (per * step) * 1e3,
                            "gpu_launches": int(cabi.launch_count() - l1), "group_setup_s": gsetup,
+                           "host_threads_per_group": int(os.environ["PM_HOST_THREADS"]), "host_cores_per_rank": cores_per_rank,
                            "note": "every client keeps its own keys, hint tables, cache and search state; results identical to each client searching alone"}
         del groups
     if rank == 0 and not args.no_cpu_baseline:

@@ -621,7 +621,7 @@ int HostThreads() {
     static const int n = [] {
         const char *v = getenv("PM_HOST_THREADS");
         int t = v && *v ? atoi(v) : 0;
-        if (t <= 0) t = std::min(8, std::max(1, omp_get_num_procs()));
+        if (t <= 0) t = std::min(8, std::max(1, omp_get_max_threads()));   // follows OMP_NUM_THREADS (torchrun sets it to 1 per rank)
         return t;
     }();
     return n;

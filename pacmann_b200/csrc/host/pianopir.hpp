@@ -80,8 +80,10 @@ struct PendingQuery {
     std::vector<uint32_t> offsets;  // what goes to the server (Dummy, Real)
 };
 
-// Threads a lock-step group uses for its per-lane host work (OpenMP team size): PM_HOST_THREADS, default min(8, cores).
-// Several groups (and several ranks) run side by side, so a team must not grab the whole machine.
+// Threads a lock-step group uses for its per-lane host work (OpenMP team size): PM_HOST_THREADS, default
+// min(8, omp_get_max_threads()).  Several groups (and several ranks) run side by side, so a team must not grab the whole
+// machine: oversubscribed spin-waiting OpenMP teams cost two orders of magnitude (measured: 8 ranks x 4 groups x 8
+// threads on 32 cores = 230 ms per step instead of 1 ms).
 int HostThreads();
 
 // localCache (pir.go:127, :381-383, :468): idx -> entry.  Entries live in fixed-size slabs (stable addresses, reused after
