@@ -267,7 +267,7 @@ void GraphANNFrontend::StartDistances(const float *queryVector, int64_t dim, int
 
 // ---- SearchKNN (search.go:114-234) as a resumable state: Begin, then NextBatch / Consume once per step, then Finish ----
 void SearchState::addKnown(const Vertex &v, float dist, int64_t step) {
-    slotOf[v.Id] = (int32_t)knownId.size();
+    slotOf.put((uint64_t)v.Id, knownId.size());
     knownId.push_back(v.Id);
     knownDist.push_back(dist);
     knownStep.push_back(step);
@@ -283,8 +283,7 @@ void SearchState::Begin(GraphANNFrontend *front, const float *q, int64_t k_, int
     // knownVertices / reachStep (search.go:117-118) as a slot table: the reference keeps whole Vertex objects in maps, but
     // only ids, neighbour lists, reach steps and distances are read back.  A vertex's distance is evaluated once, when it
     // becomes known, and reused by the final ranking (search.go:212-218 recomputes L2Dist on the same vector: same bits).
-    slotOf.clear();
-    slotOf.reserve((size_t)(maxStep * parallel * m * 2 + 64));
+    slotOf.reset((size_t)(maxStep * parallel * m + 64));
     knownId.clear(); knownStep.clear(); nbrPool.clear(); knownDist.clear();
     toBeExplored.a.clear();
     rseed = Mix64(f->randSeed, f->queryCounter++);
@@ -297,7 +296,7 @@ void SearchState::Begin(GraphANNFrontend *front, const float *q, int64_t k_, int
         std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dists[a] < dists[b]; });
         for (size_t i = 0; (int64_t)toBeExplored.Len() < parallel && i < order.size(); i++) {
             const Vertex &v = f->StartVertices[order[i]];
-            if (slotOf.count(v.Id)) continue;
+            if (slotOf.has((uint64_t)v.Id)) continue;
             addKnown(v, dists[order[i]], 0);
             toBeExplored.Push({dists[order[i]], v.Id});
         }
@@ -313,7 +312,7 @@ bool SearchState::NextBatch(std::vector<int64_t> *batchQ) {
             for (int64_t i = 0; i < m; i++) batchQ->push_back((int64_t)(Mix64(rseed, rctr++) % (uint64_t)n));
         } else {
             VD item = toBeExplored.Pop();
-            const int64_t *nb = &nbrPool[(size_t)slotOf[item.id] * (size_t)m];
+            const int64_t *nb = &nbrPool[(size_t)*slotOf.find((uint64_t)item.id) * (size_t)m];
             batchQ->insert(batchQ->end(), nb, nb + m);
         }
     }
@@ -357,7 +356,7 @@ void SearchState::collect(const A &res, const std::vector<float> &srcDists) {
     // newly discovered vertices of this step, in batch order (a repeated id is "already known" by its second occurrence)
     for (size_t i = 0; i < res.size(); i++) {
         const int64_t id = res.id(i);
-        if (slotOf.count(id)) continue;
+        if (slotOf.has((uint64_t)id)) continue;
         bool dup = false;
         for (size_t t : fresh) dup = dup || res.id(t) == id;
         if (dup) continue;
@@ -383,7 +382,7 @@ void SearchState::apply(const A &res, const float *missingDists) {
     for (size_t t = 0; t < fresh.size(); t++) {
         const size_t i = fresh[t];
         const int64_t id = res.id(i);
-        slotOf[id] = (int32_t)knownId.size();
+        slotOf.put((uint64_t)id, knownId.size());
         knownId.push_back(id);
         knownDist.push_back(dists[t]);
         knownStep.push_back(thisStep);
@@ -420,7 +419,7 @@ void SearchState::Finish(int64_t *ret, int64_t *stepRet) {
     for (int64_t i = 0; i < k; i++) { ret[i] = -1; stepRet[i] = -1; }
     for (int64_t i = 0; i < k && i < (int64_t)all.size(); i++) {
         ret[i] = all[i].id;
-        stepRet[i] = knownStep[(size_t)slotOf[all[i].id]];
+        stepRet[i] = knownStep[(size_t)*slotOf.find((uint64_t)all[i].id)];
     }
 }
 

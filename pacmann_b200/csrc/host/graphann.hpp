@@ -127,7 +127,7 @@ private:
     int64_t k = 0, maxStep = 0, parallel = 0, n = 0, dim = 0, m = 0, step = 0;
     bool benchmarking = false;
     int device = 0;
-    std::unordered_map<int64_t, int32_t> slotOf;
+    pianopir::FlatMap slotOf;   // vertex id -> slot in knownId / knownDist / knownStep / nbrPool
     std::vector<int64_t> knownId, knownStep, nbrPool;
     std::vector<float> knownDist, dists;
     ExploreQueue toBeExplored;

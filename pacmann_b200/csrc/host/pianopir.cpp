@@ -629,16 +629,17 @@ int HostThreads() {
 
 void EntryCache::Reserve(uint64_t entries) {
     while (slabs.size() * kPerSlab < entries) slabs.emplace_back(new uint64_t[kPerSlab * E]());   // value-initialised: pages touched now
+    reserved = std::max(reserved, entries);
+    if (slot.size() == 0) slot.reset(reserved);
 }
 const uint64_t *EntryCache::put(uint64_t idx, const uint64_t *entry) {
-    auto it = slot.find(idx);
     uint64_t s;
-    if (it != slot.end()) {
-        s = it->second;
+    if (const uint64_t *have = slot.find(idx)) {
+        s = *have;
     } else {
         s = used++;
         if (s / kPerSlab >= slabs.size()) slabs.emplace_back(new uint64_t[kPerSlab * E]);
-        slot.emplace(idx, s);
+        slot.put(idx, s);
     }
     uint64_t *dst = slabs[s / kPerSlab].get() + (s % kPerSlab) * E;
     memcpy(dst, entry, E * 8);
@@ -749,8 +750,8 @@ void SimpleBatchPianoPIR::beginCall(const uint64_t *idx, size_t n, bool *bad) {
     }
     const uint64_t queryNumToMake = n / PN;
     for (auto &l : wsLists) while (l.size() < queryNumToMake) l.push_back(DefaultValue);
-    wsResponses.clear();
-    wsResponses.reserve(n * 2);
+    wsResponses.reset(n);
+    wsRespList.clear();
     wsPend.clear();
     wsQueries.clear();
     wsZero.assign(E, 0);
@@ -790,7 +791,8 @@ void SimpleBatchPianoPIR::settle(size_t pbase, const uint64_t *res, const int32_
         if (pd.kind == 0) { serverQueries += 1; continue; }
         if (pd.kind == 2) {  // served from the local cache (pir.go:381-383); an earlier failure of the same index repeats as zeros
             const uint64_t *e = c.localCache.find(pd.local);
-            wsResponses[pd.global] = Resp{e ? e : wsZero.data(), kNaN};
+            wsResponses.put(pd.global, wsRespList.size());
+            wsRespList.push_back(Resp{e ? e : wsZero.data(), kNaN});
             continue;
         }
         const uint64_t *r = res + (size_t)pd.qpos * E;
@@ -801,7 +803,8 @@ void SimpleBatchPianoPIR::settle(size_t pbase, const uint64_t *res, const int32_
         }
         for (size_t k = 0; k < c.pendingCached.size(); k++)
             if (c.pendingCached[k] == pd.local) { c.pendingCached.erase(c.pendingCached.begin() + (long)k); break; }
-        wsResponses[pd.global] = Resp{r, dist ? dist[pd.qpos] : kNaN};
+        wsResponses.put(pd.global, wsRespList.size());
+        wsRespList.push_back(Resp{r, dist ? dist[pd.qpos] : kNaN});
     }
     std::fill(wsPendingReal.begin(), wsPendingReal.end(), 0);
 }
@@ -811,12 +814,13 @@ bool SimpleBatchPianoPIR::finishCall(const uint64_t *idx, size_t n, uint64_t *ou
     const uint64_t E = config.DBEntrySize;
     const float kNaN = std::nanf("");
     for (size_t i = 0; i < n; i++) {
-        auto it = wsResponses.find(idx[i]);
-        const bool have = it != wsResponses.end();
-        if (out_ptrs) out_ptrs[i] = have ? it->second.entry : wsZero.data();
-        else if (have) memcpy(out + i * E, it->second.entry, E * 8);
+        const uint64_t *pos = wsResponses.find(idx[i]);
+        const bool have = pos != nullptr;
+        const Resp *r = have ? &wsRespList[*pos] : nullptr;
+        if (out_ptrs) out_ptrs[i] = have ? r->entry : wsZero.data();
+        else if (have) memcpy(out + i * E, r->entry, E * 8);
         else memset(out + i * E, 0, E * 8);
-        if (dists) dists[i] = have ? it->second.dist : kNaN;
+        if (dists) dists[i] = have ? r->dist : kNaN;
     }
     if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) return true;
     FinishedBatchNum += n / config.BatchSize;

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../../include/pacmann_cuda.h"
+#include "flatmap.hpp"
 
 namespace pianopir {
 
@@ -94,11 +95,11 @@ class EntryCache {
 public:
     void Init(uint64_t entryWords) { E = entryWords; clear(); }
     void Reserve(uint64_t entries);
-    void clear() { slot.clear(); used = 0; }
-    bool has(uint64_t idx) const { return slot.find(idx) != slot.end(); }
+    void clear() { slot.reset(reserved); used = 0; }
+    bool has(uint64_t idx) const { return slot.has(idx); }
     const uint64_t *find(uint64_t idx) const {
-        auto it = slot.find(idx);
-        return it == slot.end() ? nullptr : at(it->second);
+        const uint64_t *s = slot.find(idx);
+        return s ? at(*s) : nullptr;
     }
     const uint64_t *put(uint64_t idx, const uint64_t *entry);
     size_t size() const { return slot.size(); }
@@ -106,9 +107,9 @@ public:
 private:
     static constexpr uint64_t kPerSlab = 512;
     const uint64_t *at(uint64_t s) const { return slabs[s / kPerSlab].get() + (s % kPerSlab) * E; }
-    uint64_t E = 0, used = 0;
+    uint64_t E = 0, used = 0, reserved = 0;
     std::vector<std::unique_ptr<uint64_t[]>> slabs;
-    std::unordered_map<uint64_t, uint64_t> slot;
+    FlatMap slot;
 };
 
 class PianoPIRClient {  // pir.go:91-471
@@ -228,7 +229,8 @@ private:
     std::vector<int32_t> wsStatus;
     std::vector<float> wsDist;
     struct Resp { const uint64_t *entry; float dist; };
-    std::unordered_map<uint64_t, Resp> wsResponses;
+    FlatMap wsResponses;           // global index -> position in wsRespList
+    std::vector<Resp> wsRespList;
     std::vector<uint64_t> wsPendingReal;
     // the three pieces of QueryFlat, shared with QueryFlatGroup
     void beginCall(const uint64_t *idx, size_t n, bool *bad);
