@@ -206,6 +206,7 @@ void GraphANNFrontend::Preprocess() {
 }
 // keep the start vertices' vectors resident on the GPU: rows of dim fp32 viewed as dim/2 uint64 (needs an even dim)
 void GraphANNFrontend::UploadStartVertices() {
+    startVersion++;
     if (startDb) { pm_db_destroy(startDb); startDb = nullptr; }
     int64_t n, dim, m;
     Graph->GetMetadata(&n, &dim, &m);
@@ -218,6 +219,39 @@ void GraphANNFrontend::UploadStartVertices() {
 }
 GraphANNFrontend::~GraphANNFrontend() {
     if (startDb) pm_db_destroy(startDb);
+    if (groupStartDb) pm_db_destroy(groupStartDb);
+}
+
+// Lock-step groups: the start vertices of all lanes in ONE resident table (lane l = rows [l*kmax, ...)), so that the
+// start distances of a round of queries are one pm_l2_batch.  Owned by the group's first frontend; rebuilt when a lane's
+// start vertices change.  Returns [act][stride] distances (lane l's first StartVertices.size() entries), or nullptr
+// when the lanes cannot be grouped (odd dimension, no start vertices).
+const float *GraphANNFrontend::GroupStartDistances(const std::vector<GraphANNFrontend *> &lanes, const float *queries, int64_t act, int64_t dim,
+                                                   size_t *stride) {
+    if (dim & 1) return nullptr;
+    uint64_t stamp = lanes.size();
+    size_t kmax = 0;
+    for (auto *f : lanes) {
+        stamp = Mix64(stamp, (uint64_t)(uintptr_t)f ^ f->startVersion);
+        kmax = std::max(kmax, f->StartVertices.size());
+    }
+    if (kmax == 0) return nullptr;
+    if (!groupStartDb || groupStamp != stamp) {
+        if (groupStartDb) { pm_db_destroy(groupStartDb); groupStartDb = nullptr; }
+        std::vector<uint64_t> rows(lanes.size() * kmax * (size_t)(dim / 2), 0);
+        groupIds.assign(lanes.size() * kmax, -1);
+        for (size_t l = 0; l < lanes.size(); l++)
+            for (size_t i = 0; i < lanes[l]->StartVertices.size(); i++) {
+                memcpy(&rows[(l * kmax + i) * (size_t)(dim / 2)], lanes[l]->StartVertices[i].Vector.data(), (size_t)dim * 4);
+                groupIds[l * kmax + i] = (int64_t)(l * kmax + i);
+            }
+        check(pm_db_create(rows.data(), lanes.size() * kmax, (uint64_t)(dim / 2), Graph->Device(), &groupStartDb), "pm_db_create(group start vertices)");
+        groupStamp = stamp;
+    }
+    groupDists.resize((size_t)act * kmax);
+    check(pm_l2_batch(groupStartDb, (uint64_t)dim, queries, (uint64_t)act, groupIds.data(), kmax, groupDists.data()), "pm_l2_batch");
+    *stride = kmax;
+    return groupDists.data();
 }
 
 // container/heap's up/down/Push/Pop with Less = dist < dist (search.go:92-111)
@@ -274,7 +308,8 @@ void SearchState::addKnown(const Vertex &v, float dist, int64_t step) {
     nbrPool.insert(nbrPool.end(), v.Neighbors.begin(), v.Neighbors.end());
 }
 
-void SearchState::Begin(GraphANNFrontend *front, const float *q, int64_t k_, int64_t maxStep_, int64_t parallel_, bool benchmarking_) {
+void SearchState::Begin(GraphANNFrontend *front, const float *q, int64_t k_, int64_t maxStep_, int64_t parallel_, bool benchmarking_,
+                        const float *startDists) {
     f = front;
     queryVector = q;
     k = k_; maxStep = maxStep_; parallel = parallel_; benchmarking = benchmarking_;
@@ -290,11 +325,22 @@ void SearchState::Begin(GraphANNFrontend *front, const float *q, int64_t k_, int
     rctr = 0;
     step = 0;
     if (!benchmarking) {  // search.go:129-148
-        f->StartDistances(queryVector, dim, device, &dists);
-        std::vector<size_t> order(f->StartVertices.size());
+        if (startDists) dists.assign(startDists, startDists + f->StartVertices.size());
+        else f->StartDistances(queryVector, dim, device, &dists);
+        // The reference sorts all start vertices by distance (stable here) and takes the first `parallel` distinct ones
+        // (search.go:135-148).  Only that prefix is read, so a partial sort under the same total order (distance, then
+        // input position) gives the same vertices; the full sort only runs if duplicates exhaust the prefix.
+        std::vector<size_t> &order = startOrder;
+        order.resize(f->StartVertices.size());
         for (size_t i = 0; i < order.size(); i++) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return dists[a] < dists[b]; });
+        auto before = [&](size_t a, size_t b) { return dists[a] < dists[b] || (dists[a] == dists[b] && a < b); };
+        size_t sorted = std::min(order.size(), (size_t)parallel * 4 + 8);
+        std::partial_sort(order.begin(), order.begin() + (long)sorted, order.end(), before);
         for (size_t i = 0; (int64_t)toBeExplored.Len() < parallel && i < order.size(); i++) {
+            if (i == sorted) {   // more duplicates than the sorted prefix: finish the sort
+                std::sort(order.begin() + (long)sorted, order.end(), before);
+                sorted = order.size();
+            }
             const Vertex &v = f->StartVertices[order[i]];
             if (slotOf.has((uint64_t)v.Id)) continue;
             addKnown(v, dists[order[i]], 0);
@@ -488,11 +534,16 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
         const int64_t act = std::min(L, nq - base);
         std::string err;
         auto t0 = now();
+        // start-vertex distances of all lanes in one launch (search.go:131-134 per lane)
+        const float *groupDists = nullptr;
+        size_t groupStride = 0;
+        if (!benchmarking) groupDists = lanes[0]->GroupStartDistances(lanes, queryVectors + base * dim, act, dim, &groupStride);
 #pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (act > 2)
         for (int64_t l = 0; l < act; l++) {
             try {
                 qptr[(size_t)l] = queryVectors + (base + l) * dim;
-                lanes[(size_t)l]->wsState.Begin(lanes[(size_t)l], qptr[(size_t)l], k, maxStep, parallel, benchmarking);
+                lanes[(size_t)l]->wsState.Begin(lanes[(size_t)l], qptr[(size_t)l], k, maxStep, parallel, benchmarking,
+                                                groupDists ? groupDists + (size_t)l * groupStride : nullptr);
             } catch (const std::exception &e) {
 #pragma omp critical
                 err = e.what();

@@ -106,7 +106,10 @@ class GraphANNFrontend;
 // SearchKNN drives it alone, SearchKNNLockstep drives one per lane with a shared fetch.
 class SearchState {
 public:
-    void Begin(GraphANNFrontend *front, const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking);
+    // startDists: distances of the frontend's start vertices to the query if the caller already has them (lock-step
+    // driver: one launch for all lanes), else nullptr
+    void Begin(GraphANNFrontend *front, const float *queryVector, int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking,
+               const float *startDists = nullptr);
     bool NextBatch(std::vector<int64_t> *batchQ);
     void Consume(const std::vector<Vertex> &queryResults, const std::vector<float> &srcDists);
     // Consume in parts: CollectFresh, then L2Dist(MissingVectors()[j], query) for every j, then ApplyFresh
@@ -132,7 +135,7 @@ private:
     std::vector<float> knownDist, dists;
     ExploreQueue toBeExplored;
     uint64_t rseed = 0, rctr = 0;
-    std::vector<size_t> fresh, missing;
+    std::vector<size_t> fresh, missing, startOrder;
     std::vector<const float *> ptrs;
 };
 
@@ -155,10 +158,16 @@ public:
 
     void StartDistances(const float *queryVector, int64_t dim, int device, std::vector<float> *out);
     SearchState wsState;                 // the search in progress (one at a time per frontend)
+    const float *GroupStartDistances(const std::vector<GraphANNFrontend *> &lanes, const float *queries, int64_t act, int64_t dim, size_t *stride);
+    uint64_t startVersion = 0;           // bumped whenever the start vertices are (re)uploaded
 
 private:
     std::vector<int64_t> wsBatch;
     pm_db *startDb = nullptr;            // start vertices' vectors, resident on the GPU
+    pm_db *groupStartDb = nullptr;       // first frontend of a lock-step group: the start vertices of all lanes
+    uint64_t groupStamp = 0;
+    std::vector<int64_t> groupIds;
+    std::vector<float> groupDists;
     std::vector<int64_t> startIds;       // 0..n_start-1
     std::vector<Vertex> wsResults;       // per-step scratch reused across steps and searches
     std::vector<float> wsSrcDists;
