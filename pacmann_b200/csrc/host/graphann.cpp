@@ -151,8 +151,7 @@ int PIRGraphInfo::FetchGroupRaw(const std::vector<PIRGraphInfo *> &infos, const 
         calls[l] = {g->PIR, g->wsIdx.data(), cnt, nullptr, queries[l], queries[l] ? dists[l]->data() : nullptr, 0, entries[l]->data()};
     }
     if (pianopir::SimpleBatchPianoPIR::QueryFlatGroup(calls, (uint64_t)infos[0]->Dim) != 0) return -1;
-#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (L > 2)
-    for (size_t l = 0; l < L; l++) {   // the reference's correctness accounting (private-search.go:480-504)
+    pianopir::WorkerPool::Local().ParallelFor(L, [&](size_t l) {   // the reference's correctness accounting (private-search.go:480-504)
         PIRGraphInfo *g = infos[l];
         for (size_t i = 0; i < ids[l]->size(); i++) {
             const uint32_t *nb = (const uint32_t *)((const uint8_t *)(*entries[l])[i] + g->Dim * 4);
@@ -162,7 +161,7 @@ int PIRGraphInfo::FetchGroupRaw(const std::vector<PIRGraphInfo *> &infos, const 
                 if (nb[j] != (uint32_t)want[j]) { correctQ = false; break; }
             if (correctQ) g->succQueryNum++;
         }
-    }
+    });
     return 0;
 }
 
@@ -532,24 +531,16 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
     auto since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     for (int64_t base = 0; base < nq; base += L) {
         const int64_t act = std::min(L, nq - base);
-        std::string err;
         auto t0 = now();
         // start-vertex distances of all lanes in one launch (search.go:131-134 per lane)
         const float *groupDists = nullptr;
         size_t groupStride = 0;
         if (!benchmarking) groupDists = lanes[0]->GroupStartDistances(lanes, queryVectors + base * dim, act, dim, &groupStride);
-#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (act > 2)
-        for (int64_t l = 0; l < act; l++) {
-            try {
-                qptr[(size_t)l] = queryVectors + (base + l) * dim;
-                lanes[(size_t)l]->wsState.Begin(lanes[(size_t)l], qptr[(size_t)l], k, maxStep, parallel, benchmarking,
-                                                groupDists ? groupDists + (size_t)l * groupStride : nullptr);
-            } catch (const std::exception &e) {
-#pragma omp critical
-                err = e.what();
-            }
-        }
-        if (!err.empty()) throw std::runtime_error(err);
+        pianopir::WorkerPool &pool = pianopir::WorkerPool::Local();
+        pool.ParallelFor((size_t)act, [&](size_t l) {
+            qptr[l] = queryVectors + (base + (int64_t)l) * dim;
+            lanes[l]->wsState.Begin(lanes[l], qptr[l], k, maxStep, parallel, benchmarking, groupDists ? groupDists + l * groupStride : nullptr);
+        });
         tBegin += since(t0);
         for (;;) {
             t0 = now();
@@ -582,12 +573,11 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
             }
             tFetch += since(t0);
             t0 = now();
-#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (act > 2)
-            for (int64_t l = 0; l < act; l++)
-                if (more[(size_t)l]) {
-                    if (groupable) lanes[(size_t)l]->wsState.CollectFreshRaw(batch[(size_t)l], rawEntries[(size_t)l], srcDists[(size_t)l]);
-                    else lanes[(size_t)l]->wsState.CollectFresh(results[(size_t)l], srcDists[(size_t)l]);
-                }
+            pool.ParallelFor((size_t)act, [&](size_t l) {
+                if (!more[l]) return;
+                if (groupable) lanes[l]->wsState.CollectFreshRaw(batch[l], rawEntries[l], srcDists[l]);
+                else lanes[l]->wsState.CollectFresh(results[l], srcDists[l]);
+            });
             tCollect += since(t0);
             t0 = now();
             // distances the fetch did not provide (entries served from a lane's local cache): one launch for all lanes
@@ -613,12 +603,11 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
             tMiss += since(t0);
             nMissTotal += nMissing;
             t0 = now();
-#pragma omp parallel for schedule(static) num_threads(pianopir::HostThreads()) if (act > 2)
-            for (int64_t l = 0; l < act; l++)
-                if (more[(size_t)l]) {
-                    if (groupable) lanes[(size_t)l]->wsState.ApplyFreshRaw(batch[(size_t)l], rawEntries[(size_t)l], missDist.data() + missBase[(size_t)l]);
-                    else lanes[(size_t)l]->wsState.ApplyFresh(results[(size_t)l], missDist.data() + missBase[(size_t)l]);
-                }
+            pool.ParallelFor((size_t)act, [&](size_t l) {
+                if (!more[l]) return;
+                if (groupable) lanes[l]->wsState.ApplyFreshRaw(batch[l], rawEntries[l], missDist.data() + missBase[l]);
+                else lanes[l]->wsState.ApplyFresh(results[l], missDist.data() + missBase[l]);
+            });
             tApply += since(t0);
         }
         for (int64_t l = 0; l < act; l++)

@@ -2,9 +2,12 @@
 #include "pianopir.hpp"
 
 #include <immintrin.h>
-#include <omp.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -619,12 +622,111 @@ int SimpleBatchPianoPIR::Query(const std::vector<uint64_t> &idx, std::vector<std
 
 int HostThreads() {
     static const int n = [] {
-        const char *v = getenv("PM_HOST_THREADS");
-        int t = v && *v ? atoi(v) : 0;
-        if (t <= 0) t = std::min(8, std::max(1, omp_get_max_threads()));   // follows OMP_NUM_THREADS (torchrun sets it to 1 per rank)
-        return t;
+        int t = 0;
+        if (const char *v = getenv("PM_HOST_THREADS")) t = atoi(v);
+        if (t <= 0)
+            if (const char *v = getenv("OMP_NUM_THREADS")) t = atoi(v);
+        if (t <= 0) t = std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        return std::min(t, 64);
     }();
     return n;
+}
+
+struct WorkerPool::Impl {
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv;
+    // state: odd = a loop is open for workers (they may take items), even = closed.  The caller opens a loop only after
+    // its fields are set and closes it before returning, then waits until no worker is inside: a late worker never
+    // sees a half-initialised loop and never runs an item of a loop that is over.
+    std::atomic<uint64_t> state{0};
+    std::atomic<size_t> next{0}, done{0};
+    std::atomic<int> sleeping{0}, active{0};
+    std::atomic<bool> stop{false};
+    size_t n = 0;
+    const std::function<void(size_t)> *fn = nullptr;
+    std::string error;
+
+    void run_items() {
+        for (;;) {
+            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= n) break;
+            try {
+                (*fn)(i);
+            } catch (const std::exception &e) {
+                std::lock_guard<std::mutex> lock(mu);
+                if (error.empty()) error = e.what();
+            }
+            done.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void worker() {
+        uint64_t seen = 0;
+        for (;;) {
+            // wait for the next open loop: spin ~50 us (a search step opens one every few hundred us), then sleep
+            uint64_t st = state.load(std::memory_order_acquire);
+            for (int spin = 0; !((st & 1) && st != seen) && spin < 20000 && !stop.load(std::memory_order_relaxed); spin++) {
+                _mm_pause();
+                st = state.load(std::memory_order_acquire);
+            }
+            if (!((st & 1) && st != seen)) {
+                std::unique_lock<std::mutex> lock(mu);
+                sleeping.fetch_add(1);
+                cv.wait(lock, [&] {
+                    const uint64_t v = state.load(std::memory_order_acquire);
+                    return ((v & 1) && v != seen) || stop.load();
+                });
+                sleeping.fetch_sub(1);
+                st = state.load(std::memory_order_acquire);
+            }
+            if (stop.load()) return;
+            if (!((st & 1) && st != seen)) continue;
+            active.fetch_add(1, std::memory_order_acq_rel);
+            if (state.load(std::memory_order_acquire) == st) run_items();   // still the loop we saw open
+            active.fetch_sub(1, std::memory_order_acq_rel);
+            seen = st;
+        }
+    }
+};
+
+WorkerPool::WorkerPool(int threads) : impl(new Impl()) {
+    for (int i = 1; i < threads; i++) impl->workers.emplace_back([this] { impl->worker(); });
+}
+WorkerPool::~WorkerPool() {
+    {
+        std::lock_guard<std::mutex> lock(impl->mu);
+        impl->stop.store(true);
+    }
+    impl->cv.notify_all();
+    for (auto &t : impl->workers) t.join();
+    delete impl;
+}
+void WorkerPool::ParallelFor(size_t n, const std::function<void(size_t)> &fn) {
+    if (n == 0) return;
+    if (impl->workers.empty() || n <= 2) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    impl->error.clear();
+    impl->fn = &fn;
+    impl->n = n;
+    impl->done.store(0, std::memory_order_relaxed);
+    impl->next.store(0, std::memory_order_relaxed);
+    const uint64_t open = impl->state.load(std::memory_order_relaxed) + 1;   // even -> odd
+    {
+        std::lock_guard<std::mutex> lock(impl->mu);   // pairs with the sleepers' predicate check
+        impl->state.store(open, std::memory_order_release);
+    }
+    if (impl->sleeping.load() > 0) impl->cv.notify_all();
+    impl->run_items();
+    while (impl->done.load(std::memory_order_acquire) < n) _mm_pause();
+    impl->state.store(open + 1, std::memory_order_release);                  // closed
+    while (impl->active.load(std::memory_order_acquire) != 0) _mm_pause();   // nobody is inside any more
+    if (!impl->error.empty()) throw std::runtime_error(impl->error);
+}
+WorkerPool &WorkerPool::Local() {
+    static thread_local WorkerPool pool(HostThreads());
+    return pool;
 }
 
 void EntryCache::Reserve(uint64_t entries) {
@@ -934,18 +1036,18 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
         gc.rc = gc.pir->QueryFlat(gc.idx, gc.n, dst, gc.query_vec, dim, gc.dists);
     }
     std::vector<size_t> base(L + 1, 0);
-#pragma omp parallel for schedule(static) num_threads(HostThreads()) if (L > 2)
-    for (size_t l = 0; l < L; l++) {
-        if (!grouped[l]) continue;
+    WorkerPool &pool = WorkerPool::Local();
+    pool.ParallelFor(L, [&](size_t l) {
+        if (!grouped[l]) return;
         SimpleBatchPianoPIR *p = calls[l].pir;
         bool bad = false;
         p->profQueryCalls += 1;
         p->beginCall(calls[l].idx, calls[l].n, &bad);
-        if (bad) { calls[l].rc = -1; p->wsQueries.clear(); p->wsPend.clear(); continue; }
+        if (bad) { calls[l].rc = -1; p->wsQueries.clear(); p->wsPend.clear(); return; }
         const uint64_t per = calls[l].n / p->config.PartitionNum;
         for (uint64_t i = 0; i < p->config.PartitionNum; i++)
             for (uint64_t j = 0; j < per; j++) p->pushRecord(i, p->wsLists[i][j]);
-    }
+    });
     for (size_t l = 0; l < L; l++) base[l + 1] = base[l] + (grouped[l] ? calls[l].pir->wsQueries.size() : 0);
     const size_t total = base[L];
     // group scratch lives in the first grouped lane's members
@@ -993,13 +1095,12 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
     const int32_t *gst = host->wsStatus.data();
     const float *gdist = host->wsDist.data();
     std::vector<char> due(L, 0);
-#pragma omp parallel for schedule(static) num_threads(HostThreads()) if (L > 2)
-    for (size_t l = 0; l < L; l++) {
-        if (!grouped[l] || calls[l].rc != 0) continue;
+    pool.ParallelFor(L, [&](size_t l) {
+        if (!grouped[l] || calls[l].rc != 0) return;
         SimpleBatchPianoPIR *p = calls[l].pir;
         p->settle(0, gout + base[l] * E, gst + base[l], (anyVec && dim && calls[l].query_vec) ? gdist + base[l] : nullptr);
         due[l] = p->finishCall(calls[l].idx, calls[l].n, calls[l].out, calls[l].out ? nullptr : calls[l].out_ptrs, calls[l].dists) ? 1 : 0;
-    }
+    });
     lap(tSettle);
     if (prof && (++nCalls % 200) == 0)
         fprintf(stderr, "[group profile] %llu calls, us per call: build %.1f | device call %.1f | settle %.1f\n", (unsigned long long)nCalls,

@@ -14,6 +14,7 @@
 // "next" in SURVEY.md 8f), caches and statistics.  This file only includes the public C header.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <memory>
 #include <string>
 #include <unordered_map>
@@ -81,11 +82,27 @@ struct PendingQuery {
     std::vector<uint32_t> offsets;  // what goes to the server (Dummy, Real)
 };
 
-// Threads a lock-step group uses for its per-lane host work (OpenMP team size): PM_HOST_THREADS, default
-// min(8, omp_get_max_threads()).  Several groups (and several ranks) run side by side, so a team must not grab the whole
-// machine: oversubscribed spin-waiting OpenMP teams cost two orders of magnitude (measured: 8 ranks x 4 groups x 8
+// Threads a lock-step group uses for its per-lane host work: PM_HOST_THREADS, else OMP_NUM_THREADS (torchrun sets it
+// to 1 per rank), else min(8, cores).  Several groups (and several ranks) run side by side, so a group must not grab the
+// whole machine: oversubscribed spin-waiting teams cost two orders of magnitude (measured: 8 ranks x 4 groups x 8
 // threads on 32 cores = 230 ms per step instead of 1 ms).
 int HostThreads();
+
+// The pool behind those threads: HostThreads() - 1 workers owned by the calling (driver) thread plus the caller itself.
+// Workers spin briefly for the next loop, then sleep.  Not OpenMP on purpose: a second OpenMP runtime in the process
+// (torch brings its own) changes libgomp's spin / sleep policy under our feet (measured: 2 800 vs 4 600 queries/s).
+class WorkerPool {
+public:
+    explicit WorkerPool(int threads);
+    ~WorkerPool();
+    // fn(i) for every i in [0, n), on the workers and the caller; returns when all are done; rethrows the first exception
+    void ParallelFor(size_t n, const std::function<void(size_t)> &fn);
+    static WorkerPool &Local();   // the calling thread's pool (created on first use)
+
+private:
+    struct Impl;
+    Impl *impl;
+};
 
 // localCache (pir.go:127, :381-383, :468): idx -> entry.  Entries live in fixed-size slabs (stable addresses, reused after
 // clear()) instead of one heap vector per entry: a search step inserts ~100 entries per client and with many clients in

@@ -86,6 +86,8 @@ def main():
         res.update(clients=a.clients, multi_client_qps=a.clients * per / mdt, multi_client_s_per_query_per_client=mdt / per)
     if a.lanes > 1:
         import threading
+        # one driver thread per group + its pool for the per-lane host work: sized to the cores (oversubscription costs)
+        os.environ.setdefault("PM_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 1) // a.groups))))
         t0 = time.perf_counter()
         groups = []
         for gi in range(a.groups):
