@@ -47,6 +47,7 @@ SIG = {
     "pmh_frontend_pir_lane": (vp, [vp, u64, C.c_uint32]),
     "pmh_search_knn_lockstep": (C.c_int, [vp, i64, vp, i64, i64, i64, i64, C.c_int, vp, vp]),
     "pmh_robust_prune_batch": (C.c_int, [vp, i64, i64, vp, i64, vp, i64, i64, C.c_float, C.c_int, vp, vp]),
+    "pmh_selftest": (C.c_int, [C.c_int]),
     "pmh_frontend_free": (None, [vp]),
     "pmh_frontend_preprocess": (C.c_int, [vp]),
     "pmh_frontend_start_ids": (i64, [vp, vp, i64]),

@@ -1,6 +1,7 @@
 // Flat C handles over the C++ host mirror (pianopir:: / graphann::) so the Python tests and benchmarks
 // can drive it through ctypes.  Not part of the drop-in boundary (that is include/pacmann_cuda.h).
 #include <algorithm>
+#include <unordered_map>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -307,6 +308,61 @@ PMH int pmh_robust_prune_batch(const float *vectors, int64_t n_vectors, int64_t 
     for (int64_t i = 0; i < n; i++) {
         out_len[i] = (int64_t)res[(size_t)i].size();
         for (int64_t j = 0; j < w; j++) out[i * w + j] = j < out_len[i] ? res[(size_t)i][(size_t)j] : -1;
+    }
+    return 0;
+    PMH_CATCH(-100)
+}
+// Self-test of the host-only building blocks (no GPU involved): the open-addressing map against std::unordered_map
+// under random inserts / overwrites / lookups / resets, and the worker pool (every index exactly once over many loops of
+// varying size, exception propagation).  Returns 0 or the number of the failed check.
+PMH int pmh_selftest(int threads) {
+    PMH_TRY
+    {
+        pianopir::FlatMap m;
+        std::unordered_map<uint64_t, uint64_t> ref;
+        uint64_t x = 88172645463325252ull;
+        auto rnd = [&] { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+        for (int round = 0; round < 20; round++) {
+            m.reset(round % 3 == 0 ? 0 : 500);
+            ref.clear();
+            for (int i = 0; i < 4000; i++) {
+                const uint64_t k = rnd() % 3000, v = rnd();
+                if (i % 3 == 0) {
+                    const uint64_t *f = m.find(k);
+                    auto it = ref.find(k);
+                    if ((f != nullptr) != (it != ref.end()) || (f && *f != it->second)) return 1;
+                } else {
+                    m.put(k, v);
+                    ref[k] = v;
+                }
+            }
+            if (m.size() != ref.size()) return 2;
+            for (auto &kv : ref) {
+                const uint64_t *f = m.find(kv.first);
+                if (!f || *f != kv.second) return 3;
+            }
+        }
+    }
+    {
+        pianopir::WorkerPool pool(threads);
+        std::vector<int> hits;
+        for (int loop = 0; loop < 3000; loop++) {
+            const size_t n = (size_t)(loop * 7919 % 67);
+            hits.assign(n, 0);
+            pool.ParallelFor(n, [&](size_t i) { hits[i] += 1 + (int)(loop & 1); });
+            for (size_t i = 0; i < n; i++)
+                if (hits[i] != 1 + (loop & 1)) return 4;
+        }
+        bool thrown = false;
+        try {
+            pool.ParallelFor(40, [&](size_t i) { if (i == 17) throw std::runtime_error("boom"); });
+        } catch (const std::exception &e) {
+            thrown = std::string(e.what()) == "boom";
+        }
+        if (!thrown) return 5;
+        std::vector<int> again(33, 0);
+        pool.ParallelFor(33, [&](size_t i) { again[i] = (int)i; });   // the pool still works after an exception
+        for (size_t i = 0; i < 33; i++) if (again[i] != (int)i) return 6;
     }
     return 0;
     PMH_CATCH(-100)

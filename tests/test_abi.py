@@ -96,3 +96,11 @@ def test_product_never_imports_the_oracle():
                         if re.search(r"(import|include|from|CDLL|dlopen|-l).*oracle", line):
                             bad.append((f, line.strip()))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("threads", [1, 2, 5])
+def test_host_building_blocks_selftest(threads):
+    """The host mirror's open-addressing map (against std::unordered_map under random operations) and its worker pool
+    (every index exactly once over thousands of loops, exception propagation): no GPU involved."""
+    from pacmann_b200 import _host
+    assert _host.lib().pmh_selftest(threads) == 0
