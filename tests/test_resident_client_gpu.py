@@ -137,3 +137,83 @@ def test_private_search_both_client_modes(oracle, resident):
     o_ret, o_step, stats = oracle.search_knn_private(o_pir, vec, graph, start, queries, 10, 10, 2)
     assert (ret == o_ret).all() and (step == o_step).all()
     assert (f.totalQueryNum, f.succQueryNum) == (int(stats[0]), int(stats[1]))
+
+
+def test_client_lanes_at_the_c_abi(oracle):
+    """pm_client_* with L x PartitionNum parts, straight through ctypes: two lanes in ONE pm_client answering one mixed
+    call (pm_client_query_batch_l2m, per-query vector ids, page-locked result buffer from pm_host_alloc) must give what two
+    separate single-lane clients give (pm_client_query_batch_l2), entry for entry, status for status, distance for
+    distance -- and leave identical hint tables behind."""
+    import ctypes as C
+    from pacmann_b200 import cabi
+    from util import splitmix_db
+    L = cabi.lib()
+    n, E, dim = 4000, 20, 24
+    rows = splitmix_db(n, E, seed=5)
+    fl = np.random.default_rng(6).standard_normal((n, dim)).astype(np.float32)
+    rows[:, :dim // 2] = fl.view(np.uint64)                       # entries start with a dim-float vector
+    db = cabi.DB(rows)
+    o = oracle.PianoPIR(n, E * 8, rows.reshape(-1), 8)
+    geo = np.array([0, n, o.chunk_size, o.set_size, o.primary_hint_num, o.max_query_per_chunk, o.max_query_num], np.uint64)
+    parts2 = np.concatenate([geo, geo])
+    keys = [oracle.derive_key(11, 0, 2, i) for i in range(2)]
+    rk = np.concatenate([cabi.expand_key(k) for k in keys]).astype(np.uint32)
+    seeds = np.array([101, 202], np.uint64)
+
+    def create(parts, nparts):
+        h = C.c_void_p()
+        cabi.check(L.pm_client_create(db.h, parts.ctypes.data_as(C.c_void_p), nparts, C.byref(h)))
+        return h
+
+    both = create(parts2, 2)
+    ids = np.array([0, 1], np.uint32)
+    cabi.check(L.pm_client_preprocess(both, ids.ctypes.data_as(C.c_void_p), 2, rk.ctypes.data_as(C.c_void_p), seeds.ctypes.data_as(C.c_void_p), 0))
+    solo = []
+    for i in range(2):
+        h = create(geo, 1)
+        z = np.array([0], np.uint32)
+        cabi.check(L.pm_client_preprocess(h, z.ctypes.data_as(C.c_void_p), 1, rk[44 * i:44 * (i + 1)].ctypes.data_as(C.c_void_p),
+                                          seeds[i:i + 1].ctypes.data_as(C.c_void_p), 0))
+        solo.append(h)
+
+    qdt = np.dtype([("part", np.uint32), ("kind", np.uint32), ("idx", np.uint64), ("dseed", np.uint64), ("dctr", np.uint64)])
+    rng = np.random.default_rng(7)
+    qv = rng.standard_normal((2, dim)).astype(np.float32)
+    pbuf = C.c_void_p()
+    nq = 24
+    cabi.check(L.pm_host_alloc(C.byref(pbuf), nq * E * 8))
+    out_m = np.ctypeslib.as_array(C.cast(pbuf, C.POINTER(C.c_uint64)), shape=(nq, E))
+    for rnd in range(6):
+        q = np.zeros(nq, qdt)
+        q["part"] = rng.integers(0, 2, nq)
+        q["kind"] = (rng.random(nq) < 0.85).astype(np.uint32)
+        q["idx"] = rng.permutation(n)[:nq]                          # no index twice in a call
+        q["dseed"], q["dctr"] = 99, np.arange(nq) * 1000 + rnd * 100000
+        vid = q["part"].astype(np.uint32)
+        st_m, di_m = np.zeros(nq, np.int32), np.zeros(nq, np.float32)
+        cabi.check(L.pm_client_query_batch_l2m(both, q.ctypes.data_as(C.c_void_p), nq, pbuf, st_m.ctypes.data_as(C.c_void_p),
+                                               qv.ctypes.data_as(C.c_void_p), 2, vid.ctypes.data_as(C.c_void_p), dim,
+                                               di_m.ctypes.data_as(C.c_void_p)))
+        for i in range(2):
+            sel = np.nonzero(q["part"] == i)[0]
+            qs = q[sel].copy()
+            qs["part"] = 0
+            o_s, st_s, di_s = np.zeros((len(sel), E), np.uint64), np.zeros(len(sel), np.int32), np.zeros(len(sel), np.float32)
+            cabi.check(L.pm_client_query_batch_l2(solo[i], qs.ctypes.data_as(C.c_void_p), len(sel), o_s.ctypes.data_as(C.c_void_p),
+                                                  st_s.ctypes.data_as(C.c_void_p), qv[i].ctypes.data_as(C.c_void_p), dim,
+                                                  di_s.ctypes.data_as(C.c_void_p)))
+            assert (out_m[sel] == o_s).all() and (st_m[sel] == st_s).all()
+            assert (di_m[sel].view(np.uint32) == di_s.view(np.uint32)).all()
+            real_ok = (qs["kind"] == 1) & (st_s == 0)
+            assert (o_s[real_ok] == rows[qs["idx"][real_ok]]).all()
+    P, B = int(o.primary_hint_num), int(o.set_size * o.max_query_per_chunk)
+    for table, words in ((0, P), (1, P * E), (2, P), (5, B), (6, B * E), (7, int(o.set_size)), (8, 1)):
+        for i in range(2):
+            a, b = np.zeros(words, np.uint64), np.zeros(words, np.uint64)
+            cabi.check(L.pm_client_download(both, i, table, a.ctypes.data_as(C.c_void_p), words))
+            cabi.check(L.pm_client_download(solo[i], 0, table, b.ctypes.data_as(C.c_void_p), words))
+            assert (a == b).all(), (table, i)
+    cabi.check(L.pm_host_free(pbuf))
+    for h in [both] + solo:
+        L.pm_client_destroy(h)
+    db.close()
