@@ -359,7 +359,8 @@ struct pm_client {
     cudaStream_t stream = nullptr;          // every client owns its stream, scratch and lock, so several clients that
     void *wbuf[2] = {nullptr, nullptr};     // share one pm_db (one per user) can be driven from different host threads
     size_t wbytes[2] = {0, 0};
-    std::vector<uint32_t> csr;   // per-part query lists of the current call (host copy)
+    void *stage_in = nullptr;    // pinned host staging for the input block of a call
+    size_t stage_in_bytes = 0;
     void *stage = nullptr;   // pinned host staging for results
     size_t stage_bytes = 0;
     cudaEvent_t ev[6] = {};
@@ -462,6 +463,7 @@ PM_EXPORT int pm_client_destroy(pm_client *c) {
         cudaFree(c->d_parts);
         for (int i = 0; i < 2; i++) if (c->wbuf[i]) cudaFree(c->wbuf[i]);
         if (c->stage) cudaFreeHost(c->stage);
+        if (c->stage_in) cudaFreeHost(c->stage_in);
         cudaStreamDestroy(c->stream);
     }
     delete c;
@@ -572,21 +574,33 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     pm_db *db = c->db;
     std::lock_guard<std::mutex> lock(c->mu);
     const uint64_t E = c->E, stride = (c->max_set + 3) & ~3ull;
-    // staging: queries | meta | offsets | answer descriptors   and   answers | out
+    // device input block, filled by ONE host-to-device copy from page-locked staging:  queries | per-part lists | query
+    // vectors | vector ids;  behind it the offsets and answer descriptors the prepare kernel produces.  Second buffer:
+    // answers | results | meta | distances (results, meta and distances leave in one copy).
     const size_t b_q = q * sizeof(ClientQueryDev), b_meta = q * sizeof(ClientMeta), b_off = q * stride * 4, b_desc = q * 24;
     void *d_in = nullptr, *d_out = nullptr;
-    const size_t b_qv = (n_vecs * dim * 4 + 15) & ~15ull, b_vid = vec_id ? q * 4 : 0, b_dist = dist_out ? q * 4 : 0;
+    const size_t b_qv = (n_vecs * dim * 4 + 15) & ~15ull, b_vid = vec_id ? (q * 4 + 15) & ~15ull : 0, b_dist = dist_out ? q * 4 : 0;
     const size_t b_csr = ((c->n_parts + 1 + q) * 4 + 15) & ~15ull;
-    if ((rc = client_scratch(c, 1, b_q + b_off + b_desc + b_qv + b_vid + b_csr + 64, &d_in))) return rc;
+    const size_t b_hdr = b_q + b_csr + b_qv + b_vid;   // sizeof(ClientQueryDev) = 32: every piece stays 16-byte aligned
+    if ((rc = client_scratch(c, 1, b_hdr + b_off + b_desc + 64, &d_in))) return rc;
     if ((rc = client_scratch(c, 0, 2 * q * E * 8 + b_meta + b_dist, &d_out))) return rc;
     ClientQueryDev *d_q = (ClientQueryDev *)d_in;
-    uint32_t *d_off = (uint32_t *)((char *)d_in + b_q);
+    uint32_t *d_start = (uint32_t *)((char *)d_in + b_q), *d_items = d_start + c->n_parts + 1;
+    float *d_qv = (float *)((char *)d_in + b_q + b_csr);
+    uint32_t *d_vid = vec_id ? (uint32_t *)((char *)d_qv + b_qv) : nullptr;
+    uint32_t *d_off = (uint32_t *)((char *)d_in + b_hdr);
     uint64_t *d_row0 = (uint64_t *)((char *)d_off + b_off), *d_nrows = d_row0 + q;
     uint32_t *d_chunk = (uint32_t *)(d_nrows + q), *d_set = d_chunk + q;
     uint64_t *d_ans = (uint64_t *)d_out, *d_res = d_ans + q * E;
-    ClientMeta *d_meta = (ClientMeta *)(d_res + q * E);  // results and their status records leave in ONE copy
-    // pinned staging (grow-only): the D2H lands at PCIe speed instead of going through the pageable path
-    float *d_qv = (float *)((((uintptr_t)(d_set + q)) + 15) & ~(uintptr_t)15), *d_dist = (float *)(d_meta + q);
+    ClientMeta *d_meta = (ClientMeta *)(d_res + q * E);
+    float *d_dist = (float *)(d_meta + q);
+    if (c->stage_in_bytes < b_hdr) {
+        if (c->stage_in) cudaFreeHost(c->stage_in);
+        c->stage_in = nullptr;
+        c->stage_in_bytes = 0;
+        PM_CUDA(cudaHostAlloc(&c->stage_in, b_hdr * 2 + 4096, cudaHostAllocDefault));
+        c->stage_in_bytes = b_hdr * 2 + 4096;
+    }
     // a page-locked `out` (pm_host_alloc) receives the answers straight from the GPU; only meta + distances are staged
     bool direct = false;
     {
@@ -606,10 +620,12 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     static const bool prof = getenv("PM_CLIENT_PROFILE") != nullptr;
     if (prof && !c->ev[0]) for (int i = 0; i < 6; i++) cudaEventCreate(&c->ev[i]);
     auto mark = [&](int i) { if (prof) cudaEventRecord(c->ev[i], c->stream); };
-    // per-part query lists (counting sort; array order within a part is the processing order)
-    c->csr.resize(c->n_parts + 1 + q);
+    // fill the input block: records, per-part query lists (counting sort; array order within a part is the processing
+    // order), query vectors and their ids
     {
-        uint32_t *start = c->csr.data(), *items = start + c->n_parts + 1;
+        char *h = (char *)c->stage_in;
+        memcpy(h, queries, b_q);
+        uint32_t *start = (uint32_t *)(h + b_q), *items = start + c->n_parts + 1;
         uint32_t acc = 0;
         for (uint64_t i = 0; i < c->n_parts; i++) { start[i] = acc; acc += per_part[i]; }
         start[c->n_parts] = acc;
@@ -617,11 +633,11 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
         for (uint64_t i = 0; i < c->n_parts; i++) cur[i] = start[i];
         for (uint64_t t = 0; t < q; t++) items[cur[queries[t].part]++] = (uint32_t)t;
         for (uint64_t i = 0; i < c->n_parts; i++) cur[i] -= start[i];   // back to counts
+        if (dist_out) memcpy(h + b_q + b_csr, query_vec, n_vecs * dim * 4);
+        if (vec_id) memcpy(h + b_q + b_csr + b_qv, vec_id, q * 4);
     }
-    uint32_t *d_start = (uint32_t *)(((uintptr_t)((char *)d_qv + b_qv + b_vid) + 15) & ~(uintptr_t)15), *d_items = d_start + c->n_parts + 1;
     mark(0);
-    PM_CUDA(cudaMemcpyAsync(d_q, queries, b_q, cudaMemcpyHostToDevice, c->stream));
-    PM_CUDA(cudaMemcpyAsync(d_start, c->csr.data(), (c->n_parts + 1 + q) * 4, cudaMemcpyHostToDevice, c->stream));
+    PM_CUDA(cudaMemcpyAsync(d_in, c->stage_in, b_hdr, cudaMemcpyHostToDevice, c->stream));
     mark(1);
     uint64_t max_p = 0;
     for (uint64_t i = 0; i < c->n_parts; i++) if (c->host_parts[i].poff) max_p = std::max<uint64_t>(max_p, c->host_parts[i].n_primary);
@@ -643,9 +659,6 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     PM_CHECK_LAUNCH();
     count_launch();
     if (dist_out) {  // distances of the answered entries' vectors to the search query, on the same stream (A10 call site)
-        uint32_t *d_vid = vec_id ? (uint32_t *)((char *)d_qv + b_qv) : nullptr;
-        PM_CUDA(cudaMemcpyAsync(d_qv, query_vec, n_vecs * dim * 4, cudaMemcpyHostToDevice, c->stream));
-        if (vec_id) PM_CUDA(cudaMemcpyAsync(d_vid, vec_id, b_vid, cudaMemcpyHostToDevice, c->stream));
         if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, vec_id ? dim : 0, d_vid, q, (uint32_t)dim, d_dist, c->stream))) return rc;
     }
     mark(4);
