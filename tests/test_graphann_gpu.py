@@ -184,3 +184,25 @@ def test_evaluate_graph_quality(oracle):
     assert abs(hit_rate - o_hit.mean()) < 1e-12
     if o_hit.any():
         assert abs(avg_steps - o_step[o_hit, 0].mean()) < 1e-9
+
+
+def test_lockstep_over_plain_frontends_and_benchmark_mode(oracle):
+    """SearchKNNLockstep also accepts lanes that cannot share a device call (BasicGraphInfo: every lane fetches for
+    itself) and the -benchmark mode of a client group (random ids, answers discarded): same results as lane by lane."""
+    from pacmann_b200 import graphann
+    n, dim, m = 3000, 32, 8
+    vec, graph = make_dataset(n, dim, m, 181)
+    queries = vec[np.random.default_rng(182).integers(0, n, 7)] + np.float32(0.02)
+    lanes = [graphann.GraphANNFrontend(vec, graph) for _ in range(2)]
+    for f in lanes:
+        f.Preprocess()
+    ret, step = graphann.SearchKNNLockstep(lanes, queries, 10, 8, 2)
+    for l in range(2):
+        ref = graphann.GraphANNFrontend(vec, graph)
+        ref.Preprocess()
+        want, wstep = ref.SearchKNNBatch(queries[l::2], 10, 8, 2)
+        assert (ret[l::2] == want).all() and (step[l::2] == wstep).all()
+    group = graphann.make_client_group(vec, graph, 3, seeds=[5, 6, 7], skipPrep=True)
+    bret, bstep = graphann.SearchKNNLockstep(group, queries[:6], 5, 4, 2, benchmarking=True)
+    assert (bret == -1).all() and (bstep == -1).all()
+    assert [g.totalQueryNum for g in group] == [2 * 4 * 2 * m] * 3
