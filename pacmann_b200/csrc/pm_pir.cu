@@ -6,7 +6,11 @@
 #include <vector>
 
 #include "pm_aes.cuh"
+#include <cooperative_groups.h>
+
 #include "pm_common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pm {
 
@@ -290,18 +294,23 @@ struct AnswerParams {
     uint64_t offsets_stride;
     uint64_t *out;
     uint32_t ev, evx;
+    uint32_t split;   // CTAs per sub-query (a thread-block cluster when > 1)
 };
 
 // CW lanes cover the columns of one row; ANS_THREADS/CW rows are fetched concurrently.
+// A call with few sub-queries (one search step of one client: 96) leaves SMs idle and is bound by the depth of one CTA's
+// row pipeline, so `split` CTAs -- a thread-block cluster -- share a sub-query: each XORs every split-th group of rows,
+// and rank 0 folds the partial parities of its peers through distributed shared memory.
 template <typename VT, int CW, int NVA>
 __global__ void __launch_bounds__(ANS_THREADS) answer_kernel(const AnswerParams P) {
     extern __shared__ uint32_t smem_u32[];
-    const uint32_t q = blockIdx.x, t = threadIdx.x;
+    const uint32_t R = P.split, q = blockIdx.x / R, rank = blockIdx.x % R, t = threadIdx.x;
     const uint32_t S = P.set_size[q], C = P.chunk_size[q];
     const uint64_t n_rows = P.n_rows[q];
     const VT *base = reinterpret_cast<const VT *>(P.db) + P.row0[q] * P.ev;
     uint32_t *s_off = smem_u32;                                             // [S]
     VT *s_red = reinterpret_cast<VT *>(smem_u32 + ((S + 3) & ~3u));         // [groups][CW*NVA]
+    VT *s_part = s_red + (ANS_THREADS / CW) * (CW * NVA);                   // [CW*NVA] this CTA's partial parity (split > 1)
     for (uint32_t c = t; c < S; c += ANS_THREADS) s_off[c] = P.offsets[q * P.offsets_stride + c];
     __syncthreads();
     constexpr int GROUPS = ANS_THREADS / CW;
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(ANS_THREADS) answer_kernel(const AnswerParams 
 #pragma unroll
         for (int k = 0; k < NVA; k++) vzero(acc[k]);
 #pragma unroll 4
-        for (uint32_t c = grp; c < S; c += GROUPS) {
+        for (uint32_t c = grp + rank * GROUPS; c < S; c += GROUPS * R) {
             const uint64_t idx = (uint64_t)s_off[c] + (uint64_t)c * C;
             const bool ok = idx < n_rows;
             const VT *rp = base + (ok ? idx : 0) * P.ev + cb + col;
@@ -326,7 +335,19 @@ __global__ void __launch_bounds__(ANS_THREADS) answer_kernel(const AnswerParams 
             VT r;
             vzero(r);
             for (int gidx = 0; gidx < GROUPS; gidx++) vxor(r, s_red[gidx * (CW * NVA) + v]);
-            reinterpret_cast<VT *>(P.out)[(uint64_t)q * P.ev + cb + v] = r;
+            if (R == 1) reinterpret_cast<VT *>(P.out)[(uint64_t)q * P.ev + cb + v] = r;
+            else s_part[v] = r;
+        }
+        if (R > 1) {
+            cg::cluster_group cluster = cg::this_cluster();
+            cluster.sync();                                   // every rank's partial parity is in its shared memory
+            if (rank == 0)
+                for (uint32_t v = t; v < CW * NVA && cb + v < P.ev; v += ANS_THREADS) {
+                    VT r = s_part[v];
+                    for (uint32_t pr = 1; pr < R; pr++) vxor(r, cluster.map_shared_rank(s_part, pr)[v]);
+                    reinterpret_cast<VT *>(P.out)[(uint64_t)q * P.ev + cb + v] = r;
+                }
+            cluster.sync();                                   // peers keep their shared memory until rank 0 has read it
         }
         __syncthreads();
     }
@@ -520,10 +541,26 @@ static int launch_answer_t(const AnswerParams &P, uint64_t q, uint32_t max_set, 
     const size_t off_words = (max_set + 3) & ~3u;
 #define PM_ANS(CW, NVA)                                                                                  \
     do {                                                                                                 \
-        size_t smem = off_words * 4 + (size_t)ANS_THREADS * NVA * sizeof(VT);                            \
+        size_t smem = off_words * 4 + (size_t)ANS_THREADS * NVA * sizeof(VT) + (size_t)CW * NVA * sizeof(VT); \
         auto kern = answer_kernel<VT, CW, NVA>;                                                          \
         PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-        kern<<<(unsigned)q, ANS_THREADS, smem, st>>>(P);                                                 \
+        if (P.split > 1) {                                                                               \
+            cudaLaunchConfig_t cfg = {};                                                                 \
+            cfg.gridDim = dim3((unsigned)(q * P.split));                                                 \
+            cfg.blockDim = dim3(ANS_THREADS);                                                            \
+            cfg.dynamicSmemBytes = smem;                                                                 \
+            cfg.stream = st;                                                                             \
+            cudaLaunchAttribute attr[1];                                                                 \
+            attr[0].id = cudaLaunchAttributeClusterDimension;                                            \
+            attr[0].val.clusterDim.x = P.split;                                                          \
+            attr[0].val.clusterDim.y = 1;                                                                \
+            attr[0].val.clusterDim.z = 1;                                                                \
+            cfg.attrs = attr;                                                                            \
+            cfg.numAttrs = 1;                                                                            \
+            PM_CUDA(cudaLaunchKernelEx(&cfg, kern, P));                                                  \
+        } else {                                                                                         \
+            kern<<<(unsigned)q, ANS_THREADS, smem, st>>>(P);                                             \
+        }                                                                                                \
     } while (0)
     if (x <= 1) PM_ANS(1, 1);
     else if (x <= 2) PM_ANS(2, 1);
@@ -552,6 +589,13 @@ int answer_enqueue(pm_db *db, const uint64_t *row0, const uint64_t *n_rows, cons
     P.offsets = offsets; P.offsets_stride = stride; P.out = out;
     P.ev = (uint32_t)(wide ? E / 2 : E);
     P.evx = (uint32_t)(wide ? (E & ~3ull) / 2 : (E & ~3ull));
+    // few sub-queries: a cluster of CTAs per sub-query so that about two CTAs per SM are at work (PM_ANS_SPLIT forces)
+    static const int force_split = env_int("PM_ANS_SPLIT", 0);
+    const uint64_t target = 2ull * (uint64_t)db->sm_count;
+    uint32_t split = (uint32_t)std::min<uint64_t>(4, std::max<uint64_t>(1, (target + q / 2) / q));
+    if (max_set < 64) split = 1;   // nothing to share
+    if (force_split >= 1 && force_split <= 8) split = (uint32_t)force_split;
+    P.split = split;
     return wide ? launch_answer_t<uint4>(P, q, max_set, st) : launch_answer_t<uint2>(P, q, max_set, st);
 }
 
