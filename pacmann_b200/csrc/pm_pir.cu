@@ -589,9 +589,10 @@ int answer_enqueue(pm_db *db, const uint64_t *row0, const uint64_t *n_rows, cons
     P.offsets = offsets; P.offsets_stride = stride; P.out = out;
     P.ev = (uint32_t)(wide ? E / 2 : E);
     P.evx = (uint32_t)(wide ? (E & ~3ull) / 2 : (E & ~3ull));
-    // few sub-queries: a cluster of CTAs per sub-query so that about two CTAs per SM are at work (PM_ANS_SPLIT forces)
+    // few sub-queries: a cluster of up to 4 CTAs per sub-query so that about three CTAs per SM are at work (measured at
+    // 96 sub-queries, us: 1 CTA 24.9 | 2 21.2 | 3 18.4 | 4 16.8 | 6 16.5 | 8 20.0).  PM_ANS_SPLIT forces.
     static const int force_split = env_int("PM_ANS_SPLIT", 0);
-    const uint64_t target = 2ull * (uint64_t)db->sm_count;
+    const uint64_t target = 3ull * (uint64_t)db->sm_count;
     uint32_t split = (uint32_t)std::min<uint64_t>(4, std::max<uint64_t>(1, (target + q / 2) / q));
     if (max_set < 64) split = 1;   // nothing to share
     if (force_split >= 1 && force_split <= 8) split = (uint32_t)force_split;
