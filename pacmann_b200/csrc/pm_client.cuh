@@ -4,7 +4,7 @@
 // query on the CPU) runs as a block-wide parallel search.  Included at the end of pm_pir.cu (same
 // translation unit as the AES table in constant memory).
 //
-// One query call = three launches on one stream:
+// One query call = three launches on one stream (the distances of pm_client_query_batch_l2[m] ride in the third):
 //   client_prepare_kernel   one CTA per sub-PIR walks its queries IN ORDER: budget checks, hint search,
 //                           set expansion, programmed-point and replacement patching (pir.go:386-447) and
 //                           the response-independent half of the refresh (tags, program point, counters)
@@ -291,9 +291,14 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
 // Thread w owns word w of every entry, so the only cross-query dependency -- two queries of a part refreshing
 // the same hint slot -- is a read-after-write inside one thread: no barrier is needed, and the operands that do not
 // depend on earlier queries (answer, replacement value, backup parity) are fetched four queries ahead.
+// With query vectors given it also evaluates, for every entry it has just finished, L2Dist(vector part of the entry,
+// the query vector of that sub-query) -- the per-step L2Dist call site of SearchKNN (search.go:204) without a launch of
+// its own: qv = [n_vecs][dim], vid = per-query vector index or nullptr (one vector for all), dist_out[t].
 __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev *parts, const uint32_t *part_start,
                                                             const uint32_t *part_items, const ClientMeta *meta, uint32_t E,
-                                                            const uint64_t *__restrict__ answers, uint64_t *__restrict__ out) {
+                                                            const uint64_t *__restrict__ answers, uint64_t *__restrict__ out,
+                                                            const float *__restrict__ qv, const uint32_t *__restrict__ vid, uint32_t dim,
+                                                            float *__restrict__ dist_out) {
     const uint32_t part = blockIdx.x;
     const ClientPartDev &D = parts[part];
     const uint32_t E4 = E & ~3u;  // EntryXor granularity (xorSlices leaves the len%4 tail untouched)
@@ -340,6 +345,18 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
                 out[(uint64_t)t * E + w] = r;
             }
         }
+    }
+    if (dist_out == nullptr) return;
+    __syncthreads();   // the entries above were written by this CTA: visible to all its threads from here on
+    const int half = threadIdx.x & 1;
+    const uint32_t n_up = (n_mine + 15) & ~15u;   // keep whole warps in the pair shuffle
+    for (uint32_t k = threadIdx.x >> 1; k < n_up; k += blockDim.x >> 1) {
+        const bool ok = k < n_mine;
+        const uint32_t t = s_list[ok ? k : 0];
+        const float *a = reinterpret_cast<const float *>(out + (uint64_t)t * E);
+        const float *b = qv + (vid ? (uint64_t)vid[t] * dim : 0);
+        const float d = l2_pair<false>(a, b, dim, half);
+        if (ok && half == 0) dist_out[t] = d;
     }
 }
 
@@ -655,12 +672,11 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     mark(2);
     if ((rc = answer_enqueue(db, d_row0, d_nrows, d_chunk, d_set, d_off, stride, q, (uint32_t)stride, d_ans, c->stream))) return rc;
     mark(3);
-    client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, c->stream>>>(c->d_parts, d_start, d_items, d_meta, (uint32_t)E, d_ans, d_res);
+    // the distances of the answered entries' vectors to the search query (A10 call site) come out of the same launch
+    client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, c->stream>>>(c->d_parts, d_start, d_items, d_meta, (uint32_t)E, d_ans, d_res,
+                                                                      dist_out ? d_qv : nullptr, d_vid, (uint32_t)dim, dist_out ? d_dist : nullptr);
     PM_CHECK_LAUNCH();
     count_launch();
-    if (dist_out) {  // distances of the answered entries' vectors to the search query, on the same stream (A10 call site)
-        if ((rc = l2_rows_enqueue((const float *)d_res, E * 2, d_qv, vec_id ? dim : 0, d_vid, q, (uint32_t)dim, d_dist, c->stream))) return rc;
-    }
     mark(4);
     if (direct) {
         PM_CUDA(cudaMemcpyAsync(out, d_res, q * E * 8, cudaMemcpyDeviceToHost, c->stream));

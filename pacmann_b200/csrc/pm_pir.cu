@@ -815,4 +815,5 @@ PM_EXPORT int pm_answer_batch(pm_db *db, const uint64_t *row0, const uint64_t *n
     return PM_OK;
 }
 
+#include "pm_l2.cuh"
 #include "pm_client.cuh"
