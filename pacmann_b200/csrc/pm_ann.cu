@@ -142,17 +142,6 @@ __global__ void __launch_bounds__(IP_THREADS, 2) ip_scan_kernel(const uint4 *row
 }
 
 // out[i] = L2Dist(a + i*a_stride, b + i*b_stride) for device-resident rows (strides in floats; b_stride 0 = one query)
-int l2_rows_enqueue(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride, const uint32_t *b_index, uint64_t n,
-                    uint32_t dim, float *out, cudaStream_t st) {
-    if (n == 0) return PM_OK;
-    uint64_t blocks = (n + L2_THREADS / 2 - 1) / (L2_THREADS / 2);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    l2_pairs_kernel<<<(unsigned)blocks, L2_THREADS, 0, st>>>(a, a_stride, b, b_stride, b_index, n, dim, out);
-    PM_CHECK_LAUNCH();
-    count_launch();
-    return PM_OK;
-}
-
 int l2_batch_enqueue(pm_db *db, uint64_t dim, const float *queries, uint64_t nq, const int64_t *ids, uint64_t k, float *out,
                      cudaStream_t st) {
     if (nq == 0 || k == 0) return PM_OK;

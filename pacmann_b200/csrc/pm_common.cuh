@@ -35,14 +35,12 @@ int set_error(int code, const char *fmt, ...);
 void count_launch(uint64_t n = 1);
 int ensure_device(int device);  // cudaSetDevice + one-time table upload; returns PM_OK / error
 int sm_count(int device);
-const void *zero_page(int device);
+const void *zero_page(int device);  // 4 KB of device zeros, allocated once per device
 // tensor-core path of the uint32 inner-product scan (pm_ipgemm.cu)
 bool ipgemm_applicable(const pm_db *db, uint64_t dim, uint64_t nq, const uint32_t *ip_out);
 size_t ipgemm_scratch_bytes(uint64_t dim, uint64_t nq);
 int ipgemm_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t nq, uint32_t *checksum, void *scratch_dev, cudaStream_t st);
 int ipgemm_check(void *scratch_dev, uint64_t dim, uint64_t nq);
-int l2_rows_enqueue(const float *a, uint64_t a_stride, const float *b, uint64_t b_stride, const uint32_t *b_index, uint64_t n,
-                    uint32_t dim, float *out, cudaStream_t st);  // pm_ann.cu  // 4 KB of device zeros, allocated once per device
 // grow-only scratch slot on a handle
 int scratch(pm_db *db, int slot, size_t bytes, void **out);
 unsigned int *sync_counter(pm_db *db);  // next barrier counter of the handle's pool
