@@ -387,13 +387,13 @@ def main():
     # ---- spot check (outside every timed region): a few parities recomputed from the PRF definition ----
     verified = None
     if rank == 0:
-        verified = spot_check(cabi, host_db, parts, rk_all, my_hints, out_host.numpy().view(np.uint64).reshape(-1, E))
+        verified = spot_check(host_db, parts, rk_all, my_hints, out_host.numpy().view(np.uint64).reshape(-1, E))
         if jobs_p2p is not None:       # the table every rank wrote into: check hints of every rank's shard
             full = torch.empty(int(part_off[-1]) * E, dtype=torch.int64)
             cudart = C.CDLL("libcudart.so.12")
             assert cudart.cudaMemcpy(C.c_void_p(full.data_ptr()), C.c_void_p(p2p_table), C.c_size_t(full.numel() * 8), 2) == 0
             all_hints = [(0, p["hints"]) for p in parts]
-            verified = verified and spot_check(cabi, host_db, parts, rk_all, all_hints, full.numpy().view(np.uint64).reshape(-1, E),
+            verified = verified and spot_check(host_db, parts, rk_all, all_hints, full.numpy().view(np.uint64).reshape(-1, E),
                                                extra=[p["hints"] * r // world for p in parts[:1] for r in range(1, world)])
 
     # ---- second half of the metric: end-to-end private-ANN queries/s on MS-MARCO-shaped data ----
@@ -435,7 +435,7 @@ def main():
                          "binding_term": "not HBM: L1 data-pipe wavefronts (row gather + AES T-table LDS) and ALU; see DESIGN.md",
                          "xor_gather_gbs": b_xor / world / (kern_ms * 1e-3) / 1e9,
                          "prf_per_s": n_prf / world / (kern_ms * 1e-3)},
-            "verified_vs_prf_definition": verified,
+            "verified_vs_oracle_prf": verified,
             "private_ann": private_ann,
             "reference_published": {"msmarco_prep_s": "9-10 (1 thread, reproduction/msmarco/README.md:26)"},
         }
@@ -614,15 +614,17 @@ def private_search(args, rank, world, local_rank, dist, dev):
     return out
 
 
-def spot_check(cabi, host_db, parts, rk_all, my_hints, got, extra=()):
-    """Recompute a handful of parities on the host from pm_prf_batch offsets + numpy XOR (no oracle)."""
+def spot_check(host_db, parts, rk_all, my_hints, got, extra=()):
+    """Outside every timed region: a handful of parities recomputed from the ORACLE's PRF (oracle/, CPU) + numpy XOR.
+    The full-size oracle comparison of this very call is tests/test_hintgen_variants_gpu.py."""
+    from oracle import oracle as o
     ok, off = True, 0
     rng = np.random.default_rng(1)
     for p, (a, b), rk in zip(parts, my_hints, rk_all):
         if b > a:
             for h in {a, b - 1, int(rng.integers(a, b))} | {x for x in extra if a <= x < b} | {x - 1 for x in extra if a < x <= b}:
                 cs = np.arange(p["set"], dtype=np.uint64)
-                offs = cabi.prf_batch(rk, np.full(p["set"], h, np.uint64), cs) & np.uint64(p["chunk"] - 1)
+                offs = o.prf_batch(rk, np.full(p["set"], h, np.uint64), cs) & np.uint64(p["chunk"] - 1)
                 rows = cs * np.uint64(p["chunk"]) + offs
                 skip = -1 if h < p["primary"] else (h - p["primary"]) // p["mqpc"]
                 sel = rows[(rows < p["n_rows"]) & (cs != skip if skip >= 0 else True)]

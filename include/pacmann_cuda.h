@@ -62,6 +62,15 @@ int pm_device_count(int *count);
 /* number of kernel launches issued by this library in this process (for accounting) */
 uint64_t pm_launch_count(void);
 
+/* Launch-time tuning knobs (tests and profiling force the launch variants the heuristics would pick at other sizes).
+ * Knobs: "hg_sync" (round barrier of the hint kernel: -1 auto, 0, 1), "hg_warps" (CTA width in warps: 0 auto, 1..16),
+ * "hg_ntab" (AES T-tables: 0 auto, 1, 4), "hg_tail_split" (shared last round: -1 auto, 0 off, 1 on), "hg_serpentine"
+ * (0, 1), "hg_xbytes" (chunk-id bytes the hoisted PRF rounds treat as varying: 0 auto, 2, 4), "ans_split" (CTAs per
+ * sub-query: 0 auto, 1..8), "hg_d2h_groups" (launch groups of pm_hintgen: 0 auto, 1..16).  Initial values come from the
+ * environment (PM_HG_SYNC, PM_HG_WARPS, ...).  Results never depend on a knob. */
+int pm_tuning_set(const char *name, int value);
+int pm_tuning_get(const char *name, int *value);
+
 int pm_db_create(const uint64_t *rows_host, uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
 int pm_db_create_empty(uint64_t n_rows, uint64_t entry_u64, int device, pm_db **out);
 /* borrow an existing device allocation (16-byte aligned, on `device`); the caller keeps ownership */
@@ -80,6 +89,17 @@ int pm_buf_free(void *dev_ptr, int device);
 int pm_buf_ipc_export(void *dev_ptr, int device, uint8_t handle[64]);
 int pm_buf_ipc_open(const uint8_t handle[64], int device, void **dev_ptr);
 int pm_buf_ipc_close(void *dev_ptr, int device);
+/* synchronous copies / clearing of such buffers (a Go caller has no cudaMemcpy of its own) */
+int pm_buf_upload(void *dev_ptr, const void *host, uint64_t bytes, int device);
+int pm_buf_download(void *host, const void *dev_ptr, uint64_t bytes, int device);
+int pm_buf_zero(void *dev_ptr, uint64_t bytes, int device);
+/* Completion flags for the peer-memory exchange.  `flags` points at (n_flags + 1) 128-byte lines in device memory
+ * (usually inside the consumer's IPC-shared buffer, zeroed once): line i holds rank i's counter in its first uint32,
+ * line n_flags a timeout marker.  pm_flag_signal_dev adds 1 to ONE counter (system-scope release) once everything
+ * enqueued before it on `stream` has finished; pm_flag_wait_dev blocks `stream` until every one of the n_flags counters
+ * has reached `target` (wrap-safe compare), or sets the marker to 1 after `timeout_ms` and lets the stream go on. */
+int pm_flag_signal_dev(void *flag, int device, void *stream);
+int pm_flag_wait_dev(void *flags, uint32_t n_flags, uint32_t target, uint32_t timeout_ms, int device, void *stream);
 
 /* A1: FIPS-197 AES-128 key schedule, 11 round keys as 44 little-endian uint32 (raw 16-byte blocks). */
 int pm_expand_key(const uint8_t key[16], uint32_t rk[44]);
@@ -173,6 +193,9 @@ int pm_client_download(pm_client *c, uint32_t part, int table, uint64_t *out, ui
  * everywhere; a pm_host_alloc'ed `out` of pm_client_query_batch* just saves one host-side copy of the answers). */
 int pm_host_alloc(void **out, uint64_t bytes);
 int pm_host_free(void *p);
+/* page-lock an existing host range (e.g. a shared-memory mapping that several per-GPU processes copy parities into) */
+int pm_host_register(void *host, uint64_t bytes);
+int pm_host_unregister(void *host);
 
 /* A9: squared L2 in the reference's exact fp32 order.  out[i] = L2Dist(a[i], b[i]), rows of `dim` floats. */
 int pm_l2_pairs(const float *a, const float *b, uint64_t n, uint64_t dim, float *out, int device);

@@ -667,7 +667,8 @@ typedef struct {
     uint64_t entry_bytes, entry_u64, db_size, batch_size, partition_num, partition_size, fail_log2;
     orc_pir **sub;
     uint64_t finished_batch_num, queries_made_in_partition, support_batch_num;
-    uint64_t key_seed, key_epoch, repl_seed;
+    uint64_t key_seed, repl_seed;
+    uint64_t *sub_epoch; /* preprocessings made so far per sub-PIR: every one draws a fresh key (pir.go:208-211) */
 } orc_batch;
 
 /* NewSimpleBatchPianoPIR : batch-pir.go:55-93 */
@@ -682,6 +683,7 @@ ORC_API orc_batch *orc_batch_new(uint64_t db_size, uint64_t entry_bytes, uint64_
     b->partition_size = (db_size + b->partition_num - 1) / b->partition_num;
     b->fail_log2 = fail_log2;
     b->sub = calloc(b->partition_num, sizeof(orc_pir *));
+    b->sub_epoch = calloc(b->partition_num, sizeof(uint64_t));
     for (uint64_t i = 0; i < b->partition_num; i++) {
         uint64_t start = i * b->partition_size, end = (i + 1) * b->partition_size;
         if (end > db_size) end = db_size;
@@ -694,6 +696,7 @@ ORC_API void orc_batch_free(orc_batch *b) {
     if (!b) return;
     for (uint64_t i = 0; i < b->partition_num; i++) orc_pir_free(b->sub[i]);
     free(b->sub);
+    free(b->sub_epoch);
     free(b);
 }
 ORC_API orc_pir *orc_batch_sub(orc_batch *b, uint64_t i) { return b->sub[i]; }
@@ -731,20 +734,19 @@ ORC_API void orc_batch_preprocessing(orc_batch *b, uint64_t key_seed, uint64_t r
 #pragma omp parallel for num_threads(outer) schedule(dynamic, 1)
     for (int i = 0; i < P; i++) {
         uint8_t key[16];
-        orc_derive_key(key_seed, b->key_epoch, b->partition_num, (uint64_t)i, key);
-        orc_pir_preprocessing(b->sub[i], key, orc_mix64(repl_seed, b->key_epoch * b->partition_num + (uint64_t)i), inner);
+        const uint64_t e = b->sub_epoch[i]++;
+        orc_derive_key(key_seed, e, b->partition_num, (uint64_t)i, key);
+        orc_pir_preprocessing(b->sub[i], key, orc_mix64(repl_seed, e * b->partition_num + (uint64_t)i), inner);
     }
-    b->key_epoch++;
     b->support_batch_num = b->sub[0]->max_query_num / QUERY_PER_PARTITION;
 }
 /* DummyPreprocessing : batch-pir.go:157-166 */
 ORC_API void orc_batch_dummy_preprocessing(orc_batch *b, uint64_t key_seed) {
     for (uint64_t i = 0; i < b->partition_num; i++) {
         uint8_t key[16];
-        orc_derive_key(key_seed, b->key_epoch, b->partition_num, i, key);
+        orc_derive_key(key_seed, b->sub_epoch[i]++, b->partition_num, i, key);
         orc_pir_dummy_preprocessing(b->sub[i], key);
     }
-    b->key_epoch++;
     b->support_batch_num = b->sub[0]->max_query_num / QUERY_PER_PARTITION;
 }
 
@@ -767,15 +769,19 @@ ORC_API int orc_batch_query(orc_batch *b, const uint64_t *idx, uint64_t n, uint6
     uint64_t *tmp = malloc(E * 8);
     for (uint64_t i = 0; i < PN; i++) {
         for (uint64_t j = 0; j < to_make; j++) {
-            if (j >= cnt[i] || lists[i * n + j] == DEFAULT_VALUE) {
+            /* PianoPIR.Query (pir.go:525-533): a sub-PIR whose budget is exactly spent re-preprocesses first, under
+             * the key of ITS next epoch */
+            if (b->sub[i]->finished_query_num == b->sub[i]->max_query_num) {
                 uint8_t key[16];
-                orc_derive_key(b->key_seed, b->key_epoch, PN, i, key);
-                orc_pir_query(b->sub[i], 0, 0, tmp, key, orc_mix64(b->repl_seed, b->key_epoch * PN + i));
+                const uint64_t e = b->sub_epoch[i]++;
+                orc_derive_key(b->key_seed, e, PN, i, key);
+                orc_pir_preprocessing(b->sub[i], key, orc_mix64(b->repl_seed, e * PN + i), 1);
+            }
+            if (j >= cnt[i] || lists[i * n + j] == DEFAULT_VALUE) {
+                orc_pir_client_query(b->sub[i], 0, 0, tmp, NULL);
             } else {
                 uint64_t g = lists[i * n + j];
-                uint8_t key[16];
-                orc_derive_key(b->key_seed, b->key_epoch, PN, i, key);
-                int rc = orc_pir_query(b->sub[i], g - i * PS, 1, tmp, key, orc_mix64(b->repl_seed, b->key_epoch * PN + i));
+                int rc = orc_pir_client_query(b->sub[i], g - i * PS, 1, tmp, NULL);
                 uint64_t r = 0;
                 while (r < nresp && resp_key[r] != g) r++;
                 if (r == nresp) nresp++;

@@ -41,6 +41,8 @@ SIGNATURES = {
     "pm_last_error": (C.c_char_p, []),
     "pm_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "pm_launch_count": (C.c_uint64, []),
+    "pm_tuning_set": (C.c_int, [C.c_char_p, C.c_int]),
+    "pm_tuning_get": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "pm_db_create": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "pm_db_create_empty": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
     "pm_db_wrap": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
@@ -53,6 +55,13 @@ SIGNATURES = {
     "pm_buf_ipc_export": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pm_buf_ipc_open": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "pm_buf_ipc_close": (C.c_int, [C.c_void_p, C.c_int]),
+    "pm_buf_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
+    "pm_buf_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
+    "pm_buf_zero": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int]),
+    "pm_flag_signal_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "pm_flag_wait_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
+    "pm_host_register": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "pm_host_unregister": (C.c_int, [C.c_void_p]),
     "pm_expand_key": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pm_expand_key_batch": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_prf_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
@@ -142,6 +151,16 @@ def launch_count():
     return lib().pm_launch_count()
 
 
+def tuning_set(name, value):
+    check(lib().pm_tuning_set(name.encode(), int(value)))
+
+
+def tuning_get(name):
+    v = C.c_int()
+    check(lib().pm_tuning_get(name.encode(), C.byref(v)))
+    return v.value
+
+
 class DB:
     """pm_db handle: device-resident rows[n_rows][entry_u64] (rawDB, pianopir/pir.go:28-39)."""
 
@@ -208,6 +227,37 @@ def buf_ipc_open(handle, device=0):
 
 def buf_ipc_close(ptr, device=0):
     check(lib().pm_buf_ipc_close(ptr, device))
+
+
+def buf_upload(ptr, host, device=0):
+    host = np.ascontiguousarray(host)
+    check(lib().pm_buf_upload(ptr, _ptr(host), host.nbytes, device))
+
+
+def buf_download(ptr, host, device=0):
+    assert host.flags.c_contiguous
+    check(lib().pm_buf_download(_ptr(host), ptr, host.nbytes, device))
+    return host
+
+
+def buf_zero(ptr, nbytes, device=0):
+    check(lib().pm_buf_zero(ptr, nbytes, device))
+
+
+def flag_signal_dev(flag_ptr, device=0, stream=None):
+    check(lib().pm_flag_signal_dev(flag_ptr, device, stream))
+
+
+def flag_wait_dev(flags_ptr, n_flags, target, timeout_ms=10000, device=0, stream=None):
+    check(lib().pm_flag_wait_dev(flags_ptr, n_flags, target & 0xFFFFFFFF, timeout_ms, device, stream))
+
+
+def host_register(addr, nbytes):
+    check(lib().pm_host_register(addr, nbytes))
+
+
+def host_unregister(addr):
+    check(lib().pm_host_unregister(addr))
 
 
 def expand_key(key):

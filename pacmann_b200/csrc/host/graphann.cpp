@@ -91,7 +91,7 @@ void PIRGraphInfo::Preprocess() {
         PIR = new pianopir::SimpleBatchPianoPIR((uint64_t)N, DBEntryByteNum, (uint64_t)M, rawDB.data(), rawDB.size(), 8, device);
         std::vector<uint64_t>().swap(rawDB);  // the device copy is the server's DB from here on
     }
-    PIR->SetSeeds(Mix64(seed, 1), Mix64(seed, 2));
+    if (seed != 0) PIR->SetSeeds(Mix64(seed, 1), Mix64(seed, 2));   // test hook; otherwise the client keeps its CSPRNG secrets
     if (residentClient && !NonPrivateMode) {
         if (laneOf && laneOf->PIR) PIR->AttachResidentClient(laneOf->PIR, lane);   // a further lane of laneOf's client group
         else PIR->EnableResidentClient(groupLanes);
@@ -184,7 +184,7 @@ int PIRGraphInfo::GetStartVertex(std::vector<Vertex> *out) {
     std::vector<uint8_t> added((size_t)N, 0);
     out->resize(targetNum);
     uint64_t ctr = 0;
-    const uint64_t s = Mix64(seed, 3);
+    const uint64_t s = seed != 0 ? Mix64(seed, 3) : pianopir::SecureRandom64();
     for (int64_t i = 0; i < targetNum; i++) {
         int64_t x = (int64_t)(Mix64(s, ctr++) % (uint64_t)N);
         while (added[x]) x = (int64_t)(Mix64(s, ctr++) % (uint64_t)N);

@@ -57,9 +57,8 @@ PMH void pmh_pir_free(void *h) {
 static PianoPIR *as_pir(void *h, int boxed) { return boxed ? ((PirBox *)h)->pir : (PianoPIR *)h; }
 PMH void pmh_pir_set_seeds(void *h, int boxed, uint64_t key_seed, uint64_t epoch, uint64_t repl_seed) {
     auto &c = as_pir(h, boxed)->client;
-    c.keySeed = key_seed;
+    c.SetSeeds(key_seed, repl_seed);
     c.keyEpoch = epoch;
-    c.replSeed = repl_seed;
 }
 PMH int pmh_pir_preprocessing(void *h, int boxed) {
     PMH_TRY

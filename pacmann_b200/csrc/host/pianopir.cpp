@@ -2,6 +2,9 @@
 #include "pianopir.hpp"
 
 #include <immintrin.h>
+#include <sys/random.h>
+
+#include <cerrno>
 
 #include <atomic>
 #include <chrono>
@@ -32,9 +35,26 @@ uint64_t Mix64(uint64_t seed, uint64_t ctr) {
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
     return z ^ (z >> 31);
 }
-PrfKey DeriveKey(uint64_t key_seed, uint64_t epoch, uint64_t parts, uint64_t i) {
+// 64 bits from the OS CSPRNG (getrandom(2)): the default source of every client secret
+uint64_t SecureRandom64() {
+    uint64_t v = 0;
+    size_t got = 0;
+    while (got < sizeof(v)) {
+        ssize_t r = getrandom((char *)&v + got, sizeof(v) - got, 0);
+        if (r < 0) {
+            if (errno == EINTR) continue;
+            throw std::runtime_error("getrandom failed: no secure randomness for the client keys");
+        }
+        got += (size_t)r;
+    }
+    return v;
+}
+// PrfKey128 of sub-PIR i at its `epoch`-th preprocessing (the analogue of RandKey128's two rng.Uint64() draws,
+// util.go:25-31).  key_seed_hi = 0 with injected (test) seeds; otherwise the second 64 secret bits, so that a default
+// client's AES key carries 128 bits of OS entropy.
+PrfKey DeriveKey(uint64_t key_seed, uint64_t epoch, uint64_t parts, uint64_t i, uint64_t key_seed_hi) {
     PrfKey k;
-    uint64_t a = Mix64(key_seed, 2 * (epoch * parts + i)), b = Mix64(key_seed, 2 * (epoch * parts + i) + 1);
+    uint64_t a = Mix64(key_seed, 2 * (epoch * parts + i)), b = Mix64(key_seed ^ key_seed_hi, 2 * (epoch * parts + i) + 1);
     memcpy(k.b, &a, 8);
     memcpy(k.b + 8, &b, 8);
     return k;
@@ -179,6 +199,12 @@ static uint64_t primaryNumParam(double /*Q*/, double ChunkSize, uint64_t target)
 }
 
 PianoPIRClient::PianoPIRClient(const PianoPIRConfig *cfg) : config(cfg) {  // pir.go:130-175
+    // secrets come from the OS CSPRNG unless a test injects seeds (SetSeeds): the reference draws its key from a
+    // time-seeded rng in every Initialization (pir.go:208-211) and its dummy offsets from the global rng (pir.go:366)
+    keySeed = SecureRandom64();
+    keySeedHi = SecureRandom64();
+    replSeed = SecureRandom64();
+    dummySeed = SecureRandom64();
     MaxQueryNum = (uint64_t)(std::sqrt((double)cfg->DBSize) * std::log((double)cfg->DBSize));
     primaryHintNum = primaryNumParam((double)MaxQueryNum, (double)cfg->ChunkSize, cfg->FailureProbLog2 + 1);
     primaryHintNum = (primaryHintNum + cfg->ThreadNum - 1) / cfg->ThreadNum * cfg->ThreadNum;
@@ -197,7 +223,10 @@ double PianoPIRClient::LocalStorageSize() const {
 
 void PianoPIRClient::Initialization() {
     FinishedQueryNum = 0;
-    masterKey = DeriveKey(keySeed, keyEpoch, keyParts, keyIndex);
+    // a fresh key for EVERY preprocessing of this client (pir.go:208-211), also the budget-triggered ones: the epoch
+    // advances here, so no hint table is ever rebuilt under a key that has already been shown to the server
+    prepEpoch = keyEpoch++;
+    masterKey = DeriveKey(keySeed, prepEpoch, keyParts, keyIndex, keySeedHi);
     longKey = GetLongKey(masterKey);
     const uint64_t S = config->SetSize, M = maxQueryPerChunk, E = config->DBEntrySize, P = primaryHintNum;
     QueryHistogram.assign(S, 0);
@@ -213,6 +242,16 @@ void PianoPIRClient::Initialization() {
     for (uint64_t i = 0; i < S * M; i++) backupShortTag[i] = shortTagCount++;
     localCache.Init(E);
     pendingCached.clear();
+}
+
+// Deterministic seeds: the explicit TEST hook (parity against the oracle needs the same keys on both sides).  The dummy
+// stream is derived from the client's own secret seed and index, never from a public constant.
+void PianoPIRClient::SetSeeds(uint64_t key_seed, uint64_t repl_seed) {
+    const uint64_t ds = Mix64(Mix64(key_seed, 0xD00D), keyIndex);
+    if (ds != dummySeed) { dummySeed = ds; dummyCtr = 0; }
+    keySeed = key_seed;
+    keySeedHi = 0;
+    replSeed = repl_seed;
 }
 
 void PianoPIRClient::FillHintJob(uint64_t row0, pm_hint_job *job, uint64_t *parity_out) const {
@@ -234,7 +273,7 @@ void PianoPIRClient::FillHintJob(uint64_t row0, pm_hint_job *job, uint64_t *pari
 // replacement indices for every (chunk, slot): pir.go:345-347 with a counter-based draw
 void PianoPIRClient::DrawReplacementIdx(std::vector<uint64_t> *local_idx) {
     const uint64_t S = config->SetSize, M = maxQueryPerChunk, C = config->ChunkSize;
-    const uint64_t seed = Mix64(replSeed, keyEpoch * keyParts + keyIndex);
+    const uint64_t seed = Mix64(replSeed, prepEpoch * keyParts + keyIndex);
     local_idx->resize(S * M);
     for (uint64_t c = 0; c < S; c++)
         for (uint64_t j = 0; j < M; j++) {
@@ -421,7 +460,6 @@ void SimpleBatchPianoPIR::Init(uint64_t DBSize, uint64_t DBEntryByteNum, uint64_
         PianoPIR *p = new PianoPIR(end - start, DBEntryByteNum, db, start, FailureProbLog2);
         p->client.keyParts = config.PartitionNum;
         p->client.keyIndex = i;
-        p->client.dummySeed = Mix64(0xD00D, i);
         subPIR.push_back(p);
     }
 }
@@ -435,10 +473,7 @@ SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
     if (ownsDB) delete db;
 }
 void SimpleBatchPianoPIR::SetSeeds(uint64_t keySeed, uint64_t replSeed) {
-    for (auto *p : subPIR) {
-        p->client.keySeed = keySeed;
-        p->client.replSeed = replSeed;
-    }
+    for (auto *p : subPIR) p->client.SetSeeds(keySeed, replSeed);
 }
 
 std::string SimpleBatchPianoPIR::PrintInfo() const {  // batch-pir.go:95-108
@@ -477,7 +512,6 @@ void SimpleBatchPianoPIR::Preprocessing() {
         std::vector<uint32_t> ids(PN);
         for (uint64_t i = 0; i < PN; i++) ids[i] = (uint32_t)i;
         PreprocessResident(ids, false);
-        for (auto *p : subPIR) p->client.keyEpoch += 1;
         RecordStats(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
         return;
     }
@@ -506,8 +540,6 @@ void SimpleBatchPianoPIR::Preprocessing() {
     check(pm_gather_rows(db->h, 0, config.DBSize, gidx.data(), gidx.size(), vals.data()), "pm_gather_rows");
     for (uint64_t i = 0; i < PN; i++)
         memcpy(subPIR[i]->client.replacementVal.data(), vals.data() + base[i] * E, (base[i + 1] - base[i]) * E * 8);
-    // next (re)preprocessing of any sub-PIR draws the next epoch's key
-    for (auto *p : subPIR) p->client.keyEpoch += 1;
     double prepTime = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     RecordStats(prepTime);
 }
@@ -517,14 +549,11 @@ void SimpleBatchPianoPIR::DummyPreprocessing() {  // batch-pir.go:157-166
         std::vector<uint32_t> ids(config.PartitionNum);
         for (uint64_t i = 0; i < config.PartitionNum; i++) ids[i] = (uint32_t)i;
         PreprocessResident(ids, true);
-        for (auto *p : subPIR) { p->client.skipPrep = true; p->client.keyEpoch += 1; }
+        for (auto *p : subPIR) p->client.skipPrep = true;
         RecordStats(0);
         return;
     }
-    for (auto *p : subPIR) {
-        p->DummyPreprocessing();
-        p->client.keyEpoch += 1;
-    }
+    for (auto *p : subPIR) p->DummyPreprocessing();
     RecordStats(0);
 }
 
@@ -800,11 +829,12 @@ void SimpleBatchPianoPIR::PreprocessResident(const std::vector<uint32_t> &ids, b
     for (size_t a = 0; a < ids.size(); a++) {
         PianoPIRClient &c = subPIR[ids[a]]->client;
         c.FinishedQueryNum = 0;
-        c.masterKey = DeriveKey(c.keySeed, c.keyEpoch, c.keyParts, c.keyIndex);
+        c.prepEpoch = c.keyEpoch++;   // a fresh key per preprocessing, as in Initialization()
+        c.masterKey = DeriveKey(c.keySeed, c.prepEpoch, c.keyParts, c.keyIndex, c.keySeedHi);
         memcpy(&keys[a * 16], c.masterKey.b, 16);
         c.localCache.Init(config.DBEntrySize);
         c.pendingCached.clear();
-        seeds[a] = Mix64(c.replSeed, c.keyEpoch * c.keyParts + c.keyIndex);
+        seeds[a] = Mix64(c.replSeed, c.prepEpoch * c.keyParts + c.keyIndex);
     }
     check(pm_expand_key_batch(keys.data(), ids.size(), rk.data()), "pm_expand_key_batch");  // GetLongKey for every sub-PIR
     for (size_t a = 0; a < ids.size(); a++) subPIR[ids[a]]->client.longKey.assign(rk.begin() + a * 44, rk.begin() + (a + 1) * 44);
@@ -858,6 +888,8 @@ void SimpleBatchPianoPIR::beginCall(const uint64_t *idx, size_t n, bool *bad) {
     wsQueries.clear();
     wsZero.assign(E, 0);
     wsPendingReal.assign(PN, 0);
+    wsCached.resize(n * E);   // sized up front: the pointers handed out below must stay valid for the whole call
+    wsCachedUsed = 0;
 }
 
 // one sub-query of partition `part` (batch-pir.go:189-216 / pir.go:354-383): a dummy, a local-cache hit, or a record for the GPU
@@ -892,7 +924,14 @@ void SimpleBatchPianoPIR::settle(size_t pbase, const uint64_t *res, const int32_
         PianoPIRClient &c = subPIR[pd.part]->client;
         if (pd.kind == 0) { serverQueries += 1; continue; }
         if (pd.kind == 2) {  // served from the local cache (pir.go:381-383); an earlier failure of the same index repeats as zeros
+            // copied out of the cache: a budget-triggered re-preprocessing later in this call clears the cache and
+            // reuses its slabs, and out_ptrs callers keep these pointers until the lane's next call
             const uint64_t *e = c.localCache.find(pd.local);
+            if (e) {
+                uint64_t *dst = wsCached.data() + (wsCachedUsed++) * E;
+                memcpy(dst, e, E * 8);
+                e = dst;
+            }
             wsResponses.put(pd.global, wsRespList.size());
             wsRespList.push_back(Resp{e ? e : wsZero.data(), kNaN});
             continue;

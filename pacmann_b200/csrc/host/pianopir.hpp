@@ -35,7 +35,8 @@ using PrfKey = PrfKey128;
 
 // counter-based stand-in for the reference's time-seeded math/rand draws (see pacmann_b200/keys.py)
 uint64_t Mix64(uint64_t seed, uint64_t ctr);
-PrfKey DeriveKey(uint64_t key_seed, uint64_t epoch, uint64_t parts, uint64_t i);
+PrfKey DeriveKey(uint64_t key_seed, uint64_t epoch, uint64_t parts, uint64_t i, uint64_t key_seed_hi = 0);
+uint64_t SecureRandom64();   // OS CSPRNG (getrandom)
 
 // util.go
 std::vector<uint32_t> GetLongKey(const PrfKey128 &key);                                   // :167-171 (GPU)
@@ -154,9 +155,11 @@ public:
     // [SetSize][maxQueryPerChunk(*E)] flattened (the Go code uses slices of slices, pir.go:113-118)
     std::vector<uint64_t> replacementIdx, replacementVal, backupShortTag, backupParity;
     EntryCache localCache;
-    // deterministic randomness (injected; the reference uses time-seeded rngs)
-    uint64_t keySeed = 1, keyEpoch = 0, keyIndex = 0, keyParts = 1, replSeed = 0, dummySeed = 0xD00D, dummyCtr = 0;
-    uint64_t replEpoch = 0;
+    // Client secrets.  Drawn from the OS CSPRNG in the constructor (128 key-seed bits); SetSeeds() injects deterministic
+    // values for the parity tests.  keyEpoch counts this client's preprocessings: every Initialization() derives a
+    // fresh key from (seed, epoch, index) and advances it; prepEpoch = the epoch of the current hint table.
+    void SetSeeds(uint64_t key_seed, uint64_t repl_seed);
+    uint64_t keySeed = 0, keySeedHi = 0, keyEpoch = 0, prepEpoch = 0, keyIndex = 0, keyParts = 1, replSeed = 0, dummySeed = 0, dummyCtr = 0;
     std::vector<uint64_t> pendingCached;  // idx prepared in the current batch whose value arrives at Finish
 };
 
@@ -242,7 +245,8 @@ private:
     std::vector<std::vector<uint64_t>> wsLists;   // per-call scratch, kept to avoid reallocation
     std::vector<PendRec> wsPend;
     std::vector<pm_client_query> wsQueries;
-    std::vector<uint64_t> wsOut, wsZero, wsSolo;
+    std::vector<uint64_t> wsOut, wsZero, wsSolo, wsCached;
+    size_t wsCachedUsed = 0;
     std::vector<int32_t> wsStatus;
     std::vector<float> wsDist;
     struct Resp { const uint64_t *entry; float dist; };

@@ -137,18 +137,81 @@ __device__ __forceinline__ uint32_t prf_low(const AesTab<NTAB> &T, const RK &rk,
 // prf_rounds<.., RA, RB> runs AES rounds RA..RB (1-based; 10 = final round + feed-forward) on `st`, so the hint
 // kernel can interleave slices of the next group's PRF with the row loads of the current group.  After round 10
 // st.s0 holds what prf_low() returns.  Identical arithmetic, different schedule.
+//
+// XB = number of low bytes of x (the chunk id) that can be non-zero: 1 for SetSize <= 256 (the MS-MARCO and SIFT
+// partitions: 196 / 124 chunks), 2 up to 65536 (pir_test's 2^20 rows: 512), 4 = no assumption.  The constant bytes
+// of word 0 join the per-hint part, and so does every term of round 2
+// that only reads constant columns of the round-1 state:
+//   XB = 4:  rounds 1-2 cost 4 + 16 lookups per evaluation  (state after round 1 = g ^ X(x), all four columns vary)
+//   XB = 2:  columns 0 and 3 vary                ->  2 +  8
+//   XB = 1:  only column 0 varies                ->  1 +  4      (111 lookups per PRF instead of 126)
+// Bit-identical to the generic path (tests: test_hintgen_low_bits_path_equals_full_prf, hg_xbytes knob sweeps).
 struct PrfState { uint32_t s0, s1, s2, s3; };
 
-template <int NTAB, int NB, int RA, int RB, typename RK>
-__device__ __forceinline__ void prf_rounds(const AesTab<NTAB> &T, const RK &rk, const PrfTagPart &g, uint32_t x, PrfState &st) {
+template <int XB> struct PrfHint;
+template <> struct PrfHint<4> { uint32_t g0, g1, g2, g3; };          // round-1 state without the x terms
+template <> struct PrfHint<2> { uint32_t g0, g3, h0, h1, h2, h3; };  // varying columns of round 1 + constant part of round 2
+template <> struct PrfHint<1> { uint32_t g0, h0, h1, h2, h3; };
+
+template <int XB, int NTAB, typename RK>
+__device__ __forceinline__ PrfHint<XB> prf_hint_part(const AesTab<NTAB> &T, const RK &rk, uint64_t tag) {
+    const uint32_t w0 = rk[0], w1 = (uint32_t)(tag << 3) ^ rk[1], w2 = rk[2], w3 = rk[3];
+    uint32_t g0 = T.t1(byte_of(w1, 1)) ^ T.t2(byte_of(w2, 2)) ^ T.t3(byte_of(w3, 3)) ^ rk[4];
+    uint32_t g1 = T.t0(byte_of(w1, 0)) ^ T.t1(byte_of(w2, 1)) ^ T.t2(byte_of(w3, 2)) ^ rk[5];
+    uint32_t g2 = T.t3(byte_of(w1, 3)) ^ T.t0(byte_of(w2, 0)) ^ T.t1(byte_of(w3, 1)) ^ rk[6];
+    uint32_t g3 = T.t2(byte_of(w1, 2)) ^ T.t0(byte_of(w3, 0)) ^ T.t3(byte_of(w2, 3)) ^ rk[7];
+    PrfHint<XB> g;
+    if constexpr (XB == 4) {
+        g.g0 = g0; g.g1 = g1; g.g2 = g2; g.g3 = g3;
+    } else {
+        g1 ^= T.t3(byte_of(w0, 3));   // bytes 2 and 3 of x are zero: word 0 contributes key bytes only
+        g2 ^= T.t2(byte_of(w0, 2));
+        if constexpr (XB == 1) g3 ^= T.t1(byte_of(w0, 1));
+        g.g0 = g0;
+        if constexpr (XB == 2) {
+            g.g3 = g3;
+            g.h0 = T.t1(byte_of(g1, 1)) ^ T.t2(byte_of(g2, 2)) ^ rk[8];
+            g.h1 = T.t0(byte_of(g1, 0)) ^ T.t1(byte_of(g2, 1)) ^ rk[9];
+            g.h2 = T.t0(byte_of(g2, 0)) ^ T.t3(byte_of(g1, 3)) ^ rk[10];
+            g.h3 = T.t2(byte_of(g1, 2)) ^ T.t3(byte_of(g2, 3)) ^ rk[11];
+        } else {
+            g.h0 = T.t1(byte_of(g1, 1)) ^ T.t2(byte_of(g2, 2)) ^ T.t3(byte_of(g3, 3)) ^ rk[8];
+            g.h1 = T.t0(byte_of(g1, 0)) ^ T.t1(byte_of(g2, 1)) ^ T.t2(byte_of(g3, 2)) ^ rk[9];
+            g.h2 = T.t0(byte_of(g2, 0)) ^ T.t1(byte_of(g3, 1)) ^ T.t3(byte_of(g1, 3)) ^ rk[10];
+            g.h3 = T.t0(byte_of(g3, 0)) ^ T.t2(byte_of(g1, 2)) ^ T.t3(byte_of(g2, 3)) ^ rk[11];
+        }
+    }
+    return g;
+}
+
+template <int XB, int NTAB, int NB, int RA, int RB, typename RK>
+__device__ __forceinline__ void prf_rounds(const AesTab<NTAB> &T, const RK &rk, const PrfHint<XB> &g, uint32_t x, PrfState &st) {
 #pragma unroll
     for (int r = RA; r <= RB; r++) {
         if (r == 1) {
-            uint32_t w0 = x ^ rk[0];
+            const uint32_t w0 = x ^ rk[0];
             st.s0 = g.g0 ^ T.t0(byte_of(w0, 0));
-            st.s1 = g.g1 ^ T.t3(byte_of(w0, 3));
-            st.s2 = g.g2 ^ T.t2(byte_of(w0, 2));
-            st.s3 = g.g3 ^ T.t1(byte_of(w0, 1));
+            if constexpr (XB == 4) {
+                st.s1 = g.g1 ^ T.t3(byte_of(w0, 3));
+                st.s2 = g.g2 ^ T.t2(byte_of(w0, 2));
+                st.s3 = g.g3 ^ T.t1(byte_of(w0, 1));
+            } else if constexpr (XB == 2) {
+                st.s3 = g.g3 ^ T.t1(byte_of(w0, 1));
+            }
+        } else if (r == 2 && XB != 4) {
+            const uint32_t s0 = st.s0;
+            if constexpr (XB == 2) {
+                const uint32_t s3 = st.s3;
+                st.s0 = g.h0 ^ T.t0(byte_of(s0, 0)) ^ T.t3(byte_of(s3, 3));
+                st.s1 = g.h1 ^ T.t3(byte_of(s0, 3)) ^ T.t2(byte_of(s3, 2));
+                st.s2 = g.h2 ^ T.t2(byte_of(s0, 2)) ^ T.t1(byte_of(s3, 1));
+                st.s3 = g.h3 ^ T.t1(byte_of(s0, 1)) ^ T.t0(byte_of(s3, 0));
+            } else if constexpr (XB == 1) {
+                st.s0 = g.h0 ^ T.t0(byte_of(s0, 0));
+                st.s1 = g.h1 ^ T.t3(byte_of(s0, 3));
+                st.s2 = g.h2 ^ T.t2(byte_of(s0, 2));
+                st.s3 = g.h3 ^ T.t1(byte_of(s0, 1));
+            }
         } else if (r < 9) {
             aes_round(T, st.s0, st.s1, st.s2, st.s3, rk[4 * r], rk[4 * r + 1], rk[4 * r + 2], rk[4 * r + 3]);
         } else if (r == 9) {
@@ -166,11 +229,13 @@ __device__ __forceinline__ void prf_rounds(const AesTab<NTAB> &T, const RK &rk, 
         }
     }
 }
-// rounds of phase PH when the 10 rounds are cut into NPH slices
-template <int PH, int NPH>
+// rounds of phase PH when the 10 rounds are cut into NPH slices.  With hoisted rounds 1-2 (XB < 4) the four-slice cut
+// is 1-3 | 4-5 | 6-7 | 8-10 (21..32 lookups each) instead of 1-2 | 3-5 | 6-7 | 8-10.
+template <int PH, int NPH, int XB>
 struct PrfPhase {
-    static constexpr int first = PH * 10 / NPH + 1;
-    static constexpr int last = (PH + 1) * 10 / NPH;
+    static constexpr int cut(int i) { return (NPH == 4 && XB != 4) ? (i == 0 ? 0 : i == 1 ? 3 : i == 2 ? 5 : i == 3 ? 7 : 10) : i * 10 / NPH; }
+    static constexpr int first = cut(PH) + 1;
+    static constexpr int last = cut(PH + 1);
 };
 
 }  // namespace pm

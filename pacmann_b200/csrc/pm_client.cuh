@@ -121,14 +121,15 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
                                                                     const uint32_t *part_start, const uint32_t *part_items,
                                                                     uint32_t q, uint32_t stride, uint32_t *offsets,
                                                                     ClientMeta *meta, uint64_t *a_row0, uint64_t *a_nrows,
-                                                                    uint32_t *a_chunk, uint32_t *a_set) {
+                                                                    uint32_t *a_chunk, uint32_t *a_set, uint32_t mirror) {
     extern __shared__ uint32_t smem[];
     const uint32_t NT = blockDim.x;
     uint32_t *s_tab = smem;                           // compact Te0 (4 KB): few PRFs here, the shared memory buys occupancy
     uint32_t *s_rk = smem + aes_tab_words<8>();       // 44 round-key words
     uint32_t *s_offs = s_rk + 64;                     // [stride]
     uint32_t *s_list = s_offs + stride;               // [CL_MAX_LIST]
-    uint32_t *s_pp = s_list + CL_MAX_LIST;            // [P] program points (only when the offset index is in use)
+    uint32_t *s_pp = s_list + CL_MAX_LIST;            // [P] program points (offset index in use and `mirror`: they fit in shared
+                                                      // memory; pir_test's 2^20-row instance has P = 59392 and reads pp32 instead)
     __shared__ uint32_t s_hit;
     __shared__ int s_status;
     __shared__ uint64_t s_ingroup, s_newtag, s_fin;
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     aes_tab_fill<8>(s_tab, c_te0);
     if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
     const bool indexed = D.poff != nullptr;
-    if (indexed) {   // values < 2^31 or 0x7fffffff; s_pp is 16-byte aligned (every region before it is a multiple of 4 words)
+    if (indexed && mirror) {   // values < 2^31 or 0x7fffffff; s_pp is 16-byte aligned (every region before it is a multiple of 4 words)
         const uint4 *src = reinterpret_cast<const uint4 *>(D.pp32);
         uint4 *dst = reinterpret_cast<uint4 *>(s_pp);
         for (uint64_t i = threadIdx.x; i < P / 4; i += NT) dst[i] = __ldcg(src + i);
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             const uint16_t *col = D.poff + chunkId * P;
             auto consider = [&](uint64_t i, uint32_t v) {
                 if (v == (uint32_t)offset) {
-                    const uint32_t pp = s_pp[i];
+                    const uint32_t pp = mirror ? s_pp[i] : __ldcg(D.pp32 + i);
                     if (pp == (uint32_t)kDefaultProgramPoint || pp / C != chunkId) atomicMin(&s_hit, (uint32_t)i);
                 }
             };
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         if (threadIdx.x == 0) {
             ridx = D.ridx[slot];
             btag = D.btags[slot];
-            pp_hit = indexed ? (uint64_t)s_pp[hit] : D.pp[hit];
+            pp_hit = indexed ? (uint64_t)(mirror ? s_pp[hit] : __ldcg(D.pp32 + hit)) : D.pp[hit];
         }
         if (indexed) {
             for (uint32_t c = threadIdx.x; c < S; c += NT) s_offs[c] = __ldcg(D.poff + (uint64_t)c * P + hit);
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             D.tags[hit] = btag;
             D.pp[hit] = Q.idx;
             D.pp32[hit] = (uint32_t)Q.idx;
-            if (indexed) s_pp[hit] = (uint32_t)Q.idx;
+            if (indexed && mirror) s_pp[hit] = (uint32_t)Q.idx;
             *D.finished = s_fin + 1;
             D.hist[chunkId] = inGroup + 1;
             s_newtag = btag;
@@ -658,15 +659,19 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     mark(1);
     uint64_t max_p = 0;
     for (uint64_t i = 0; i < c->n_parts; i++) if (c->host_parts[i].poff) max_p = std::max<uint64_t>(max_p, c->host_parts[i].n_primary);
-    const size_t smem = (aes_tab_words<8>() + 64 + stride + CL_MAX_LIST + max_p) * 4;
-    if (smem > 200 * 1024) return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: primaryHintNum too large for the shared-memory mirror");
+    // the program points are mirrored in shared memory when they fit; larger instances (P = 59392 for 2^20 rows) read the
+    // u32 copy in global memory on the few offset matches of a column scan instead
+    const size_t smem_base = (aes_tab_words<8>() + 64 + stride + CL_MAX_LIST) * 4;
+    const uint32_t mirror = smem_base + max_p * 4 <= 200 * 1024 ? 1u : 0u;
+    const size_t smem = smem_base + (mirror ? max_p * 4 : 0);
+    if (smem > 200 * 1024) return set_error(PM_ERR_UNSUPPORTED, "pm_client_query_batch: set_size too large for the prepare kernel's shared memory");
     PM_CUDA(cudaFuncSetAttribute(client_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // 512-thread CTAs (2 per SM by registers) give the shortest call for one client (16 parts: 37 vs 48 us); clients
     // that carry a lock-step group run 256-thread CTAs (4 per SM): more parts -- of this call and of the other groups'
     // concurrent calls -- are resident at once (measured: one 32-lane group 139 -> 116 us, 4 x 16 lanes +5 % queries/s)
     const unsigned prep_threads = c->n_parts <= 64 ? CL_THREADS : CL_THREADS / 2;
     client_prepare_kernel<<<(unsigned)c->n_parts, prep_threads, smem, c->stream>>>(c->d_parts, d_q, d_start, d_items, (uint32_t)q, (uint32_t)stride,
-                                                                                  d_off, d_meta, d_row0, d_nrows, d_chunk, d_set);
+                                                                                  d_off, d_meta, d_row0, d_nrows, d_chunk, d_set, mirror);
     PM_CHECK_LAUNCH();
     count_launch();
     mark(2);

@@ -32,6 +32,9 @@ struct pm_db {
 namespace pm {
 
 int set_error(int code, const char *fmt, ...);
+// launch-time tuning knobs (pm_tuning_set / environment), see pm_core.cu
+enum Tune { T_HG_SYNC, T_HG_WARPS, T_HG_NTAB, T_HG_TAIL_SPLIT, T_HG_SERPENTINE, T_HG_XBYTES, T_ANS_SPLIT, T_HG_D2H_GROUPS, T_COUNT };
+int tune(Tune t);
 void count_launch(uint64_t n = 1);
 int ensure_device(int device);  // cudaSetDevice + one-time table upload; returns PM_OK / error
 int sm_count(int device);
@@ -77,6 +80,24 @@ __device__ __forceinline__ uint2 ldg_stream(const uint2 *p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
     return v;
 }
+// predicated form: zeros when !pred, and no access at all
+__device__ __forceinline__ uint4 ldg_row(const uint4 *p, bool pred) {
+    uint4 v;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\tmov.u32 %3, 0;\n\t"
+        "@p ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
+        : "=&r"(v.x), "=&r"(v.y), "=&r"(v.z), "=&r"(v.w)
+        : "l"(p), "r"((uint32_t)pred));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_row(const uint2 *p, bool pred) {
+    uint2 v;
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\t"
+        "@p ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n\t}"
+        : "=&r"(v.x), "=&r"(v.y)
+        : "l"(p), "r"((uint32_t)pred));
+    return v;
+}
+
 __device__ __forceinline__ void vxor(uint4 &a, const uint4 &b) { a.x ^= b.x; a.y ^= b.y; a.z ^= b.z; a.w ^= b.w; }
 __device__ __forceinline__ void vxor(uint2 &a, const uint2 &b) { a.x ^= b.x; a.y ^= b.y; }
 __device__ __forceinline__ void vzero(uint4 &a) { a = make_uint4(0, 0, 0, 0); }

@@ -1,4 +1,5 @@
 // Handle management, error reporting and device initialisation for libpacmann_cuda.so.
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -21,6 +22,30 @@ int set_error(int code, const char *fmt, ...) {
     return code;
 }
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- launch-time tuning knobs ---------------------------------------------------------------------------------
+// Every launch heuristic that the parity tests must be able to force (the benchmarked variants included) is a knob
+// here: read at every launch, initialised once from the environment (PM_HG_SYNC, ...), changed with pm_tuning_set().
+struct TuneKnob { const char *name, *env; int dflt; std::atomic<int> value; std::atomic<bool> init; };
+static TuneKnob g_knobs[T_COUNT] = {
+    {"hg_sync", "PM_HG_SYNC", -1, {0}, {false}},       // round barrier of the hint kernel: -1 auto, 0 off, 1 on
+    {"hg_warps", "PM_HG_WARPS", 0, {0}, {false}},      // CTA width of the hint kernel in warps: 0 auto, 1..16
+    {"hg_ntab", "PM_HG_NTAB", 0, {0}, {false}},        // AES T-tables in shared memory: 0 auto, 1, 4
+    {"hg_tail_split", "PM_HG_TAIL_SPLIT", -1, {0}, {false}},   // last partial round shared by all CTAs (stream-K): -1 auto (on), 0 off, 1 on
+    {"hg_serpentine", "PM_HG_SERPENTINE", 1, {0}, {false}},   // alternate the sweep direction between rounds: 0 off, 1 on
+    {"hg_xbytes", "PM_HG_XBYTES", 0, {0}, {false}},    // varying chunk-id bytes assumed by the hoisted PRF rounds: 0 auto, 1, 2, 4
+    {"ans_split", "PM_ANS_SPLIT", 0, {0}, {false}},    // CTAs per sub-query of the answer kernel: 0 auto, 1..8
+    {"hg_d2h_groups", "PM_HG_D2H_GROUPS", 0, {0}, {false}},   // launch groups of the host-buffer pm_hintgen: 0 auto, 1..16
+};
+int tune(Tune t) {
+    TuneKnob &k = g_knobs[t];
+    if (!k.init.load(std::memory_order_acquire)) {
+        const char *v = getenv(k.env);
+        k.value.store(v && *v ? atoi(v) : k.dflt, std::memory_order_relaxed);
+        k.init.store(true, std::memory_order_release);
+    }
+    return k.value.load(std::memory_order_relaxed);
+}
 
 constexpr int MAX_DEV = 64;
 static std::mutex g_dev_mu;
@@ -124,6 +149,26 @@ using namespace pm;
 PM_EXPORT const char *pm_version(void) { return "pacmann-b200 0.1 (sm_100a)"; }
 PM_EXPORT const char *pm_last_error(void) { return t_err; }
 PM_EXPORT uint64_t pm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+PM_EXPORT int pm_tuning_set(const char *name, int value) {
+    if (!name) return set_error(PM_ERR_ARG, "pm_tuning_set: null name");
+    for (int t = 0; t < T_COUNT; t++)
+        if (!strcmp(name, g_knobs[t].name)) {
+            g_knobs[t].value.store(value, std::memory_order_relaxed);
+            g_knobs[t].init.store(true, std::memory_order_release);
+            return PM_OK;
+        }
+    return set_error(PM_ERR_ARG, "pm_tuning_set: unknown knob '%s'", name);
+}
+PM_EXPORT int pm_tuning_get(const char *name, int *value) {
+    if (!name || !value) return set_error(PM_ERR_ARG, "pm_tuning_get: null pointer");
+    for (int t = 0; t < T_COUNT; t++)
+        if (!strcmp(name, g_knobs[t].name)) {
+            *value = tune((Tune)t);
+            return PM_OK;
+        }
+    return set_error(PM_ERR_ARG, "pm_tuning_get: unknown knob '%s'", name);
+}
 
 PM_EXPORT int pm_device_count(int *count) {
     if (!count) return set_error(PM_ERR_ARG, "pm_device_count: null pointer");
@@ -294,5 +339,88 @@ PM_EXPORT int pm_buf_ipc_close(void *dev_ptr, int device) {
     int rc = ensure_device(device);
     if (rc) return rc;
     PM_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return PM_OK;
+}
+
+PM_EXPORT int pm_buf_upload(void *dev_ptr, const void *host, uint64_t bytes, int device) {
+    if (bytes && (!dev_ptr || !host)) return set_error(PM_ERR_ARG, "pm_buf_upload: null pointer");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    if (bytes) PM_CUDA(cudaMemcpy(dev_ptr, host, bytes, cudaMemcpyHostToDevice));
+    return PM_OK;
+}
+PM_EXPORT int pm_buf_download(void *host, const void *dev_ptr, uint64_t bytes, int device) {
+    if (bytes && (!dev_ptr || !host)) return set_error(PM_ERR_ARG, "pm_buf_download: null pointer");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    if (bytes) PM_CUDA(cudaMemcpy(host, dev_ptr, bytes, cudaMemcpyDeviceToHost));
+    return PM_OK;
+}
+PM_EXPORT int pm_buf_zero(void *dev_ptr, uint64_t bytes, int device) {
+    if (bytes && !dev_ptr) return set_error(PM_ERR_ARG, "pm_buf_zero: null pointer");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    if (bytes) PM_CUDA(cudaMemset(dev_ptr, 0, bytes));
+    return PM_OK;
+}
+PM_EXPORT int pm_host_register(void *host, uint64_t bytes) {
+    if (!host || !bytes) return set_error(PM_ERR_ARG, "pm_host_register: null pointer");
+    int rc = ensure_device(-1);
+    if (rc) return rc;
+    PM_CUDA(cudaHostRegister(host, bytes, cudaHostRegisterPortable));
+    return PM_OK;
+}
+PM_EXPORT int pm_host_unregister(void *host) {
+    if (!host) return PM_OK;
+    PM_CUDA(cudaHostUnregister(host));
+    return PM_OK;
+}
+
+// ---- completion flags in (peer-mapped) device memory ---------------------------------------------------------------
+// The exchange step of multi-GPU hint generation: every rank's kernel stores its parities straight into the consumer's
+// table over NVLink; what is left of a "gather" is telling the consumer that the stores have landed.  A rank signals by
+// adding 1 to a counter in the consumer's memory (system-scope release, stream-ordered behind its hint kernel); the
+// consumer's stream waits until the counter reaches the expected epoch value.  No NCCL call, no host round trip.
+namespace pm {
+__global__ void flag_signal_kernel(unsigned int *flag) {
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(flag) : "memory");
+}
+// thread i waits for flags[32*i] (one 128-byte line per signalling rank: a fast rank running ahead cannot stand in for a
+// slow one); a timeout is reported in flags[32*n] and the stream goes on -- never hang the GPU
+__global__ void flag_wait_kernel(unsigned int *flags, unsigned int target, unsigned long long timeout_ns) {
+    unsigned int *flag = flags + 32 * threadIdx.x, *timed_out = flags + 32 * blockDim.x;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned int seen;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+        if ((int)(seen - target) >= 0) return;
+        __nanosleep(200);
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > timeout_ns) {
+            *timed_out = 1;
+            return;
+        }
+    }
+}
+}  // namespace pm
+PM_EXPORT int pm_flag_signal_dev(void *flag, int device, void *stream) {
+    if (!flag) return set_error(PM_ERR_ARG, "pm_flag_signal_dev: null pointer");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    flag_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned int *)flag);
+    PM_CHECK_LAUNCH();
+    count_launch();
+    return PM_OK;
+}
+PM_EXPORT int pm_flag_wait_dev(void *flags, uint32_t n_flags, uint32_t target, uint32_t timeout_ms, int device, void *stream) {
+    if (!flags || n_flags == 0 || n_flags > 1024) return set_error(PM_ERR_ARG, "pm_flag_wait_dev: bad argument");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    flag_wait_kernel<<<1, n_flags, 0, (cudaStream_t)stream>>>((unsigned int *)flags, target, (unsigned long long)timeout_ms * 1000000ull);
+    PM_CHECK_LAUNCH();
+    count_launch();
     return PM_OK;
 }

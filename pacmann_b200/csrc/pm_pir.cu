@@ -9,6 +9,7 @@
 #include <cooperative_groups.h>
 
 #include "pm_common.cuh"
+#include "pm_hg_params.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -45,6 +46,8 @@ int upload_tables() {  // called once per device from ensure_device()
     uint32_t te0[256];
     build_te0(te0);
     PM_CUDA(cudaMemcpyToSymbol(c_te0, te0, sizeof(te0)));
+    int rc;   // the hint kernel's translation units keep their own copy
+    if ((rc = hg_upload_tables_a(te0)) || (rc = hg_upload_tables_b(te0)) || (rc = hg_upload_tables_c(te0))) return rc;
     return PM_OK;
 }
 
@@ -92,194 +95,6 @@ __global__ void __launch_bounds__(256) prf_batch_kernel(const __grid_constant__ 
         uint32_t s0 = in0, s1 = in1, s2 = 0, s3 = 0;
         aes128_encrypt<1>(T, R, s0, s1, s2, s3);
         out[i] = (uint64_t)(s0 ^ in0) | ((uint64_t)(s1 ^ in1) << 32);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// A5/A7 hint generation
-// ---------------------------------------------------------------------------------------------
-// Hint-stationary: a group of G lanes owns one hint and keeps its parity in registers across all
-// set_size chunks; each lane of the group evaluates the PRF for a different chunk (G chunks per
-// step, all 32 lanes of the warp busy in AES), offsets are exchanged by shuffle, and the G lanes
-// then read the selected row together (G*16 contiguous bytes per load instruction, whole 128-byte
-// lines for G = 8).  Parities are written once.  CTAs walk tiles in a static round-robin so that
-// all resident CTAs sweep the same DB slice chunk 0..S-1 at the same pace: each chunk is pulled
-// from HBM once and re-hit in L2 by the other ~H'/ChunkSize hints that select rows of it.
-constexpr int HG_THREADS = 512;        // default CTA width (16 warps); the width is chosen per launch: 12..16 warps
-constexpr int HG_MAX_THREADS = 512;    // wider CTAs would cap the kernel below the 128 registers it needs (spills)
-constexpr int HG_MAX_JOBS = 16;
-
-struct HintJobDev {
-    uint32_t rk[44];
-    uint64_t row0, n_rows;
-    uint64_t hint_begin, n_hints, n_primary, backup_group;
-    const uint64_t *tags;
-    const int32_t *skip;
-    uint64_t *out;
-    uint32_t chunk_mask, chunk_shift, set_size, tile_begin;
-};
-struct HintParams {
-    HintJobDev jobs[HG_MAX_JOBS];
-    const void *db;
-    uint32_t n_jobs, n_tiles;
-    uint32_t threads;   // CTA width of this launch
-    uint32_t ev, evx;  // vectors per row (incl. un-xored tail), vectors that are xored
-    unsigned int *sync;  // round barrier counter (cooperative launch) or nullptr
-};
-struct RkOfJob {
-    const HintParams &P;
-    int j;
-    __device__ __forceinline__ uint32_t operator[](int i) const { return P.jobs[j].rk[i]; }
-};
-
-__device__ __forceinline__ uint4 ldg_row(const uint4 *p, bool pred) {
-    uint4 v;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\tmov.u32 %2, 0;\n\tmov.u32 %3, 0;\n\t"
-        "@p ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];\n\t}"
-        : "=&r"(v.x), "=&r"(v.y), "=&r"(v.z), "=&r"(v.w)
-        : "l"(p), "r"((uint32_t)pred));
-    return v;
-}
-__device__ __forceinline__ uint2 ldg_row(const uint2 *p, bool pred) {
-    uint2 v;
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\tmov.u32 %0, 0;\n\tmov.u32 %1, 0;\n\t"
-        "@p ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];\n\t}"
-        : "=&r"(v.x), "=&r"(v.y)
-        : "l"(p), "r"((uint32_t)pred));
-    return v;
-}
-
-// ---- software pipelining and load policy ------------------------------------------------------------
-// Details of the inner loop, all about keeping the pipes busy:
-//  * the PRF of the NEXT group of G chunks is evaluated in NPH = G/U slices interleaved with the U-row load
-//    batches of the CURRENT group, so each warp hides its own row-load latency behind its own AES work;
-//  * no per-load predicates: a (hint, chunk) pair that must not contribute (zero padding past n_rows, the
-//    skipped chunk, inactive lanes, chunks past S in the last group) still loads a real, harmless row -- a
-//    different one per pair, so no L2 line becomes a hot spot -- and bit 31 of the exchanged row word says
-//    whether to XOR it.  The common case (every pair of the warp's batch contributes) is one warp-uniform
-//    vote and the unmasked 3-input XOR;
-//  * FULL = the row is an exact multiple of G vectors (896 B, 640 B, 128 B rows): no column predicates either.
-constexpr uint32_t ROW_CONTRIB = 0x80000000u;
-template <typename VT, int G, int NV, int NTAB, int NB, int U, bool FULL, int PH, int NPH, typename RK>
-__device__ __forceinline__ void hg_phase(const AesTab<NTAB> &T, const RK &R, const PrfTagPart &g, uint32_t c_next,
-                                         PrfState &st, uint32_t row_cur, int gbase, int gl, const VT *base,
-                                         uint32_t ev, uint32_t evx, VT (&par)[NV]) {
-    VT buf[U][NV];
-    uint32_t rr[U];
-    bool all_in = true;
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-        rr[u] = __shfl_sync(0xffffffffu, row_cur, gbase + PH * U + u);
-        all_in = all_in && (rr[u] & ROW_CONTRIB);
-        const VT *rp = base + (uint64_t)(rr[u] & ~ROW_CONTRIB) * ev;
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            if (FULL) buf[u][k] = ldg_stream(rp + k * G);
-            else buf[u][k] = ldg_row(rp + k * G, (uint32_t)(k * G + gl) < evx);
-        }
-    }
-    prf_rounds<NTAB, NB, PrfPhase<PH, NPH>::first, PrfPhase<PH, NPH>::last>(T, R, g, c_next, st);
-    if (__all_sync(0xffffffffu, all_in)) {
-#pragma unroll
-        for (int u = 0; u < U; u++)
-#pragma unroll
-            for (int k = 0; k < NV; k++) vxor(par[k], buf[u][k]);
-    } else {
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if (rr[u] & ROW_CONTRIB) {
-#pragma unroll
-                for (int k = 0; k < NV; k++) vxor(par[k], buf[u][k]);
-            }
-    }
-}
-
-template <typename VT, int G, int NV, int NTAB, int NB, int U, bool FULL>
-__global__ void __launch_bounds__(HG_MAX_THREADS, 1) hintgen_kernel(const __grid_constant__ HintParams P) {
-    extern __shared__ uint32_t smem[];
-    aes_tab_fill<NTAB>(smem, c_te0);
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const AesTab<NTAB> T{smem + lane};
-    constexpr int GPW = 32 / G, NPH = G / U;
-    const int gl = lane & (G - 1), gbase = lane & ~(G - 1), gw = lane / G;
-    const uint32_t hints_per_tile = (blockDim.x / 32) * GPW;
-    const uint32_t ev = P.ev, evx = P.evx;
-
-    // Rounds: in round r the CTAs process tiles r*grid .. r*grid+grid-1, i.e. one contiguous range of hints of
-    // (nearly always) one sub-PIR, and all of them sweep that sub-PIR's DB slice from chunk 0.  With the round
-    // barrier the CTAs start every sweep together, so a chunk is fetched from HBM once per round and re-hit in L2
-    // by the other CTAs; without it they drift apart until the sweeps are uncorrelated.
-    const uint32_t rounds = (P.n_tiles + gridDim.x - 1) / gridDim.x;
-    for (uint32_t round = 0; round < rounds; round++) {
-        const uint32_t tile = round * gridDim.x + blockIdx.x;
-        if (P.sync && round > 0) {
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(P.sync, 1u);
-                const unsigned int target = round * gridDim.x;
-                unsigned int seen;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.sync));
-                    if (seen < target) __nanosleep(100);
-                } while (seen < target);
-            }
-            __syncthreads();
-        }
-        if (tile >= P.n_tiles) continue;
-        int j = 0;
-        while (j + 1 < (int)P.n_jobs && tile >= P.jobs[j + 1].tile_begin) j++;
-        const HintJobDev &J = P.jobs[j];
-        const RkOfJob R{P, j};
-        const uint64_t i = (uint64_t)(tile - J.tile_begin) * hints_per_tile + warp * GPW + gw;
-        const bool active = i < J.n_hints;
-        uint64_t tag = 0;
-        int32_t skip = PM_NO_SKIP;
-        if (active) {
-            const uint64_t h = J.hint_begin + i;
-            tag = J.tags ? J.tags[i] : h;
-            if (J.skip) skip = J.skip[i];
-            else if (h >= J.n_primary && J.backup_group) skip = (int32_t)((h - J.n_primary) / J.backup_group);
-        }
-        const PrfTagPart g = prf_tag_part(T, R, tag);
-        const uint32_t S = J.set_size, cmask = J.chunk_mask, cshift = J.chunk_shift;
-        const uint32_t n_rows = (uint32_t)J.n_rows;
-        const VT *base = reinterpret_cast<const VT *>(P.db) + J.row0 * ev + gl;
-
-        VT par[NV];
-#pragma unroll
-        for (int k = 0; k < NV; k++) vzero(par[k]);
-
-        // row word exchanged inside the group: bits 0..30 = a row that is always safe to read, bit 31 = contributes
-        auto to_row = [&](uint32_t c, uint32_t prf) -> uint32_t {
-            const uint32_t off = prf & cmask, row = (c << cshift) + off;
-            const bool in = c < S && row < n_rows;
-            const uint32_t safe = in ? row : (off < n_rows ? off : 0);
-            return safe | ((in && active && (int32_t)c != skip) ? ROW_CONTRIB : 0u);
-        };
-        PrfState st;
-        prf_rounds<NTAB, NB, 1, 10>(T, R, g, (uint32_t)gl, st);  // prologue: rows of the first group
-        uint32_t row_next = to_row(gl, st.s0);
-        for (uint32_t c0 = 0; c0 < S; c0 += G) {
-            const uint32_t row_cur = row_next, c_next = c0 + G + gl;
-            hg_phase<VT, G, NV, NTAB, NB, U, FULL, 0, NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
-            if (NPH > 1) hg_phase<VT, G, NV, NTAB, NB, U, FULL, (NPH > 1 ? 1 : 0), NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
-            if (NPH > 2) {
-                hg_phase<VT, G, NV, NTAB, NB, U, FULL, (NPH > 2 ? 2 : 0), NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
-                hg_phase<VT, G, NV, NTAB, NB, U, FULL, (NPH > 2 ? 3 : 0), NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
-            }
-            row_next = to_row(c_next, st.s0);
-        }
-        if (active) {
-            VT *o = reinterpret_cast<VT *>(J.out) + i * ev + gl;
-#pragma unroll
-            for (int k = 0; k < NV; k++)
-                if ((uint32_t)(k * G + gl) < ev) o[k * G] = par[k];
-            VT z;
-            vzero(z);
-            for (uint32_t col = NV * G + gl; col < ev; col += G) o[col - gl] = z;
-        }
     }
 }
 
@@ -376,164 +191,7 @@ __global__ void xor_slices_kernel(uint64_t *dst, const uint64_t *src, uint64_t n
 // ---------------------------------------------------------------------------------------------
 // dispatch
 // ---------------------------------------------------------------------------------------------
-// tuning knob (read once): PM_HG_NTAB=1|4 forces the number of T-tables; default by row width (measured on B200:
-// four tables win while the PRF dominates, i.e. rows up to 640 B; one table + PRMT rotations wins for 896 B rows)
-static int env_int(const char *name, int dflt) {
-    const char *v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
-}
-template <typename KERN>
-static int launch_hg(KERN kern, int smem, const HintParams &P, int sm, cudaStream_t st) {
-    PM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    const uint32_t grid = P.n_tiles < (uint32_t)sm ? P.n_tiles : (uint32_t)sm;
-    if (P.sync && P.n_tiles > grid) {
-        // round barrier needs every CTA resident: cooperative launch (one 512-thread CTA per SM always fits)
-        PM_CUDA(cudaMemsetAsync(P.sync, 0, sizeof(unsigned int), st));
-        void *args[] = {(void *)&P};
-        PM_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(P.threads), args, (size_t)smem, st));
-    } else {
-        HintParams Q = P;
-        Q.sync = nullptr;
-        kern<<<grid, Q.threads, smem, st>>>(Q);
-    }
-    PM_CHECK_LAUNCH();
-    count_launch();
-    return PM_OK;
-}
-template <typename VT, int G, int NV, int NB>
-static int launch_hintgen_t(const HintParams &P, int sm, cudaStream_t st) {
-    constexpr int U = (G >= 2) ? 2 : 1;
-    constexpr bool kFourTables = sizeof(VT) == 16 && NB == 2;  // instantiated only where it is ever selected
-    static const int forced = env_int("PM_HG_NTAB", 0);
-    const int ntab = forced ? forced : (NV * G <= 40 ? 4 : 1);
-    const bool full = (P.evx == (uint32_t)(NV * G));
-    if (kFourTables && ntab == 4) {
-        if (full) return launch_hg(hintgen_kernel<VT, G, NV, kFourTables ? 4 : 1, NB, U, true>, aes_tab_words<4>() * 4, P, sm, st);
-        return launch_hg(hintgen_kernel<VT, G, NV, kFourTables ? 4 : 1, NB, U, false>, aes_tab_words<4>() * 4, P, sm, st);
-    }
-    if (full) return launch_hg(hintgen_kernel<VT, G, NV, 1, NB, U, true>, aes_tab_words<1>() * 4, P, sm, st);
-    return launch_hg(hintgen_kernel<VT, G, NV, 1, NB, U, false>, aes_tab_words<1>() * 4, P, sm, st);
-}
-template <typename VT, int G, int NB>
-static int launch_hintgen_nv(int nv, const HintParams &P, int sm, cudaStream_t st) {
-    switch (nv) {
-    case 1: return launch_hintgen_t<VT, G, 1, NB>(P, sm, st);
-    case 2: return launch_hintgen_t<VT, G, 2, NB>(P, sm, st);
-    case 3: return launch_hintgen_t<VT, G, 3, NB>(P, sm, st);
-    case 4: return launch_hintgen_t<VT, G, 4, NB>(P, sm, st);
-    case 5: return launch_hintgen_t<VT, G, 5, NB>(P, sm, st);
-    case 6: return launch_hintgen_t<VT, G, 6, NB>(P, sm, st);
-    case 7: return launch_hintgen_t<VT, G, 7, NB>(P, sm, st);
-    case 8: return launch_hintgen_t<VT, G, 8, NB>(P, sm, st);
-    }
-    return set_error(PM_ERR_UNSUPPORTED, "hintgen: entry too wide (nv=%d)", nv);
-}
-template <typename VT, int NB>
-static int launch_hintgen_g(uint32_t evx, const HintParams &P, int sm, cudaStream_t st, uint32_t *hints_per_tile,
-                            bool query_only) {
-    const uint32_t x = evx ? evx : 1;
-    int G = x >= 8 ? 8 : x >= 4 ? 4 : x >= 2 ? 2 : 1;
-    int nv = (int)((x + G - 1) / G);
-    *hints_per_tile = (32 / G);   // hints per warp; the caller multiplies by the warps of the CTA width it picks
-    if (query_only) return nv <= 8 ? PM_OK : set_error(PM_ERR_UNSUPPORTED, "hintgen: entry_u64 too large");
-    switch (G) {
-    case 8: return launch_hintgen_nv<VT, 8, NB>(nv, P, sm, st);
-    case 4: return nv == 1 ? launch_hintgen_t<VT, 4, 1, NB>(P, sm, st) : launch_hintgen_t<VT, 4, 2, NB>(P, sm, st);
-    case 2: return nv == 1 ? launch_hintgen_t<VT, 2, 1, NB>(P, sm, st) : launch_hintgen_t<VT, 2, 2, NB>(P, sm, st);
-    default: return launch_hintgen_t<VT, 1, 1, NB>(P, sm, st);
-    }
-}
-
-// Enqueue hint generation for `jobs` (all pointers inside are device pointers) on `st`.
-int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStream_t st) {
-    const uint64_t E = db->entry_u64;
-    const bool wide = (E % 2 == 0);  // 16-byte vectors need 16-byte aligned rows
-    const uint32_t ev = (uint32_t)(wide ? E / 2 : E), evx = (uint32_t)(wide ? (E & ~3ull) / 2 : (E & ~3ull));
-    bool need4 = false;
-    for (uint64_t a = 0; a < n_jobs; a++) {
-        const pm_hint_job &J = jobs[a];
-        if (J.chunk_size == 0 || (J.chunk_size & (J.chunk_size - 1)))
-            return set_error(PM_ERR_ARG, "hintgen: chunk_size %llu is not a power of two", (unsigned long long)J.chunk_size);
-        if (J.row0 + J.n_rows > db->n_rows) return set_error(PM_ERR_ARG, "hintgen: job %llu exceeds the table", (unsigned long long)a);
-        if (J.n_rows >= 0x7fffffffull || J.set_size >= 0x7fffffffull || J.chunk_size > 0x80000000ull ||
-            J.chunk_size * J.set_size > 0xffffffffull)
-            return set_error(PM_ERR_UNSUPPORTED, "hintgen: instance too large for 32-bit row offsets");
-        if (J.n_hints && !J.parity_out) return set_error(PM_ERR_ARG, "hintgen: parity_out is null");
-        if (J.chunk_size > 65536) need4 = true;
-    }
-    uint64_t a = 0;
-    while (a < n_jobs) {
-        HintParams P;
-        memset(&P, 0, sizeof(P));
-        P.db = db->d_rows;
-        // The round barrier pays when a sub-PIR's slice does not fit in L2 (measured: 896 B x 200 k rows = 179 MB,
-        // -12 % time); for slices that stay L2-resident anyway (SIFT-shaped: 40 MB) it only costs.  PM_HG_SYNC=0|1 forces.
-        static const int force_sync = env_int("PM_HG_SYNC", -1);
-        uint64_t max_slice = 0;
-        for (uint64_t b = a; b < n_jobs && b < a + HG_MAX_JOBS; b++) max_slice = std::max<uint64_t>(max_slice, jobs[b].n_rows * E * 8);
-        const bool use_sync = force_sync >= 0 ? force_sync != 0 : max_slice > (64ull << 20);
-        P.sync = use_sync ? sync_counter(db) : nullptr;
-        P.ev = ev;
-        P.evx = evx;
-        uint32_t hpw = 0;   // hints per warp
-        int rc = wide ? launch_hintgen_g<uint4, 2>(evx, P, 0, st, &hpw, true) : launch_hintgen_g<uint2, 2>(evx, P, 0, st, &hpw, true);
-        if (rc != PM_OK) return rc;
-        // CTA width.  Every lane group keeps one hint for a whole sweep, so a tile costs one sweep whatever it holds and
-        // the CTAs run ceil(tiles / SMs) rounds.  A round gets cheaper with fewer warps, but less than proportionally
-        // (measured on B200, MS-MARCO rows: 16 -> 14 warps = -5 % per round, i.e. round time ~ warps + 24), so a
-        // narrower CTA only pays when it saves nothing in rounds: 1/8 of the hints (8 GPUs) is 5.2 -> 6 rounds at 16
-        // warps and 5.95 -> 6 at 14 (-4.3 %); at 1, 2 and 4 GPUs 16 warps stay best.  PM_HG_WARPS forces a width.
-        static const int force_warps = env_int("PM_HG_WARPS", 0);
-        uint32_t warps = HG_THREADS / 32;
-        {
-            uint64_t best = ~0ull;
-            for (uint32_t w = 12; w <= (uint32_t)HG_MAX_THREADS / 32; w++) {
-                uint64_t t = 0, nj2 = 0;
-                for (uint64_t b = a; b < n_jobs && nj2 < HG_MAX_JOBS; b++) {
-                    if (jobs[b].n_hints == 0 || jobs[b].n_rows == 0) continue;
-                    nj2++;
-                    t += (jobs[b].n_hints + (uint64_t)w * hpw - 1) / ((uint64_t)w * hpw);
-                }
-                const uint64_t g = std::max<uint64_t>(1, std::min<uint64_t>(t, (uint64_t)db->sm_count));
-                const uint64_t cost = ((t + g - 1) / g) * (w + 24);
-                if (cost <= best) { best = cost; warps = w; }
-            }
-            if (force_warps >= 1 && force_warps <= HG_MAX_THREADS / 32) warps = (uint32_t)force_warps;
-        }
-        const uint32_t hpt = hpw * warps;
-        P.threads = warps * 32;
-        uint32_t tiles = 0;
-        uint32_t nj = 0;
-        for (; a < n_jobs && nj < HG_MAX_JOBS; a++) {
-            const pm_hint_job &J = jobs[a];
-            if (J.n_hints == 0) continue;
-            if (J.n_rows == 0) {  // an empty instance has all-zero parities
-                PM_CUDA(cudaMemsetAsync(J.parity_out, 0, J.n_hints * E * 8, st));
-                continue;
-            }
-            HintJobDev &D = P.jobs[nj++];
-            memcpy(D.rk, J.rk, sizeof(D.rk));
-            D.row0 = J.row0; D.n_rows = J.n_rows;
-            D.hint_begin = J.hint_begin; D.n_hints = J.n_hints; D.n_primary = J.n_primary; D.backup_group = J.backup_group;
-            D.tags = J.tags; D.skip = J.skip_chunk; D.out = J.parity_out;
-            D.chunk_mask = (uint32_t)(J.chunk_size - 1);
-            D.chunk_shift = (uint32_t)__builtin_ctzll(J.chunk_size);
-            D.set_size = (uint32_t)J.set_size;
-            D.tile_begin = tiles;
-            tiles += (uint32_t)((J.n_hints + hpt - 1) / hpt);
-        }
-        if (nj == 0) break;
-        P.n_jobs = nj;
-        P.n_tiles = tiles;
-        uint32_t unused = 0;
-        if (wide) rc = need4 ? launch_hintgen_g<uint4, 4>(evx, P, db->sm_count, st, &unused, false)
-                             : launch_hintgen_g<uint4, 2>(evx, P, db->sm_count, st, &unused, false);
-        else if (need4) rc = set_error(PM_ERR_UNSUPPORTED, "hintgen: odd entry_u64 with chunk_size > 65536 is not built");
-        else rc = launch_hintgen_g<uint2, 2>(evx, P, db->sm_count, st, &unused, false);
-        if (rc != PM_OK) return rc;
-    }
-    return PM_OK;
-}
+int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStream_t st);   // pm_hintgen.cu
 
 template <typename VT>
 static int launch_answer_t(const AnswerParams &P, uint64_t q, uint32_t max_set, cudaStream_t st) {
@@ -590,8 +248,8 @@ int answer_enqueue(pm_db *db, const uint64_t *row0, const uint64_t *n_rows, cons
     P.ev = (uint32_t)(wide ? E / 2 : E);
     P.evx = (uint32_t)(wide ? (E & ~3ull) / 2 : (E & ~3ull));
     // few sub-queries: a cluster of up to 4 CTAs per sub-query so that about three CTAs per SM are at work (measured at
-    // 96 sub-queries, us: 1 CTA 24.9 | 2 21.2 | 3 18.4 | 4 16.8 | 6 16.5 | 8 20.0).  PM_ANS_SPLIT forces.
-    static const int force_split = env_int("PM_ANS_SPLIT", 0);
+    // 96 sub-queries, us: 1 CTA 24.9 | 2 21.2 | 3 18.4 | 4 16.8 | 6 16.5 | 8 20.0).  The ans_split knob forces.
+    const int force_split = tune(T_ANS_SPLIT);
     const uint64_t target = 3ull * (uint64_t)db->sm_count;
     uint32_t split = (uint32_t)std::min<uint64_t>(4, std::max<uint64_t>(1, (target + q / 2) / q));
     if (max_set < 64) split = 1;   // nothing to share
@@ -685,65 +343,6 @@ PM_EXPORT int pm_xor_slices(uint64_t *dst, const uint64_t *src, uint64_t len_src
     if (e == cudaSuccess) e = cudaMemcpy(dst, d, n4 * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return set_error(PM_ERR_CUDA, "pm_xor_slices: %s", cudaGetErrorString(e));
-    return PM_OK;
-}
-
-PM_EXPORT int pm_hintgen_dev(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, void *stream) {
-    if (!db || (n_jobs && !jobs)) return set_error(PM_ERR_ARG, "pm_hintgen_dev: null pointer");
-    int rc = ensure_device(db->device);
-    if (rc) return rc;
-    return hintgen_enqueue(db, jobs, n_jobs, stream ? (cudaStream_t)stream : db->stream);
-}
-
-// Host-buffer variant: tags/skip uploaded, parities downloaded.  Jobs are issued in a few launch
-// groups so the D2H of one group's parities overlaps the next group's kernel.
-PM_EXPORT int pm_hintgen(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs) {
-    if (!db || (n_jobs && !jobs)) return set_error(PM_ERR_ARG, "pm_hintgen: null pointer");
-    int rc = ensure_device(db->device);
-    if (rc) return rc;
-    std::lock_guard<std::mutex> lock(db->mu);
-    const uint64_t E = db->entry_u64;
-    uint64_t total_hints = 0, explicit_tags = 0, explicit_skip = 0;
-    for (uint64_t a = 0; a < n_jobs; a++) {
-        total_hints += jobs[a].n_hints;
-        if (jobs[a].tags) explicit_tags += jobs[a].n_hints;
-        if (jobs[a].skip_chunk) explicit_skip += jobs[a].n_hints;
-    }
-    if (total_hints == 0) return PM_OK;
-    void *d_out = nullptr, *d_tags = nullptr, *d_skip = nullptr;
-    if ((rc = scratch(db, 0, total_hints * E * 8, &d_out))) return rc;
-    if (explicit_tags && (rc = scratch(db, 1, explicit_tags * 8, &d_tags))) return rc;
-    if (explicit_skip && (rc = scratch(db, 2, explicit_skip * 4, &d_skip))) return rc;
-
-    std::vector<pm_hint_job> dj(jobs, jobs + n_jobs);
-    uint64_t ho = 0, to = 0, so = 0;
-    for (uint64_t a = 0; a < n_jobs; a++) {
-        dj[a].parity_out = (uint64_t *)d_out + ho * E;
-        ho += jobs[a].n_hints;
-        if (jobs[a].n_hints && !jobs[a].parity_out) return set_error(PM_ERR_ARG, "pm_hintgen: parity_out is null");
-        if (jobs[a].tags) {
-            dj[a].tags = (uint64_t *)d_tags + to;
-            PM_CUDA(cudaMemcpyAsync((void *)dj[a].tags, jobs[a].tags, jobs[a].n_hints * 8, cudaMemcpyHostToDevice, db->stream));
-            to += jobs[a].n_hints;
-        }
-        if (jobs[a].skip_chunk) {
-            dj[a].skip_chunk = (int32_t *)d_skip + so;
-            PM_CUDA(cudaMemcpyAsync((void *)dj[a].skip_chunk, jobs[a].skip_chunk, jobs[a].n_hints * 4, cudaMemcpyHostToDevice, db->stream));
-            so += jobs[a].n_hints;
-        }
-    }
-    const uint64_t groups = n_jobs < 4 ? n_jobs : 4;
-    for (uint64_t gi = 0; gi < groups; gi++) {
-        const uint64_t a0 = n_jobs * gi / groups, a1 = n_jobs * (gi + 1) / groups;
-        if ((rc = hintgen_enqueue(db, dj.data() + a0, a1 - a0, db->stream))) return rc;
-        PM_CUDA(cudaEventRecord(db->ev[gi & 3], db->stream));
-        PM_CUDA(cudaStreamWaitEvent(db->copy_stream, db->ev[gi & 3], 0));
-        for (uint64_t a = a0; a < a1; a++)
-            if (jobs[a].n_hints)
-                PM_CUDA(cudaMemcpyAsync(jobs[a].parity_out, dj[a].parity_out, jobs[a].n_hints * E * 8, cudaMemcpyDeviceToHost, db->copy_stream));
-    }
-    PM_CUDA(cudaStreamSynchronize(db->copy_stream));
-    PM_CUDA(cudaStreamSynchronize(db->stream));
     return PM_OK;
 }
 

@@ -23,9 +23,11 @@ def L2Dist(v1, v2, device=0):
 class GraphANNFrontend:
     """graphann.GraphANNFrontend over BasicGraphInfo (non-private) or PIRGraphInfo (private, private-search.go)."""
 
-    def __init__(self, vectors, graph, private=False, skipPrep=False, nonPrivateMode=False, seed=1, device=0, resident=True,
+    def __init__(self, vectors, graph, private=False, skipPrep=False, nonPrivateMode=False, seed=None, device=0, resident=True,
                  share_db_with=None, group_lanes=1, lane_of=None, lane=0):
-        """share_db_with: another private frontend (already preprocessed) whose GPU-resident rawDB this client reuses --
+        """seed: None = the client draws its keys, replacement and dummy offsets and start vertices from the OS CSPRNG (what
+        a deployment wants); an integer > 0 makes everything deterministic -- the hook the parity tests use.
+        share_db_with: another private frontend (already preprocessed) whose GPU-resident rawDB this client reuses --
         one DB replica per GPU, one client (keys, hint tables, search state) per user.
         group_lanes / lane_of / lane: client groups for SearchKNNLockstep -- the first client is created with
         group_lanes=L and preprocessed, clients 1..L-1 with lane_of=first, lane=i (see make_client_group)."""
@@ -33,6 +35,7 @@ class GraphANNFrontend:
         self.graph = np.ascontiguousarray(graph, np.int32)
         self.n, self.dim = self.vectors.shape
         self.m = self.graph.shape[1]
+        seed = 0 if seed is None else int(seed)
         L = _host.lib()
         self._shared = share_db_with if share_db_with is not None else lane_of      # keep the owner of the DB / client group alive
         if lane_of is not None:
@@ -102,8 +105,9 @@ class GraphANNFrontend:
 
 def make_client_group(vectors, graph, lanes, seeds=None, skipPrep=False, device=0):
     """L independent private clients (own keys, hint tables, caches, search state) over ONE GPU-resident rawDB whose hint
-    tables live in ONE pm_client, preprocessed and ready for SearchKNNLockstep.  seeds[i] = client i's seed."""
-    seeds = list(seeds) if seeds is not None else [1 + i for i in range(lanes)]
+    tables live in ONE pm_client, preprocessed and ready for SearchKNNLockstep.  seeds[i] = client i's seed (tests);
+    None = every client draws its own secrets from the OS CSPRNG."""
+    seeds = list(seeds) if seeds is not None else [None] * lanes
     first = GraphANNFrontend(vectors, graph, private=True, skipPrep=skipPrep, seed=seeds[0], device=device, group_lanes=lanes)
     first.Preprocess()
     group = [first]
