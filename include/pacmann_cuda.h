@@ -189,6 +189,44 @@ int pm_client_query_batch_l2m(pm_client *c, const pm_client_query *queries, uint
  * 8 FinishedQueryNum */
 int pm_client_download(pm_client *c, uint32_t part, int table, uint64_t *out, uint64_t cap_words);
 
+/* ---- GPU-resident lock-step search -----------------------------------------------------
+ * graphann.SearchKNN's frontier (explore heap, known set, reach steps, final re-rank: graphann/search.go:114-234) and
+ * SimpleBatchPianoPIR.Query's bookkeeping around the fetch (bucketing, drops, dummy padding, the client's local cache:
+ * pianopir/batch-pir.go:170-248, pir.go:381-383,468) for `lanes` independent clients of one pm_client (lane l = parts
+ * [l*partition_num, (l+1)*partition_num)), all resident in HBM.  A round runs one SearchKNN per listed lane, in lock
+ * step: pm_search_begin, then max_step times pm_search_fetch (which only ENQUEUES the step: next batch from the neighbour
+ * lists in HBM -> client prepare -> server answer -> client finish + distances), then pm_search_finish (final ranking,
+ * one small copy back).  No entry, neighbour list or distance visits the host.  Every lane returns exactly what its
+ * client returns searching alone (start ranking by (distance, position), container/heap explore queue, final ranking by
+ * (distance, id)); pm_client_preprocess of a part also clears that part's cache here. */
+typedef struct pm_search pm_search;
+typedef struct pm_search_config {
+    uint64_t n, dim, m;                       /* vertices, vector dimension, degree: an entry is dim f32 || m u32 */
+    uint64_t max_step, parallel;              /* SearchKNN parameters (search.go:114) */
+    uint64_t lanes;                           /* independent clients */
+    uint64_t partition_num, partition_size;   /* SimpleBatchPianoPIR geometry (batch-pir.go:62-64) */
+    uint64_t n_start;                         /* start vertices per lane (search.go:51-65: sqrt(n)) */
+    uint64_t cache_entries;                   /* local-cache capacity per sub-PIR (MaxQueryNum) */
+} pm_search_config;
+int pm_search_create(pm_client *c, const pm_search_config *cfg, pm_search **out);
+int pm_search_destroy(pm_search *s);
+/* start vertices of one lane: ids [n_start], vectors [n_start][dim], neighbours [n_start][m] (plaintext copies, private-search.go:508-531) */
+int pm_search_set_start(pm_search *s, uint32_t lane, const int64_t *ids, const float *vectors, const int32_t *neighbors);
+/* seeds of the lane's dummy-query offset streams, one per sub-PIR (pir.go:363-371) */
+int pm_search_set_dummy_seed(pm_search *s, uint32_t lane, const uint64_t *seeds);
+/* start a round: lanes[a] searches queries[a]; rand_seeds[a] seeds the "random vertex" branch (search.go:155-159) */
+int pm_search_begin(pm_search *s, const uint32_t *lanes, uint64_t act, const float *queries, const uint64_t *rand_seeds, uint64_t k,
+                    int benchmarking);
+int pm_search_fetch(pm_search *s, int apply_previous);
+int pm_search_apply(pm_search *s);
+/* ret / step_ret: [act][k] (-1 padded); stats: [act][3] = fetched entries, entries equal to the true row, server sub-queries;
+ * finished: [act][partition_num] = FinishedQueryNum of every sub-PIR after the round */
+int pm_search_finish(pm_search *s, int apply_previous, int64_t *ret, int64_t *step_ret, uint64_t *stats, uint64_t *finished);
+/* the cached (index, entry) pairs of one sub-PIR of one lane, in insertion order; idx_out / entries_out may be NULL to
+ * query the count */
+int pm_search_cache_download(pm_search *s, uint32_t lane, uint32_t part, uint64_t *idx_out, uint64_t *entries_out, uint64_t cap,
+                             uint64_t *count);
+
 /* Page-locked host memory for callers that want result buffers the GPU can write directly (any host pointer works
  * everywhere; a pm_host_alloc'ed `out` of pm_client_query_batch* just saves one host-side copy of the answers). */
 int pm_host_alloc(void **out, uint64_t bytes);

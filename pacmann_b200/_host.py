@@ -39,6 +39,8 @@ SIG = {
     "pmh_batch_enable_resident": (C.c_int, [vp]),
     "pmh_batch_local_storage": (C.c_double, [vp]),
     "pmh_batch_prep_time": (C.c_double, [vp]),
+    "pmh_batch_prep_total": (C.c_double, [vp]),
+    "pmh_batch_prep_count": (C.c_uint64, [vp]),
     "pmh_l2dist": (C.c_float, [vp, vp, u64, C.c_int]),
     "pmh_frontend_basic": (vp, [i64, i64, i64, vp, vp]),
     "pmh_frontend_pir": (vp, [i64, i64, i64, vp, vp, C.c_int, C.c_int, u64, C.c_int, C.c_int]),
@@ -46,6 +48,7 @@ SIG = {
     "pmh_frontend_set_group_lanes": (C.c_int, [vp, C.c_uint32]),
     "pmh_frontend_pir_lane": (vp, [vp, u64, C.c_uint32]),
     "pmh_search_knn_lockstep": (C.c_int, [vp, i64, vp, i64, i64, i64, i64, C.c_int, vp, vp]),
+    "pmh_device_search_stats": (None, [vp]),
     "pmh_robust_prune_batch": (C.c_int, [vp, i64, i64, vp, i64, vp, i64, i64, C.c_float, C.c_int, vp, vp]),
     "pmh_selftest": (C.c_int, [C.c_int]),
     "pmh_frontend_free": (None, [vp]),

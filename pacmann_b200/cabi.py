@@ -78,6 +78,15 @@ SIGNATURES = {
     "pm_client_query_batch_l2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_client_query_batch_l2m": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p,
                                             C.c_uint64, C.c_void_p]),
+    "pm_search_create": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "pm_search_destroy": (C.c_int, [C.c_void_p]),
+    "pm_search_set_start": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pm_search_set_dummy_seed": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "pm_search_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
+    "pm_search_fetch": (C.c_int, [C.c_void_p, C.c_int]),
+    "pm_search_apply": (C.c_int, [C.c_void_p]),
+    "pm_search_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pm_search_cache_download": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "pm_host_alloc": (C.c_int, [C.c_void_p, C.c_uint64]),
     "pm_host_free": (C.c_int, [C.c_void_p]),
     "pm_client_download": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_uint64]),

@@ -2,6 +2,7 @@
 #include "graphann.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -498,6 +499,120 @@ int GraphANNFrontend::SearchKNNBatch(const float *queryVectors, int64_t nq, int6
     return 0;
 }
 
+// ---- lock-step search with the frontier on the GPU (pm_search_*) ----
+// Usable when the lanes are clients of ONE resident pm_client group.  The host only enqueues the steps and keeps the
+// counters that need no entry data: the batch budget of every lane (batch-pir.go:239-245: a due Preprocessing() is
+// issued between two steps, after the fetch has been applied) and the statistics.  A lane one of whose sub-PIRs could
+// reach its query budget within the round (pir.go:527-530 would re-preprocess in the middle of a call) leaves the
+// device path for the rest of its batch epoch: its device caches are pulled into the host-side localCache and it
+// searches through the host path until the next Preprocessing() of its whole batch.
+static bool deviceSearchEnabled() {   // PM_SEARCH_DEVICE=0 keeps the frontier on the host (read per call: tests flip it)
+    const char *v = getenv("PM_SEARCH_DEVICE");
+    return !(v && *v == '0');
+}
+
+static pm_search *deviceSearchFor(const std::vector<GraphANNFrontend *> &lanes, const std::vector<PIRGraphInfo *> &infos, int64_t maxStep,
+                                  int64_t parallel) {
+    // the lanes must be exactly the clients of one group, lane l in parts [l*PN, (l+1)*PN)
+    pianopir::SimpleBatchPianoPIR *owner = nullptr;
+    const size_t L = lanes.size();
+    for (size_t l = 0; l < L; l++) {
+        pianopir::SimpleBatchPianoPIR *p = infos[l] ? infos[l]->PIR : nullptr;
+        if (!p || !p->resident || !p->rclient || infos[l]->NonPrivateMode) return nullptr;
+        if (p->rclient != infos[0]->PIR->rclient || p->clientLanes != L) return nullptr;
+        if (p->partBase != (uint32_t)(l * p->config.PartitionNum)) return nullptr;
+        if (lanes[l]->StartVertices.size() != lanes[0]->StartVertices.size() || lanes[l]->StartVertices.empty()) return nullptr;
+        if (p->ownsClient) owner = p;
+    }
+    if (!owner) return nullptr;
+    int64_t n, dim, m;
+    lanes[0]->Graph->GetMetadata(&n, &dim, &m);
+    if ((uint64_t)(parallel * m) < owner->config.PartitionNum) return nullptr;
+    uint64_t key = Mix64(Mix64((uint64_t)maxStep, (uint64_t)parallel), L);
+    for (auto *f : lanes) key = Mix64(key, (uint64_t)(uintptr_t)f ^ f->startVersion);
+    if (owner->devSearch && owner->devSearchKey == key) return owner->devSearch;
+    if (owner->devSearch) { pm_search_destroy(owner->devSearch); owner->devSearch = nullptr; }
+    pm_search_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.n = (uint64_t)n; cfg.dim = (uint64_t)dim; cfg.m = (uint64_t)m;
+    cfg.max_step = (uint64_t)maxStep; cfg.parallel = (uint64_t)parallel; cfg.lanes = L;
+    cfg.partition_num = owner->config.PartitionNum; cfg.partition_size = owner->config.PartitionSize;
+    cfg.n_start = lanes[0]->StartVertices.size();
+    cfg.cache_entries = 0;
+    for (auto *p : owner->subPIR) cfg.cache_entries = std::max<uint64_t>(cfg.cache_entries, p->client.MaxQueryNum);
+    pm_search *s = nullptr;
+    if (pm_search_create(owner->rclient, &cfg, &s) != PM_OK) return nullptr;   // e.g. shapes the kernels do not cover: host path
+    std::vector<int64_t> ids(cfg.n_start);
+    std::vector<float> vec(cfg.n_start * (size_t)dim);
+    std::vector<int32_t> nb(cfg.n_start * (size_t)m);
+    std::vector<uint64_t> dseed(cfg.partition_num);
+    for (size_t l = 0; l < L; l++) {
+        for (size_t i = 0; i < cfg.n_start; i++) {
+            const Vertex &v = lanes[l]->StartVertices[i];
+            ids[i] = v.Id;
+            memcpy(&vec[i * (size_t)dim], v.Vector.data(), (size_t)dim * 4);
+            for (int64_t j = 0; j < m; j++) nb[i * (size_t)m + (size_t)j] = (int32_t)v.Neighbors[(size_t)j];
+        }
+        check(pm_search_set_start(s, (uint32_t)l, ids.data(), vec.data(), nb.data()), "pm_search_set_start");
+        for (uint64_t p = 0; p < cfg.partition_num; p++) dseed[p] = Mix64(infos[l]->PIR->subPIR[p]->client.dummySeed, 0x5EA7C4);
+        check(pm_search_set_dummy_seed(s, (uint32_t)l, dseed.data()), "pm_search_set_dummy_seed");
+    }
+    owner->devSearch = s;
+    owner->devSearchKey = key;
+    return s;
+}
+
+static std::atomic<uint64_t> g_deviceRounds{0}, g_deviceQueries{0}, g_hostModeQueries{0};
+void DeviceSearchStats(uint64_t out[3]) { out[0] = g_deviceRounds.load(); out[1] = g_deviceQueries.load(); out[2] = g_hostModeQueries.load(); }
+
+// one round of the device path: lanes[sel[a]] searches query qidx[a]
+static int deviceRound(pm_search *s, const std::vector<GraphANNFrontend *> &lanes, const std::vector<PIRGraphInfo *> &infos,
+                       const std::vector<uint32_t> &sel, const float *queryVectors, const std::vector<int64_t> &qidx, int64_t dim, int64_t m,
+                       int64_t k, int64_t maxStep, int64_t parallel, bool benchmarking, int64_t *ret, int64_t *stepRet) {
+    const size_t act = sel.size();
+    const size_t n = (size_t)(parallel * m);
+    g_deviceRounds += 1;
+    g_deviceQueries += act;
+    std::vector<float> q(act * (size_t)dim);
+    std::vector<uint64_t> rseeds(act);
+    for (size_t a = 0; a < act; a++) {
+        memcpy(&q[a * (size_t)dim], queryVectors + qidx[a] * dim, (size_t)dim * 4);
+        GraphANNFrontend *f = lanes[sel[a]];
+        rseeds[a] = Mix64(f->randSeed, f->queryCounter++);
+    }
+    check(pm_search_begin(s, sel.data(), act, q.data(), rseeds.data(), (uint64_t)k, benchmarking ? 1 : 0), "pm_search_begin");
+    bool applied = true;   // nothing to apply before the first fetch
+    for (int64_t step = 0; step < maxStep; step++) {
+        check(pm_search_fetch(s, applied ? 0 : 1), "pm_search_fetch");
+        applied = false;
+        bool anyDue = false;
+        std::vector<char> due(act, 0);
+        for (size_t a = 0; a < act; a++) {
+            due[a] = infos[sel[a]]->PIR->DeviceFetchAccounting(n) ? 1 : 0;
+            anyDue = anyDue || due[a];
+        }
+        if (anyDue) {   // batch-pir.go:239-245: the call's responses are booked first, then the whole batch is preprocessed again
+            check(pm_search_apply(s), "pm_search_apply");
+            applied = true;
+            for (size_t a = 0; a < act; a++)
+                if (due[a]) infos[sel[a]]->PIR->Preprocessing();
+        }
+    }
+    std::vector<int64_t> r(act * (size_t)k), st(act * (size_t)k);
+    std::vector<uint64_t> stats(act * 3), fin(act * infos[0]->PIR->config.PartitionNum);
+    check(pm_search_finish(s, applied ? 0 : 1, r.data(), st.data(), stats.data(), fin.data()), "pm_search_finish");
+    const uint64_t PN = infos[0]->PIR->config.PartitionNum;
+    for (size_t a = 0; a < act; a++) {
+        memcpy(ret + qidx[a] * k, &r[a * (size_t)k], (size_t)k * 8);
+        memcpy(stepRet + qidx[a] * k, &st[a * (size_t)k], (size_t)k * 8);
+        PIRGraphInfo *g = infos[sel[a]];
+        g->totalQueryNum += (int64_t)stats[a * 3];
+        g->succQueryNum += (int64_t)stats[a * 3 + 1];
+        g->PIR->AbsorbDeviceRound(&fin[a * PN], stats[a * 3 + 2]);
+    }
+    return 0;
+}
+
 // Lock-step search over several lanes.  Query i goes to lane i % L; every lane runs its queries in
 // order exactly as its own SearchKNNBatch would -- same client state, same results -- but each step fetches the
 // vertices of all lanes together: one FetchGroupRaw (one device call) per step instead of one per lane.
@@ -514,6 +629,33 @@ int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float 
     for (int64_t l = 0; l < L; l++) {
         infos[(size_t)l] = dynamic_cast<PIRGraphInfo *>(lanes[(size_t)l]->Graph);
         groupable = groupable && infos[(size_t)l] != nullptr && !infos[(size_t)l]->NonPrivateMode;
+    }
+    if (groupable && deviceSearchEnabled()) {
+        if (pm_search *ds = deviceSearchFor(lanes, infos, maxStep, parallel)) {
+            for (int64_t base = 0; base < nq; base += L) {
+                const int64_t act = std::min(L, nq - base);
+                std::vector<uint32_t> sel;
+                std::vector<int64_t> qidx;
+                std::vector<int64_t> hostLanes;
+                for (int64_t l = 0; l < act; l++) {
+                    pianopir::SimpleBatchPianoPIR *p = infos[(size_t)l]->PIR;
+                    if (!p->hostMode && !p->DeviceRoundIsSafe((uint64_t)maxStep, (size_t)(parallel * m))) p->EnterHostMode(ds);
+                    if (p->hostMode) hostLanes.push_back(l);
+                    else { sel.push_back((uint32_t)l); qidx.push_back(base + l); }
+                }
+                if (!sel.empty() &&
+                    deviceRound(ds, lanes, infos, sel, queryVectors, qidx, dim, m, k, maxStep, parallel, benchmarking, ret->data(), stepRet->data()) != 0)
+                    return -1;
+                std::vector<int64_t> r1, s1;
+                g_hostModeQueries += hostLanes.size();
+                for (int64_t l : hostLanes) {   // rare: this lane's budget epoch is about to end, it searches through the host path
+                    if (lanes[(size_t)l]->SearchKNN(queryVectors + (base + l) * dim, k, maxStep, parallel, benchmarking, &r1, &s1) != 0) return -1;
+                    memcpy(&(*ret)[(size_t)((base + l) * k)], r1.data(), (size_t)k * 8);
+                    memcpy(&(*stepRet)[(size_t)((base + l) * k)], s1.data(), (size_t)k * 8);
+                }
+            }
+            return 0;
+        }
     }
     std::vector<std::vector<int64_t>> batch((size_t)L);
     std::vector<std::vector<Vertex>> results((size_t)L);

@@ -181,6 +181,10 @@ private:
 void RobustPruneBatch(pm_db *vecDb, int64_t dim, const std::vector<int64_t> &us, const std::vector<std::vector<int64_t>> &candidates,
                       int64_t m, float alpha, std::vector<std::vector<int64_t>> *out);
 
+// process-wide counters of the device-resident search path: rounds, queries searched on the device, queries of lanes that
+// had left the device path (host mode)
+void DeviceSearchStats(uint64_t out[3]);
+
 // Lock-step SearchKNNBatch over several frontends ("lanes"): query i is searched by lane i % L; results are those of
 // each lane's own SearchKNNBatch over its queries, the per-step fetches of all lanes share one device call.
 int SearchKNNLockstep(const std::vector<GraphANNFrontend *> &lanes, const float *queryVectors, int64_t nq, int64_t k, int64_t maxStep,

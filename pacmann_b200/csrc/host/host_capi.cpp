@@ -201,6 +201,8 @@ PMH uint64_t pmh_batch_get(void *h, int what) {
 }
 PMH double pmh_batch_local_storage(void *h) { return ((SimpleBatchPianoPIR *)h)->LocalStorageSize(); }
 PMH double pmh_batch_prep_time(void *h) { return ((SimpleBatchPianoPIR *)h)->PreprocessingTime(); }
+PMH double pmh_batch_prep_total(void *h) { return ((SimpleBatchPianoPIR *)h)->preprocessingTotal; }
+PMH uint64_t pmh_batch_prep_count(void *h) { return ((SimpleBatchPianoPIR *)h)->preprocessingCount; }
 
 // ---- graphann ----
 PMH float pmh_l2dist(const float *a, const float *b, uint64_t dim, int device) {
@@ -284,6 +286,7 @@ PMH int pmh_search_knn_lockstep(void **handles, int64_t n_lanes, const float *qu
     return 0;
     PMH_CATCH(-100)
 }
+PMH void pmh_device_search_stats(uint64_t *out) { graphann::DeviceSearchStats(out); }
 // robustPrune for a batch of vertices: candidates = [n][k] (every vertex k candidates), out = [n][m] padded with -1,
 // out_len[n].  vectors are uploaded for the call (rows of dim fp32; dim must be even).
 PMH int pmh_robust_prune_batch(const float *vectors, int64_t n_vectors, int64_t dim, const int64_t *us, int64_t n, const int64_t *candidates,

@@ -467,6 +467,7 @@ SimpleBatchPianoPIR::~SimpleBatchPianoPIR() {
     if (getenv("PM_HOST_PROFILE") && profQueryCalls)
         fprintf(stderr, "[host profile] Query calls %llu: %.1f us per call, of which pm_client_query_batch %.1f us\n",
                 (unsigned long long)profQueryCalls, profQueryTotal / profQueryCalls * 1e6, profGpuCall / profQueryCalls * 1e6);
+    if (devSearch) pm_search_destroy(devSearch);
     if (rclient && ownsClient) pm_client_destroy(rclient);
     if (groupBuf) pm_host_free(groupBuf);
     for (auto *p : subPIR) delete p;
@@ -495,6 +496,8 @@ std::string SimpleBatchPianoPIR::PrintInfo() const {  // batch-pir.go:95-108
 
 void SimpleBatchPianoPIR::RecordStats(double prepTime) {  // batch-pir.go:110-117
     preprocessingTime = prepTime;
+    preprocessingTotal += prepTime;
+    preprocessingCount += 1;
     localStorage = (uint64_t)LocalStorageSize();
     commCostPerBatchOnline = CommCostPerBatchOnline();
     SupportBatchNum = subPIR[0]->client.MaxQueryNum / QueryPerPartition;
@@ -512,6 +515,7 @@ void SimpleBatchPianoPIR::Preprocessing() {
         std::vector<uint32_t> ids(PN);
         for (uint64_t i = 0; i < PN; i++) ids[i] = (uint32_t)i;
         PreprocessResident(ids, false);
+        hostMode = false;   // every cache, on the host and on the device, is empty again
         RecordStats(std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
         return;
     }
@@ -1149,6 +1153,45 @@ int SimpleBatchPianoPIR::QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t 
     for (size_t l = 0; l < L; l++)
         if (calls[l].rc != 0) return calls[l].rc;
     return 0;
+}
+
+// ---- host side of the device-resident search path ----
+bool SimpleBatchPianoPIR::DeviceFetchAccounting(size_t n) {
+    profQueryCalls += 1;
+    serverLaunches += 1;
+    if (QueriesMadeInPartition >= subPIR[0]->client.MaxQueryNum - 2) return true;
+    FinishedBatchNum += n / config.BatchSize;
+    QueriesMadeInPartition += n / config.PartitionNum;
+    return false;
+}
+void SimpleBatchPianoPIR::AbsorbDeviceRound(const uint64_t *finished, uint64_t serverQ) {
+    for (uint64_t i = 0; i < config.PartitionNum; i++) subPIR[i]->client.FinishedQueryNum = finished[i];
+    serverQueries += serverQ;
+}
+bool SimpleBatchPianoPIR::DeviceRoundIsSafe(uint64_t maxStep, size_t n) const {
+    const uint64_t per = n / config.PartitionNum;
+    for (auto *p : subPIR)
+        if (p->client.FinishedQueryNum + maxStep * per >= p->client.MaxQueryNum) return false;
+    return true;
+}
+void SimpleBatchPianoPIR::EnterHostMode(pm_search *s) {
+    if (hostMode) return;
+    const uint64_t E = config.DBEntrySize, PN = config.PartitionNum;
+    std::vector<uint64_t> idx, entries;
+    for (uint64_t i = 0; i < PN; i++) {
+        PianoPIRClient &c = subPIR[i]->client;
+        uint64_t cnt = 0;
+        check(pm_search_cache_download(s, partBase / (uint32_t)PN, (uint32_t)i, nullptr, nullptr, 0, &cnt), "pm_search_cache_download");
+        c.localCache.Init(E);
+        c.localCache.Reserve(c.MaxQueryNum);
+        c.pendingCached.clear();
+        if (cnt == 0) continue;
+        idx.resize(cnt);
+        entries.resize(cnt * E);
+        check(pm_search_cache_download(s, partBase / (uint32_t)PN, (uint32_t)i, idx.data(), entries.data(), cnt, &cnt), "pm_search_cache_download");
+        for (uint64_t k = 0; k < cnt; k++) c.localCache.put(idx[k], &entries[k * E]);
+    }
+    hostMode = true;
 }
 
 double SimpleBatchPianoPIR::LocalStorageSize() const {

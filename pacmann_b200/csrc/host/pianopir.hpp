@@ -207,7 +207,8 @@ public:
     bool ownsDB = true;
     uint64_t FinishedBatchNum = 0, QueriesMadeInPartition = 0, SupportBatchNum = 0;
     uint64_t localStorage = 0, commCostPerBatchOnline = 0, commCostPerBatchOffline = 0;
-    double preprocessingTime = 0;
+    double preprocessingTime = 0, preprocessingTotal = 0;   // last / sum over all Preprocessing() calls (the "maintenance" of private-search.go:219-240)
+    uint64_t preprocessingCount = 0;
     uint64_t serverQueries = 0, serverLaunches = 0;  // accounting: sub-queries answered / pm_answer_batch calls
 
     // GPU-resident client (pm_client_*): hint tables stay in HBM, hint search / refresh run on the GPU.
@@ -232,6 +233,16 @@ public:
     // QueryFlat of several lanes of one pm_client at once.  Every lane ends in exactly the state its own QueryFlat
     // would have left (a lane that may exhaust a sub-PIR's budget inside this call is simply run on its own).
     static int QueryFlatGroup(std::vector<GroupCall> &calls, uint64_t dim);
+    // ---- device-resident search (pm_search_*): the owner of a client group also owns the search
+    // object; every lane keeps the host-side counters that need no entry data (batch budget, statistics).
+    pm_search *devSearch = nullptr;            // owner only
+    uint64_t devSearchKey = 0;                 // (max_step, parallel, start-vertex stamp) the object was built for
+    bool hostMode = false;                     // this lane left the device path (a sub-PIR budget about to run out); its local
+                                               // cache lives on the host until the next Preprocessing() of the whole batch
+    bool DeviceFetchAccounting(size_t n);      // batch-pir.go:239-245 for one device-built Query call; true = Preprocessing() due
+    void AbsorbDeviceRound(const uint64_t *finished, uint64_t serverQ);
+    bool DeviceRoundIsSafe(uint64_t maxStep, size_t n) const;   // no sub-PIR can reach its query budget within maxStep calls
+    void EnterHostMode(pm_search *s);          // pull this lane's device caches into the host-side localCache
     bool resident = false;
     bool ownsClient = true;
     uint32_t partBase = 0, clientLanes = 1;

@@ -67,8 +67,14 @@ __global__ void client_init_kernel(const ClientPartDev *parts, const uint32_t *p
 // of part_items.  The host builds these lists (a counting sort of q records) -- an earlier version let every CTA scan
 // the whole query array for its own entries, which at 3072 queries and 512 CTAs was most of the kernels' time.
 constexpr uint32_t CL_MAX_LIST = 2048;   // queries of one sub-PIR per call
+// Device-built calls (pm_search.cuh) use a fixed layout instead: CTA b owns records [b*fixed_per, (b+1)*fixed_per).
 __device__ __forceinline__ uint32_t client_load_list(const uint32_t *part_start, const uint32_t *part_items, uint32_t part,
-                                                      uint32_t *s_list, uint32_t cap) {
+                                                      uint32_t *s_list, uint32_t cap, uint32_t fixed_per = 0) {
+    if (fixed_per) {
+        for (uint32_t i = threadIdx.x; i < fixed_per; i += blockDim.x) s_list[i] = blockIdx.x * fixed_per + i;
+        __syncthreads();
+        return fixed_per;
+    }
     const uint32_t b = part_start[part], n = min(part_start[part + 1] - b, cap);
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) s_list[i] = part_items[b + i];
     __syncthreads();
@@ -121,7 +127,8 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
                                                                     const uint32_t *part_start, const uint32_t *part_items,
                                                                     uint32_t q, uint32_t stride, uint32_t *offsets,
                                                                     ClientMeta *meta, uint64_t *a_row0, uint64_t *a_nrows,
-                                                                    uint32_t *a_chunk, uint32_t *a_set, uint32_t mirror) {
+                                                                    uint32_t *a_chunk, uint32_t *a_set, uint32_t mirror,
+                                                                    const uint32_t *part_map, uint32_t fixed_per) {
     extern __shared__ uint32_t smem[];
     const uint32_t NT = blockDim.x;
     uint32_t *s_tab = smem;                           // compact Te0 (4 KB): few PRFs here, the shared memory buys occupancy
@@ -133,12 +140,12 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     __shared__ uint32_t s_hit;
     __shared__ int s_status;
     __shared__ uint64_t s_ingroup, s_newtag, s_fin;
-    const uint32_t part = blockIdx.x;
+    const uint32_t part = part_map ? part_map[blockIdx.x] : blockIdx.x;   // CTA b works for sub-PIR part_map[b] (device-built calls)
     const ClientPartDev &D = parts[part];
     const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
     const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
-    if (part_start[part] == part_start[part + 1]) return;
-    const uint32_t n_mine = client_load_list(part_start, part_items, part, s_list, CL_MAX_LIST);
+    if (!fixed_per && part_start[part] == part_start[part + 1]) return;
+    const uint32_t n_mine = client_load_list(part_start, part_items, part, s_list, CL_MAX_LIST, fixed_per);
     aes_tab_fill<8>(s_tab, c_te0);
     if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
     const bool indexed = D.poff != nullptr;
@@ -157,6 +164,10 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         const ClientQueryDev Q = queries[t];
         if (threadIdx.x == 0) {
             a_row0[t] = D.row0; a_nrows[t] = D.n_rows; a_chunk[t] = (uint32_t)C; a_set[t] = S;
+        }
+        if (Q.kind >= 2) {  // device-built call: a slot served from the client's cache or by an earlier record -- no server query
+            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, -2, 0}; a_set[t] = 0; }
+            continue;
         }
         if (Q.kind == 0) {  // dummy query: SetSize random offsets (pir.go:363-371)
             for (uint32_t c = threadIdx.x; c < S; c += NT)
@@ -299,15 +310,18 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
                                                             const uint32_t *part_items, const ClientMeta *meta, uint32_t E,
                                                             const uint64_t *__restrict__ answers, uint64_t *__restrict__ out,
                                                             const float *__restrict__ qv, const uint32_t *__restrict__ vid, uint32_t dim,
-                                                            float *__restrict__ dist_out) {
-    const uint32_t part = blockIdx.x;
+                                                            float *__restrict__ dist_out, const uint32_t *part_map, uint32_t fixed_per,
+                                                            uint64_t *const *__restrict__ out_rows) {
+    // out_rows (device-built calls): record t's entry goes to out_rows[t] instead of out + t*E -- the search keeps every
+    // successful answer in its client's local cache, so the answer is finished straight into its cache slot
+    const uint32_t part = part_map ? part_map[blockIdx.x] : blockIdx.x;
     const ClientPartDev &D = parts[part];
     const uint32_t E4 = E & ~3u;  // EntryXor granularity (xorSlices leaves the len%4 tail untouched)
     __shared__ uint32_t s_list[CL_MAX_LIST];
     struct FinMeta { uint32_t hit, slot; int32_t status; };
     __shared__ FinMeta s_meta[CL_MAX_LIST];
-    if (part_start[part] == part_start[part + 1]) return;
-    const uint32_t n_mine = client_load_list(part_start, part_items, part, s_list, CL_MAX_LIST);
+    if (!fixed_per && part_start[part] == part_start[part + 1]) return;
+    const uint32_t n_mine = client_load_list(part_start, part_items, part, s_list, CL_MAX_LIST, fixed_per);
     for (uint32_t k = threadIdx.x; k < n_mine; k += blockDim.x) {
         const ClientMeta m = meta[s_list[k]];
         s_meta[k] = FinMeta{(uint32_t)m.hit, (uint32_t)m.slot, m.status};
@@ -332,8 +346,9 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
             for (int j = 0; j < B; j++) {
                 if (k0 + j >= n_mine) break;
                 const uint32_t t = s_list[k0 + j];
+                uint64_t *orow = out_rows ? out_rows[t] : out + (uint64_t)t * E;
                 if (s_meta[k0 + j].status != 0) {  // dummy or failed: zero entry (pir.go:356-360)
-                    out[(uint64_t)t * E + w] = 0;
+                    orow[w] = 0;
                     continue;
                 }
                 uint64_t *par = D.parity + (uint64_t)s_meta[k0 + j].hit * E;
@@ -343,7 +358,7 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
                     np ^= r;                             // pir.go:463
                 }
                 par[w] = np;
-                out[(uint64_t)t * E + w] = r;
+                orow[w] = r;
             }
         }
     }
@@ -354,7 +369,7 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
     for (uint32_t k = threadIdx.x >> 1; k < n_up; k += blockDim.x >> 1) {
         const bool ok = k < n_mine;
         const uint32_t t = s_list[ok ? k : 0];
-        const float *a = reinterpret_cast<const float *>(out + (uint64_t)t * E);
+        const float *a = reinterpret_cast<const float *>(out_rows ? out_rows[t] : out + (uint64_t)t * E);
         const float *b = qv + (vid ? (uint64_t)vid[t] * dim : 0);
         const float d = l2_pair<false>(a, b, dim, half);
         if (ok && half == 0) dist_out[t] = d;
@@ -366,7 +381,12 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
 // =============================================================================================
 // C-ABI: pm_client_*
 // =============================================================================================
+struct pm_search;
+namespace pm {
+int search_clear_cache(pm_search *s, const uint32_t *part_ids, uint64_t n, cudaStream_t st);   // pm_search.cuh
+}
 struct pm_client {
+    pm_search *search = nullptr;   // device-resident search state attached to this client (its local caches follow the tables)
     pm_db *db;
     uint64_t n_parts, E;
     std::vector<pm::ClientPartDev> host_parts;  // device pointers inside
@@ -513,6 +533,7 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
     uint64_t *d_seed = (uint64_t *)((char *)d_tmp + ((n * 4 + 7) & ~7ull));
     PM_CUDA(cudaMemcpyAsync(d_ids, part_ids, n * 4, cudaMemcpyHostToDevice, c->stream));
     PM_CUDA(cudaMemcpyAsync(d_seed, repl_seed, n * 8, cudaMemcpyHostToDevice, c->stream));
+    if (c->search && (rc = search_clear_cache(c->search, part_ids, n, c->stream))) return rc;   // Initialization clears localCache (pir.go:127)
     dim3 grid((unsigned)std::min<uint64_t>((max_n + 255) / 256, 64), (unsigned)n);
     client_init_kernel<<<grid, 256, 0, c->stream>>>(c->d_parts, d_ids, d_seed, skip_prep);
     PM_CHECK_LAUNCH();
@@ -671,7 +692,7 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     // concurrent calls -- are resident at once (measured: one 32-lane group 139 -> 116 us, 4 x 16 lanes +5 % queries/s)
     const unsigned prep_threads = c->n_parts <= 64 ? CL_THREADS : CL_THREADS / 2;
     client_prepare_kernel<<<(unsigned)c->n_parts, prep_threads, smem, c->stream>>>(c->d_parts, d_q, d_start, d_items, (uint32_t)q, (uint32_t)stride,
-                                                                                  d_off, d_meta, d_row0, d_nrows, d_chunk, d_set, mirror);
+                                                                                  d_off, d_meta, d_row0, d_nrows, d_chunk, d_set, mirror, nullptr, 0);
     PM_CHECK_LAUNCH();
     count_launch();
     mark(2);
@@ -679,7 +700,7 @@ static int client_query_impl(pm_client *c, const pm_client_query *queries, uint6
     mark(3);
     // the distances of the answered entries' vectors to the search query (A10 call site) come out of the same launch
     client_finish_kernel<<<(unsigned)c->n_parts, 256, 0, c->stream>>>(c->d_parts, d_start, d_items, d_meta, (uint32_t)E, d_ans, d_res,
-                                                                      dist_out ? d_qv : nullptr, d_vid, (uint32_t)dim, dist_out ? d_dist : nullptr);
+                                                                      dist_out ? d_qv : nullptr, d_vid, (uint32_t)dim, dist_out ? d_dist : nullptr, nullptr, 0, nullptr);
     PM_CHECK_LAUNCH();
     count_launch();
     mark(4);

@@ -416,3 +416,4 @@ PM_EXPORT int pm_answer_batch(pm_db *db, const uint64_t *row0, const uint64_t *n
 
 #include "pm_l2.cuh"
 #include "pm_client.cuh"
+#include "pm_search.cuh"

@@ -132,6 +132,13 @@ def SearchKNNLockstep(lanes, queryVectors, k, maxStep, parallel, benchmarking=Fa
     return ret, step
 
 
+def DeviceSearchStats():
+    """(rounds, queries searched with the frontier on the GPU, queries of lanes in host mode) since the process started"""
+    out = np.zeros(3, np.uint64)
+    _host.lib().pmh_device_search_stats(_p(out))
+    return tuple(int(x) for x in out)
+
+
 def RobustPruneBatch(vectors, us, candidates, m, alpha, device=0):
     """robustPrune (build_graph.go:169-236) for many vertices at once: candidates[i] are the candidates of vertex us[i]
     (an [n][k] array; k <= m returns them unchanged as the reference does).  Every distance the reference evaluates --

@@ -198,6 +198,10 @@ class SimpleBatchPianoPIR:
     def PreprocessingTime(self):
         return _host.lib().pmh_batch_prep_time(self.h)
 
+    def PreprocessingTotal(self):
+        """(seconds spent in all Preprocessing() calls so far, their number): the maintenance the reference reports separately"""
+        return _host.lib().pmh_batch_prep_total(self.h), _host.lib().pmh_batch_prep_count(self.h)
+
 
 def NewSimpleBatchPianoPIR(DBSize, DBEntryByteNum, BatchSize, rawDB, FailureProbLog2, device=0):
     return SimpleBatchPianoPIR(DBSize, DBEntryByteNum, BatchSize, rawDB, FailureProbLog2, device)
