@@ -127,6 +127,10 @@ typedef struct pm_hint_job {
     const uint64_t *tags;          /* [n_hints] or NULL */
     const int32_t *skip_chunk;     /* [n_hints] or NULL */
     uint64_t *parity_out;          /* [n_hints][entry_u64] */
+    uint16_t *offsets_out;         /* optional (device pointer, pm_hintgen_dev only; chunk_size <= 65536):
+                                      [n_hints][(set_size + 7) & ~7] the offset PRF(rk, tag_i, c) & (chunk_size-1) of every
+                                      (hint, chunk) -- the kernel evaluates them all anyway; the resident client keeps them
+                                      as its offset index so that the online hint search needs no AES */
 } pm_hint_job;
 
 int pm_hintgen(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs);

@@ -31,7 +31,7 @@ class HintJob(C.Structure):
         ("rk", C.c_uint32 * 44),
         ("hint_begin", C.c_uint64), ("n_hints", C.c_uint64),
         ("n_primary", C.c_uint64), ("backup_group", C.c_uint64),
-        ("tags", C.c_void_p), ("skip_chunk", C.c_void_p), ("parity_out", C.c_void_p),
+        ("tags", C.c_void_p), ("skip_chunk", C.c_void_p), ("parity_out", C.c_void_p), ("offsets_out", C.c_void_p),
     ]
 
 
@@ -293,14 +293,14 @@ def xor_slices(dst, src):
 
 
 def make_job(row0, n_rows, chunk_size, set_size, rk, hint_begin, n_hints, n_primary, backup_group,
-             tags=None, skip_chunk=None, parity_out=None):
+             tags=None, skip_chunk=None, parity_out=None, offsets_out=None):
     j = HintJob()
     j.row0, j.n_rows, j.chunk_size, j.set_size = row0, n_rows, chunk_size, set_size
     rk = _arr(rk, np.uint32)
     assert rk.size == 44
     C.memmove(j.rk, rk.ctypes.data, 176)
     j.hint_begin, j.n_hints, j.n_primary, j.backup_group = hint_begin, n_hints, n_primary, backup_group
-    j.tags, j.skip_chunk, j.parity_out = _addr(tags), _addr(skip_chunk), _addr(parity_out)
+    j.tags, j.skip_chunk, j.parity_out, j.offsets_out = _addr(tags), _addr(skip_chunk), _addr(parity_out), _addr(offsets_out)
     return j
 
 

@@ -30,6 +30,8 @@ struct ClientPartDev {
     uint64_t *hist;                            // [S]
     uint64_t *finished;                        // [1]
     uint16_t *poff;                            // [S][P] offset index of the primary hints (nullptr if chunk_size > 65536)
+    uint16_t *roff;                            // [P+B][spad] the offsets of EVERY hint, row-major, as the hint kernel emits them:
+    uint32_t spad;                             // the promoted backup hint's row is copied from here (no AES online); spad = (S+7)&~7
     uint32_t *pp32;                            // [P] program points once more as u32 (all values < 2^31), 16-byte aligned: the
                                                // prepare kernel mirrors them in shared memory with a few vector loads
 };
@@ -86,27 +88,46 @@ struct RkOfPtr {
     __device__ __forceinline__ uint32_t operator[](int i) const { return p[i]; }
 };
 
-// Offset index of the primary hints: poff[c][i] = PRF(tag_i, c) & (ChunkSize-1).  With it the online hint search
-// (pir.go:405-414, up to primaryHintNum AES evaluations per query) is a scan of one 2*P-byte column and the set
-// expansion (pir.go:424-427) a strided read of one row; only a promoted backup hint costs SetSize PRF evaluations
-// (its row is rewritten).  Filled once per preprocessing: one thread per hint, all chunks, coalesced 2-byte stores.
-__global__ void __launch_bounds__(256) client_fill_poff_kernel(const ClientPartDev *parts, const uint32_t *part_ids) {
+// Offset index.  poff[c][i] = PRF(tag_i, c) & (ChunkSize-1) for the primary hints: with it the online hint search
+// (pir.go:405-414, up to primaryHintNum AES evaluations per query) is a scan of one 2*P-byte column and the set expansion
+// (pir.go:424-427) a strided read of one row.  roff[h][c] holds the same for EVERY hint in hint-number order, row-major:
+// the hint kernel evaluates all those PRFs anyway and writes them as a side output (pm_hint_job.offsets_out), so building
+// the index costs a transpose, and a promoted backup hint's row (pir.go:460-463) is a copy -- the online path runs no AES.
+// DummyPreprocessing (no hint kernel) fills roff here instead.
+__global__ void __launch_bounds__(256) client_fill_roff_kernel(const ClientPartDev *parts, const uint32_t *part_ids) {
     extern __shared__ uint32_t smem[];
     __shared__ uint32_t s_rk[44];
     const ClientPartDev &D = parts[part_ids[blockIdx.y]];
     aes_tab_fill<1>(smem, c_te0);
     if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
     __syncthreads();
-    if (!D.poff) return;
+    if (!D.roff) return;
     const AesTab<1> T{smem + (threadIdx.x & 31)};
     const RkOfPtr R{s_rk};
-    const uint64_t P = D.n_primary;
+    const uint64_t H = D.n_primary + D.set_size * D.backup_group;
     const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P; i += (uint64_t)gridDim.x * blockDim.x) {
-        const PrfTagPart g = prf_tag_part(T, R, D.tags[i]);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < H; i += (uint64_t)gridDim.x * blockDim.x) {
+        const PrfTagPart g = prf_tag_part(T, R, i);      // Initialization numbering: tag == hint number
 #pragma unroll 2
-        for (uint32_t c = 0; c < S; c++) D.poff[(uint64_t)c * P + i] = (uint16_t)(prf_low<1, 2>(T, R, g, c) & cmask);
+        for (uint32_t c = 0; c < S; c++) D.roff[i * D.spad + c] = (uint16_t)(prf_low<1, 2>(T, R, g, c) & cmask);
     }
+}
+// poff[c][i] = roff[i][c] for the primary hints (tiles of 32 x 32 through shared memory)
+__global__ void __launch_bounds__(256) client_transpose_kernel(const ClientPartDev *parts, const uint32_t *part_ids) {
+    __shared__ uint16_t tile[32][34];
+    const ClientPartDev &D = parts[part_ids[blockIdx.z]];
+    if (!D.poff) return;
+    const uint64_t P = D.n_primary;
+    const uint32_t S = (uint32_t)D.set_size, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (uint64_t i0 = (uint64_t)blockIdx.x * 32; i0 < P; i0 += (uint64_t)gridDim.x * 32)
+        for (uint32_t c0 = blockIdx.y * 32; c0 < S; c0 += gridDim.y * 32) {
+            for (uint32_t r = ty; r < 32; r += 8)
+                if (i0 + r < P && c0 + tx < S) tile[r][tx] = D.roff[(i0 + r) * D.spad + c0 + tx];
+            __syncthreads();
+            for (uint32_t r = ty; r < 32; r += 8)
+                if (c0 + r < S && i0 + tx < P) D.poff[(uint64_t)(c0 + r) * P + i0 + tx] = tile[tx][r];
+            __syncthreads();
+        }
 }
 
 struct ClientQueryDev {  // mirrors pm_client_query
@@ -119,10 +140,14 @@ struct ClientMeta {
     int32_t pad;
 };
 
-// Per query the critical path is two global round trips and one PRF: phase A loads the query's column of the offset
-// index together with the budget counters, phase B the hit hint's row together with the scalars thread 0 needs,
-// phase C rewrites the promoted backup hint's row.  Program points are mirrored in shared memory (u32) so the
-// not-programmed-in-this-chunk test needs no dependent load.
+// Per query the critical path is two global round trips and two barriers:
+//   A  the query's column of the offset index (the first-match search of pir.go:405-414 without any AES; program points
+//      mirrored in shared memory) -- while one thread fetches the budget counters and, behind them, the replacement index
+//      and the backup tag of the slot this query will consume;
+//   B  the hit hint's row of the index (= the set expansion of pir.go:424-427) together with the promoted backup hint's
+//      row; every thread patches its own chunk (programmed point, replacement) and stores the offset for the server and
+//      the new index entry, thread 0 books the response-independent half of the refresh.
+// Instances without the 16-bit index (chunk_size > 65536) evaluate the PRF instead.
 __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const ClientPartDev *parts, const ClientQueryDev *queries,
                                                                     const uint32_t *part_start, const uint32_t *part_items,
                                                                     uint32_t q, uint32_t stride, uint32_t *offsets,
@@ -133,28 +158,31 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
     const uint32_t NT = blockDim.x;
     uint32_t *s_tab = smem;                           // compact Te0 (4 KB): few PRFs here, the shared memory buys occupancy
     uint32_t *s_rk = smem + aes_tab_words<8>();       // 44 round-key words
-    uint32_t *s_offs = s_rk + 64;                     // [stride]
+    uint32_t *s_offs = s_rk + 64;                     // [stride] (PRF path only)
     uint32_t *s_list = s_offs + stride;               // [CL_MAX_LIST]
     uint32_t *s_pp = s_list + CL_MAX_LIST;            // [P] program points (offset index in use and `mirror`: they fit in shared
                                                       // memory; pir_test's 2^20-row instance has P = 59392 and reads pp32 instead)
     __shared__ uint32_t s_hit;
     __shared__ int s_status;
-    __shared__ uint64_t s_ingroup, s_newtag, s_fin;
+    __shared__ uint64_t s_ingroup, s_fin, s_ridx, s_btag;
     const uint32_t part = part_map ? part_map[blockIdx.x] : blockIdx.x;   // CTA b works for sub-PIR part_map[b] (device-built calls)
     const ClientPartDev &D = parts[part];
     const uint32_t S = (uint32_t)D.set_size, cmask = D.chunk_mask;
     const uint64_t C = D.chunk_size, M = D.backup_group, P = D.n_primary;
     if (!fixed_per && part_start[part] == part_start[part + 1]) return;
     const uint32_t n_mine = client_load_list(part_start, part_items, part, s_list, CL_MAX_LIST, fixed_per);
-    aes_tab_fill<8>(s_tab, c_te0);
-    if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
     const bool indexed = D.poff != nullptr;
+    if (!indexed) {   // only instances without the 16-bit offset index evaluate the PRF online
+        aes_tab_fill<8>(s_tab, c_te0);
+        if (threadIdx.x < 44) s_rk[threadIdx.x] = D.rk[threadIdx.x];
+    }
     if (indexed && mirror) {   // values < 2^31 or 0x7fffffff; s_pp is 16-byte aligned (every region before it is a multiple of 4 words)
         const uint4 *src = reinterpret_cast<const uint4 *>(D.pp32);
         uint4 *dst = reinterpret_cast<uint4 *>(s_pp);
         for (uint64_t i = threadIdx.x; i < P / 4; i += NT) dst[i] = __ldcg(src + i);
         for (uint64_t i = (P & ~3ull) + threadIdx.x; i < P; i += NT) s_pp[i] = D.pp32[i];
     }
+    if (threadIdx.x == 0) { s_fin = *D.finished; s_hit = 0xffffffffu; }   // only this CTA changes the part's counters during the call
     __syncthreads();
     const AesTab<8> T{s_tab + (threadIdx.x & 3)};
     const RkOfPtr R{s_rk};
@@ -176,14 +204,17 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             continue;
         }
         const uint64_t chunkId = Q.idx / C, offset = Q.idx % C;
-        // ---- phase A: budget counters + first-match search (pir.go:386-414) ----
-        if (threadIdx.x == 0) s_hit = 0xffffffffu;
-        __syncthreads();
-        if (threadIdx.x == 32) {   // a lane of another warp than the one that is busiest in the scan tail
-            const uint64_t fin = *D.finished, h = D.hist[chunkId];
-            s_status = fin >= D.max_query_num ? 2 : (h >= M ? 3 : 0);   // pir.go:386-391, 396-400
+        // ---- phase A: budget counters + first-match search (pir.go:386-414); s_hit was reset behind the last barrier ----
+        if (threadIdx.x == 32 % NT) {   // a lane of another warp than the one that is busiest in the scan tail
+            const uint64_t fin = s_fin, h = D.hist[chunkId];
+            const int st = fin >= D.max_query_num ? 2 : (h >= M ? 3 : 0);   // pir.go:386-391, 396-400
+            s_status = st;
             s_ingroup = h;
-            s_fin = fin;
+            if (st == 0) {   // the slot this query consumes: replacement index and backup tag (pir.go:436-439, 460)
+                const uint64_t slot = chunkId * M + h;
+                s_ridx = D.ridx[slot];
+                s_btag = D.btags[slot];
+            }
         }
         uint32_t hit = 0xffffffffu;
         if (indexed) {  // scan one column of the offset index: no AES
@@ -255,50 +286,55 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         }
         const int status = s_status != 0 ? s_status : (hit == 0xffffffffu ? 4 : 0);   // pir.go:416-419
         if (status != 0) {
-            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, status, 0}; a_set[t] = 0; }
+            if (threadIdx.x == 0) { meta[t] = ClientMeta{0, 0, status, 0}; a_set[t] = 0; s_hit = 0xffffffffu; }
             __syncthreads();
             continue;
         }
-        // ---- phase B: expand the hit hint to a full set (pir.go:424-427) + the scalars of the refresh ----
-        const uint64_t inGroup = s_ingroup, slot = chunkId * M + inGroup;
-        uint64_t ridx = 0, btag = 0, pp_hit = 0;
-        if (threadIdx.x == 0) {
-            ridx = D.ridx[slot];
-            btag = D.btags[slot];
-            pp_hit = indexed ? (uint64_t)(mirror ? s_pp[hit] : __ldcg(D.pp32 + hit)) : D.pp[hit];
-        }
+        // ---- phase B: expand the hit hint to a full set (pir.go:424-427), patch it (pir.go:430-439), hand it to the server kernel;
+        // the promoted backup hint takes over the slot (pir.go:460-467) ----
+        const uint64_t inGroup = s_ingroup, slot = chunkId * M + inGroup, ridx = s_ridx, btag = s_btag;
         if (indexed) {
-            for (uint32_t c = threadIdx.x; c < S; c += NT) s_offs[c] = __ldcg(D.poff + (uint64_t)c * P + hit);
+            const uint64_t pp_hit = mirror ? (uint64_t)s_pp[hit] : (uint64_t)__ldcg(D.pp32 + hit);
+            const uint32_t c_pp = pp_hit != kDefaultProgramPoint ? (uint32_t)(pp_hit / C) : 0xffffffffu;
+            const uint16_t *row = D.roff + (P + slot) * D.spad;     // offsets of the backup hint, evaluated by the hint kernel
+            for (uint32_t c = threadIdx.x; c < S; c += NT) {
+                uint32_t v = __ldcg(D.poff + (uint64_t)c * P + hit);
+                const uint16_t nv = __ldcg(row + c);
+                if (c == c_pp) v = (uint32_t)(pp_hit & cmask);                // pir.go:430-433
+                if (c == (uint32_t)chunkId) v = (uint32_t)(ridx & cmask);     // pir.go:436-439
+                offsets[(uint64_t)t * stride + c] = v;
+                D.poff[(uint64_t)c * P + hit] = nv;
+            }
+            __syncthreads();   // every thread has read s_pp[hit] before thread 0 replaces it
         } else {
             const PrfTagPart g = prf_tag_part(T, R, D.tags[hit]);
             for (uint32_t c = threadIdx.x; c < S; c += NT) s_offs[c] = prf_low<8, 4>(T, R, g, c) & cmask;
+            const uint64_t pp_hit = D.pp[hit];
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                if (pp_hit != kDefaultProgramPoint) s_offs[pp_hit / C] = (uint32_t)(pp_hit & cmask);
+                s_offs[chunkId] = (uint32_t)(ridx & cmask);
+            }
+            __syncthreads();
+            for (uint32_t c = threadIdx.x; c < S; c += NT) offsets[(uint64_t)t * stride + c] = s_offs[c];
         }
-        __syncthreads();
         if (threadIdx.x == 0) {
-            if (pp_hit != kDefaultProgramPoint) s_offs[pp_hit / C] = (uint32_t)(pp_hit & cmask);   // pir.go:430-433
-            s_offs[chunkId] = (uint32_t)(ridx & cmask);                                            // pir.go:436-439
             meta[t] = ClientMeta{hit, slot, 0, 0};
             // response-independent half of the refresh (pir.go:460-467)
             D.tags[hit] = btag;
             D.pp[hit] = Q.idx;
             D.pp32[hit] = (uint32_t)Q.idx;
             if (indexed && mirror) s_pp[hit] = (uint32_t)Q.idx;
-            *D.finished = s_fin + 1;
+            s_fin += 1;
+            *D.finished = s_fin;
             D.hist[chunkId] = inGroup + 1;
-            s_newtag = btag;
-        }
-        __syncthreads();
-        // ---- phase C: hand the offsets to the server kernel; the promoted backup hint takes over the slot ----
-        for (uint32_t c = threadIdx.x; c < S; c += NT) offsets[(uint64_t)t * stride + c] = s_offs[c];
-        if (indexed) {
-            const PrfTagPart g = prf_tag_part(T, R, s_newtag);
-            for (uint32_t c = threadIdx.x; c < S; c += NT)
-                D.poff[(uint64_t)c * P + hit] = (uint16_t)(prf_low<8, 2>(T, R, g, c) & cmask);
+            s_hit = 0xffffffffu;
         }
         __threadfence_block();
         __syncthreads();
     }
 }
+
 
 // Thread w owns word w of every entry, so the only cross-query dependency -- two queries of a part refreshing
 // the same hint slot -- is a read-after-write inside one thread: no barrier is needed, and the operands that do not
@@ -441,7 +477,7 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
             return set_error(PM_ERR_ARG, "pm_client_create: bad geometry for part %llu", (unsigned long long)i);
         const uint64_t P = p.n_primary, B = p.set_size * p.backup_group;
         words += 2 * P + P * E + 2 * B + 2 * B * E + p.set_size + 2;
-        if (p.chunk_size <= 65536) words += (p.set_size * P * 2 + 7) / 8 + 2;   // offset index
+        if (p.chunk_size <= 65536) words += (p.set_size * P * 2 + 7) / 8 + 2 + ((P + B) * ((p.set_size + 7) & ~7ull) * 2 + 7) / 8 + 2;   // offset index
         words += (P * 4 + 7) / 8 + 2;                                           // u32 program points
         words = (words + 3) & ~1ull;
         if (p.set_size > max_set) max_set = p.set_size;
@@ -474,9 +510,14 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
         D.finished = cur; cur += 2;
         if ((uintptr_t)cur & 15) cur += 1;
         D.poff = nullptr;
+        D.roff = nullptr;
+        D.spad = (uint32_t)((p.set_size + 7) & ~7ull);
         if (p.chunk_size <= 65536) {
             D.poff = (uint16_t *)cur;
             cur += (p.set_size * P * 2 + 7) / 8;
+            if ((uintptr_t)cur & 15) cur += 1;
+            D.roff = (uint16_t *)cur;
+            cur += ((P + B) * D.spad * 2 + 7) / 8;
             if ((uintptr_t)cur & 15) cur += 1;
         }
         D.pp32 = (uint32_t *)cur;
@@ -538,12 +579,15 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
     client_init_kernel<<<grid, 256, 0, c->stream>>>(c->d_parts, d_ids, d_seed, skip_prep);
     PM_CHECK_LAUNCH();
     count_launch();
-    {
-        uint64_t max_p = 0;
-        for (uint64_t a = 0; a < n; a++) max_p = std::max<uint64_t>(max_p, c->host_parts[part_ids[a]].n_primary);
-        dim3 fgrid((unsigned)std::max<uint64_t>(1, (max_p + 255) / 256), (unsigned)n);
-        PM_CUDA(cudaFuncSetAttribute(client_fill_poff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_tab_words<1>() * 4));
-        client_fill_poff_kernel<<<fgrid, 256, aes_tab_words<1>() * 4, c->stream>>>(c->d_parts, d_ids);
+    if (skip_prep) {   // DummyPreprocessing runs no hint kernel: the offsets of all hints are evaluated here
+        uint64_t max_h = 0;
+        for (uint64_t a = 0; a < n; a++) {
+            const ClientPartDev &D = c->host_parts[part_ids[a]];
+            max_h = std::max<uint64_t>(max_h, D.n_primary + D.set_size * D.backup_group);
+        }
+        dim3 fgrid((unsigned)std::max<uint64_t>(1, (max_h + 255) / 256), (unsigned)n);
+        PM_CUDA(cudaFuncSetAttribute(client_fill_roff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, aes_tab_words<1>() * 4));
+        client_fill_roff_kernel<<<fgrid, 256, aes_tab_words<1>() * 4, c->stream>>>(c->d_parts, d_ids);
         PM_CHECK_LAUNCH();
         count_launch();
     }
@@ -561,6 +605,7 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
         memcpy(j.rk, D.rk, sizeof(j.rk));
         j.hint_begin = 0; j.n_hints = P + B; j.n_primary = P; j.backup_group = D.backup_group;
         j.parity_out = D.parity;
+        j.offsets_out = D.roff;     // nullptr when chunk_size > 65536 (no 16-bit index)
         jobs.push_back(j);
     }
     if (!jobs.empty()) {
@@ -569,6 +614,14 @@ PM_EXPORT int pm_client_preprocess(pm_client *c, const uint32_t *part_ids, uint6
             const ClientPartDev &D = c->host_parts[part_ids[a]];
             if ((rc = gather_enqueue(db, D.row0, D.n_rows, D.ridx, D.set_size * D.backup_group, D.rval, c->stream))) return rc;
         }
+    }
+    {   // primary rows of roff -> the column-major index the hint search scans
+        uint64_t max_p = 0;
+        for (uint64_t a = 0; a < n; a++) max_p = std::max<uint64_t>(max_p, c->host_parts[part_ids[a]].n_primary);
+        dim3 tgrid((unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (max_p + 31) / 32), 256), 8, (unsigned)n);
+        client_transpose_kernel<<<tgrid, 256, 0, c->stream>>>(c->d_parts, d_ids);
+        PM_CHECK_LAUNCH();
+        count_launch();
     }
     PM_CUDA(cudaStreamSynchronize(c->stream));
     return PM_OK;

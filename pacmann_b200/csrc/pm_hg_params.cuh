@@ -18,6 +18,7 @@ struct HintJobDev {
     const uint64_t *tags;
     const int32_t *skip;
     uint64_t *out;
+    uint16_t *off;      // optional offset index output [n_hints][(set_size + 7) & ~7]
     uint32_t chunk_mask, chunk_shift, set_size, tile_begin;
 };
 struct HintParams {

@@ -81,6 +81,7 @@ int hintgen_enqueue(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs, cudaStr
             D.row0 = J.row0; D.n_rows = J.n_rows;
             D.hint_begin = J.hint_begin; D.n_hints = J.n_hints; D.n_primary = J.n_primary; D.backup_group = J.backup_group;
             D.tags = J.tags; D.skip = J.skip_chunk; D.out = J.parity_out;
+            D.off = J.chunk_size <= 65536 ? J.offsets_out : nullptr;
             D.chunk_mask = (uint32_t)(J.chunk_size - 1);
             D.chunk_shift = (uint32_t)__builtin_ctzll(J.chunk_size);
             D.set_size = (uint32_t)J.set_size;
@@ -163,6 +164,7 @@ PM_EXPORT int pm_hintgen(pm_db *db, const pm_hint_job *jobs, uint64_t n_jobs) {
     std::vector<pm_hint_job> dj(jobs, jobs + n_jobs);
     uint64_t ho = 0, to = 0, so = 0;
     for (uint64_t a = 0; a < n_jobs; a++) {
+        dj[a].offsets_out = nullptr;   // a device-side output: not part of the host-buffer call
         dj[a].parity_out = (uint64_t *)d_out + ho * E;
         ho += jobs[a].n_hints;
         if (jobs[a].n_hints && !jobs[a].parity_out) return set_error(PM_ERR_ARG, "pm_hintgen: parity_out is null");

@@ -136,9 +136,13 @@ __device__ PM_HG_SWEEP_INLINE void hg_sweep(const HintParams &P, const AesTab<NT
     };
     const uint32_t c_step = rev ? (uint32_t)(-G) : (uint32_t)G;
     uint32_t c_cur = (rev ? g_end - 1 : g_begin) * G + gl;   // this lane's chunk of the current group
+    // optional side output: the offset of every (hint, chunk) this sweep evaluates, row-major per hint (16 contiguous bytes
+    // per lane group and step); the resident client builds its offset index from it
+    uint16_t *off_row = (J.off && active) ? J.off + i * ((S + 7) & ~7u) : nullptr;
     PrfState st;
     prf_rounds<XB, NTAB, NB, 1, 10>(T, R, g, c_cur, st);  // prologue: rows of the first group
     uint32_t row_next = to_row(c_cur, st.s0);
+    if (off_row && c_cur < S) off_row[c_cur] = (uint16_t)(st.s0 & cmask);
     for (uint32_t it = g_begin; it < g_end; it++) {
         // c_next runs one group past the range in the last iteration: that PRF value is never used
         const uint32_t row_cur = row_next, c_next = c_cur + c_step;
@@ -149,6 +153,7 @@ __device__ PM_HG_SWEEP_INLINE void hg_sweep(const HintParams &P, const AesTab<NT
             hg_phase<VT, G, NV, NTAB, NB, XB, U, FULL, (NPH > 2 ? 3 : 0), NPH>(T, R, g, c_next, st, row_cur, gbase, gl, base, ev, evx, par);
         }
         row_next = to_row(c_next, st.s0);
+        if (off_row && it + 1 < g_end && c_next < S) off_row[c_next] = (uint16_t)(st.s0 & cmask);
         c_cur = c_next;
     }
     if (!active) return;
@@ -176,9 +181,11 @@ __global__ void __launch_bounds__(HG_MAX_THREADS, 1) hintgen_kernel(const __grid
     const uint32_t rounds = P.full_rounds + (P.tail_tiles ? 1u : 0u);
     for (uint32_t round = 0; round < rounds; round++) {
         if (P.sync && round > 0) {   // round barrier: every sweep starts together
+            // A rendezvous in time only: no CTA reads what another wrote, so there is deliberately NO memory fence here -- a
+            // fence would wait for this CTA's parity stores to be performed, and with the table in a peer GPU's memory
+            // that is an NVLink drain per round (measured at 8 GPUs: 0.72 ms per step instead of 0.5).
             __syncthreads();
             if (threadIdx.x == 0) {
-                __threadfence();
                 atomicAdd(P.sync, 1u);
                 const unsigned int target = round * gridDim.x;
                 unsigned int seen;

@@ -60,35 +60,40 @@ __device__ __forceinline__ void hash_put(uint32_t *keys, uint32_t *vals, uint32_
 
 // container/heap (search.go:92-111): Push = append + up, Pop = swap(0, n-1) + down(0, n-1) + remove last; Less = dist <
 struct HeapView { float *d; uint32_t *s; uint32_t n; };
-__device__ __forceinline__ void heap_swap(HeapView &h, uint32_t i, uint32_t j) {
-    const float td = h.d[i]; h.d[i] = h.d[j]; h.d[j] = td;
-    const uint32_t ts = h.s[i]; h.s[i] = h.s[j]; h.s[j] = ts;
-}
+// Both walks keep the moving element in registers and shift the others (the arrangement they leave is the one the
+// reference's swap-based up/down leaves: the same comparisons in the same order decide where the element stops).
 __device__ void heap_push(HeapView &h, float dist, uint32_t slot) {
     uint32_t j = h.n++;
-    h.d[j] = dist; h.s[j] = slot;
     while (j > 0) {
         const uint32_t i = (j - 1) / 2;
-        if (!(h.d[j] < h.d[i])) break;
-        heap_swap(h, i, j);
+        const float di = h.d[i];
+        if (!(dist < di)) break;
+        h.d[j] = di; h.s[j] = h.s[i];
         j = i;
     }
+    h.d[j] = dist; h.s[j] = slot;
 }
 __device__ uint32_t heap_pop(HeapView &h) {
-    const uint32_t n = h.n - 1;
-    heap_swap(h, 0, n);
+    const uint32_t n = h.n - 1, top = h.s[0];
+    const float x = h.d[n];          // heap.Pop: Swap(0, n-1), down(0, n-1): the last element sinks from the root
+    const uint32_t xs = h.s[n];
     uint32_t i = 0;
     for (;;) {
         const uint32_t j1 = 2 * i + 1;
         if (j1 >= n) break;
         uint32_t j = j1;
-        if (j1 + 1 < n && h.d[j1 + 1] < h.d[j1]) j = j1 + 1;
-        if (!(h.d[j] < h.d[i])) break;
-        heap_swap(h, i, j);
+        float dj = h.d[j1];
+        if (j1 + 1 < n) {
+            const float d2 = h.d[j1 + 1];
+            if (d2 < dj) { j = j1 + 1; dj = d2; }
+        }
+        if (!(dj < x)) break;
+        h.d[i] = dj; h.s[i] = h.s[j];
         i = j;
     }
+    if (n > 0) { h.d[i] = x; h.s[i] = xs; }
     h.n = n;
-    return h.s[n];
+    return top;
 }
 
 constexpr int SR_THREADS = 128;
