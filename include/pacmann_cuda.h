@@ -93,6 +93,8 @@ int pm_buf_ipc_close(void *dev_ptr, int device);
 int pm_buf_upload(void *dev_ptr, const void *host, uint64_t bytes, int device);
 int pm_buf_download(void *host, const void *dev_ptr, uint64_t bytes, int device);
 int pm_buf_zero(void *dev_ptr, uint64_t bytes, int device);
+/* asynchronous device-to-device copy on `stream` (either side may be a peer GPU's IPC-mapped buffer: copy engines over NVLink) */
+int pm_buf_copy_dev(void *dst, const void *src, uint64_t bytes, int device, void *stream);
 /* Completion flags for the peer-memory exchange.  `flags` points at (n_flags + 1) 128-byte lines in device memory
  * (usually inside the consumer's IPC-shared buffer, zeroed once): line i holds rank i's counter in its first uint32,
  * line n_flags a timeout marker.  pm_flag_signal_dev adds 1 to ONE counter (system-scope release) once everything

@@ -58,6 +58,7 @@ SIGNATURES = {
     "pm_buf_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "pm_buf_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "pm_buf_zero": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int]),
+    "pm_buf_copy_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "pm_flag_signal_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "pm_flag_wait_dev": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]),
     "pm_host_register": (C.c_int, [C.c_void_p, C.c_uint64]),
@@ -247,6 +248,10 @@ def buf_download(ptr, host, device=0):
     assert host.flags.c_contiguous
     check(lib().pm_buf_download(_ptr(host), ptr, host.nbytes, device))
     return host
+
+
+def buf_copy_dev(dst, src, nbytes, device=0, stream=None):
+    check(lib().pm_buf_copy_dev(dst, src, nbytes, device, stream))
 
 
 def buf_zero(ptr, nbytes, device=0):

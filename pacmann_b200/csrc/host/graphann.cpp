@@ -490,6 +490,13 @@ int GraphANNFrontend::SearchKNNBatch(const float *queryVectors, int64_t nq, int6
     Graph->GetMetadata(&n, &dim, &m);
     ret->assign((size_t)(nq * k), -1);
     stepRet->assign((size_t)(nq * k), -1);
+    // a single resident client is a lock-step group of one lane: its searches run with the frontier on the GPU as well
+    // (same results; the host only enqueues the steps)
+    if (auto *pg = dynamic_cast<PIRGraphInfo *>(Graph))
+        if (!pg->NonPrivateMode && pg->PIR && pg->PIR->resident && pg->PIR->clientLanes == 1 && pg->PIR->ownsClient && nq > 0) {
+            std::vector<GraphANNFrontend *> one{this};
+            return SearchKNNLockstep(one, queryVectors, nq, k, maxStep, parallel, benchmarking, ret, stepRet);
+        }
     std::vector<int64_t> r, s;
     for (int64_t i = 0; i < nq; i++) {  // search.go:236-245: a plain loop
         if (SearchKNN(queryVectors + i * dim, k, maxStep, parallel, benchmarking, &r, &s) != 0) return -1;

@@ -141,6 +141,65 @@ __global__ void __launch_bounds__(IP_THREADS, 2) ip_scan_kernel(const uint4 *row
     }
 }
 
+// Few queries, checksums only (the reference's scan loop keeps nothing but the sum, graphann_test.go:268-273): a pure
+// stream.  Thread t walks the table as 16-byte vectors t, t + T, t + 2T, ... (T = all threads: fully coalesced, no shared
+// memory staging, eight loads in flight per thread); its column index advances by T mod dim4 with one conditional
+// subtract.  Integer sums mod 2^32 are order-free, so the result is the reference's bit for bit.
+constexpr int IPS_THREADS = 256, IPS_UNROLL = 8;
+template <int QT>
+__global__ void __launch_bounds__(IPS_THREADS) ip_stream_kernel(const uint4 *__restrict__ rows, uint64_t n_vec, uint32_t dim4,
+                                                                const uint32_t *queries, uint32_t n_queries, uint32_t q0, uint32_t *checksum) {
+    extern __shared__ __align__(16) uint32_t s_qw[];
+    uint4 *s_q4 = reinterpret_cast<uint4 *>(s_qw);           // [QT][dim4]
+    const uint32_t nq = min((uint32_t)QT, n_queries - q0);
+    for (uint32_t i = threadIdx.x; i < QT * dim4; i += IPS_THREADS) {
+        const uint32_t t = i / dim4, c = i % dim4;
+        s_q4[i] = t < nq ? reinterpret_cast<const uint4 *>(queries)[(uint64_t)(q0 + t) * dim4 + c] : make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+    const uint64_t T = (uint64_t)gridDim.x * IPS_THREADS;
+    const uint32_t step = (uint32_t)(T % dim4);
+    uint64_t idx = (uint64_t)blockIdx.x * IPS_THREADS + threadIdx.x;
+    uint32_t c = (uint32_t)(idx % dim4);
+    uint32_t total[QT];
+#pragma unroll
+    for (int t = 0; t < QT; t++) total[t] = 0;
+    while (idx < n_vec) {
+        uint4 v[IPS_UNROLL];
+        uint32_t cc[IPS_UNROLL];
+#pragma unroll
+        for (int u = 0; u < IPS_UNROLL; u++) {
+            const uint64_t i = idx + (uint64_t)u * T;
+            cc[u] = c;
+            v[u] = i < n_vec ? ldg_stream(rows + i) : make_uint4(0, 0, 0, 0);
+            c += step;
+            if (c >= dim4) c -= dim4;
+        }
+#pragma unroll
+        for (int u = 0; u < IPS_UNROLL; u++)
+#pragma unroll
+            for (int t = 0; t < QT; t++) {
+                const uint4 qv = s_q4[t * dim4 + cc[u]];
+                total[t] += v[u].x * qv.x + v[u].y * qv.y + v[u].z * qv.z + v[u].w * qv.w;
+            }
+        idx += (uint64_t)IPS_UNROLL * T;
+    }
+    __shared__ uint32_t s_red[IPS_THREADS / 32][QT];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < QT; t++) {
+        uint32_t v = total[t];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][t] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < nq) {
+        uint32_t v = 0;
+        for (int w = 0; w < IPS_THREADS / 32; w++) v += s_red[w][threadIdx.x];
+        atomicAdd(checksum + q0 + threadIdx.x, v);
+    }
+}
+
 // out[i] = L2Dist(a + i*a_stride, b + i*b_stride) for device-resident rows (strides in floats; b_stride 0 = one query)
 int l2_batch_enqueue(pm_db *db, uint64_t dim, const float *queries, uint64_t nq, const int64_t *ids, uint64_t k, float *out,
                      cudaStream_t st) {
@@ -193,6 +252,17 @@ int ip_scan_enqueue(pm_db *db, uint64_t dim, const uint32_t *queries, uint64_t n
     };
     uint64_t q0 = 0;
     int rc = PM_OK;
+    if (!ip_out && nq <= 4) {   // checksums of a few queries: the streaming kernel (no staging), one pass
+        const uint64_t n_vec = db->n_rows * dim4;
+        const unsigned sblocks = (unsigned)std::min<uint64_t>(std::max<uint64_t>(1, (n_vec + IPS_THREADS * IPS_UNROLL - 1) / (IPS_THREADS * IPS_UNROLL)),
+                                                               (uint64_t)db->sm_count * 8);
+        const size_t smem = (size_t)(nq == 1 ? 1 : 4) * dim * 4;
+        if (nq == 1) ip_stream_kernel<1><<<sblocks, IPS_THREADS, smem, st>>>((const uint4 *)db->d_rows, n_vec, dim4, queries, (uint32_t)nq, 0, checksum);
+        else ip_stream_kernel<4><<<sblocks, IPS_THREADS, smem, st>>>((const uint4 *)db->d_rows, n_vec, dim4, queries, (uint32_t)nq, 0, checksum);
+        PM_CHECK_LAUNCH();
+        count_launch();
+        return PM_OK;
+    }
     while (q0 < nq && rc == PM_OK) {  // passes of 16 queries, then 4, then single queries for the remainder
         const uint64_t left = nq - q0;
         if (left >= 16 || left > 4) { rc = launch(ip_scan_kernel<16>, 16, q0); q0 += 16; }

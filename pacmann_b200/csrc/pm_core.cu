@@ -356,6 +356,14 @@ PM_EXPORT int pm_buf_download(void *host, const void *dev_ptr, uint64_t bytes, i
     if (bytes) PM_CUDA(cudaMemcpy(host, dev_ptr, bytes, cudaMemcpyDeviceToHost));
     return PM_OK;
 }
+// asynchronous device-to-device copy (unified addressing: either side may be a peer GPU's IPC-mapped buffer), on `stream`
+PM_EXPORT int pm_buf_copy_dev(void *dst, const void *src, uint64_t bytes, int device, void *stream) {
+    if (bytes && (!dst || !src)) return set_error(PM_ERR_ARG, "pm_buf_copy_dev: null pointer");
+    int rc = ensure_device(device);
+    if (rc) return rc;
+    if (bytes) PM_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return PM_OK;
+}
 PM_EXPORT int pm_buf_zero(void *dev_ptr, uint64_t bytes, int device) {
     if (bytes && !dev_ptr) return set_error(PM_ERR_ARG, "pm_buf_zero: null pointer");
     int rc = ensure_device(device);

@@ -226,6 +226,7 @@ static int launch_answer_t(const AnswerParams &P, uint64_t q, uint32_t max_set, 
     else if (x <= 8) PM_ANS(8, 1);
     else if (x <= 16) PM_ANS(16, 1);
     else if (x <= 32) PM_ANS(32, 1);
+    else if (x == 40) PM_ANS(8, 5);      // 640-byte rows (SIFT-shaped): 8 lanes x 5 vectors keep every lane busy (32 x 2 idles 37 %)
     else if (x <= 64) PM_ANS(32, 2);
     else PM_ANS(32, 4);
 #undef PM_ANS

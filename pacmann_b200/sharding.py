@@ -11,6 +11,40 @@ def shard_range(n_hints, rank, world):
     return n_hints * rank // world, n_hints * (rank + 1) // world
 
 
+def partition_owner_range(n_parts, rank, world):
+    """partition sharding (batch-pir.go:79-85: sub-PIRs own disjoint DB slices): the half-open range of sub-PIRs that `rank`
+    owns WHOLE, together with only their rows.  world must divide n_parts."""
+    if n_parts % world:
+        raise ValueError(f"partition sharding needs world | n_parts ({world} does not divide {n_parts})")
+    return n_parts * rank // world, n_parts * (rank + 1) // world
+
+
+def hints_of(mode, hints_per_part, rank, world):
+    """per sub-PIR, the half-open hint range `rank` computes: mode "hintset" (every rank a slice of every sub-PIR, DB
+    replicated) or "partition" (every rank all hints of its own sub-PIRs, DB sharded by rows)"""
+    if mode == "partition":
+        lo, hi = partition_owner_range(len(hints_per_part), rank, world)
+        return [(0, h) if lo <= i < hi else (0, 0) for i, h in enumerate(hints_per_part)]
+    return [shard_range(h, rank, world) for h in hints_per_part]
+
+
+def table_runs(ranges, part_offsets):
+    """(table position, packed local position, length) in hints of the maximal contiguous runs of a rank's hints, given its
+    per-sub-PIR ranges and the hint offset of every sub-PIR in the one [hints] table: what a rank copies into the
+    consumer's table (one run per rank under partition sharding)"""
+    runs, local = [], 0
+    for i, (a, b) in enumerate(ranges):
+        if b <= a:
+            continue
+        pos = part_offsets[i] + a
+        if runs and runs[-1][0] + runs[-1][2] == pos and runs[-1][1] + runs[-1][2] == local:
+            runs[-1] = (runs[-1][0], runs[-1][1], runs[-1][2] + b - a)
+        else:
+            runs.append((pos, local, b - a))
+        local += b - a
+    return runs
+
+
 def shard_sizes(hints_per_part, world):
     """per-rank total hint counts over all sub-PIRs"""
     return [sum(shard_range(h, r, world)[1] - shard_range(h, r, world)[0] for h in hints_per_part) for r in range(world)]

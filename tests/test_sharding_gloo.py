@@ -64,6 +64,79 @@ def test_hint_set_sharding_gathers_to_the_unsharded_tables(world, tmp_path):
     assert result.read_text() == "ok"
 
 
+def _table_worker(rank, world, port, result_file, mode, shm_name):
+    """every rank computes its share (hint-set or partition sharding) and writes it into ONE shared table at the positions
+    bench.py uses for its peer-memory / copy-engine exchange (here: a shared-memory file stands in for rank 0's HBM)"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as o
+    from pacmann_b200 import sharding
+    from util import splitmix_db
+
+    n, E, batch = 8003, 4, 8
+    rows = splitmix_db(n, E, seed=98)
+    full = o.SimpleBatchPianoPIR(n, E * 8, batch, rows.reshape(-1), 8)
+    parts = full.partition_num
+    subs = [full.sub(i) for i in range(parts)]
+    hints = [s.primary_hint_num + s.set_size * s.max_query_per_chunk for s in subs]
+    offs = np.concatenate([[0], np.cumsum(hints)]).astype(np.int64)
+    table = np.memmap(shm_name, dtype=np.uint64, mode="r+", shape=(int(offs[-1]), E))
+    ranges = sharding.hints_of(mode, hints, rank, world)
+    local = np.zeros((sum(b - a for a, b in ranges), E), np.uint64)
+    pos = 0
+    for i, (a, b) in enumerate(ranges):
+        if b > a:
+            subs[i].preprocessing_range(o.derive_key(7, 0, parts, i), a, b)
+            tab = np.concatenate([subs[i].table("primary_parity"), subs[i].table("backup_parity").reshape(-1, E)])
+            local[pos:pos + b - a] = tab[a:b]
+            pos += b - a
+    runs = sharding.table_runs(ranges, offs)
+    if mode == "partition":
+        assert len(runs) == 1      # whole consecutive sub-PIRs: one copy per rank
+    for tpos, lpos, cnt in runs:
+        table[tpos:tpos + cnt] = local[lpos:lpos + cnt]
+    table.flush()
+    dist.barrier()
+    if rank == 0:
+        full.preprocessing(key_seed=7, repl_seed=0, threads=2)
+        ok = True
+        for i in range(parts):
+            s = full.sub(i)
+            want = np.concatenate([s.table("primary_parity"), s.table("backup_parity").reshape(-1, E)])
+            ok = ok and bool((np.asarray(table[offs[i]:offs[i + 1]]) == want).all())
+        open(result_file, "w").write("ok" if ok else "mismatch")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,world", [("partition", 2), ("partition", 4), ("hintset", 3)])
+def test_sharded_ranks_fill_one_table(mode, world, tmp_path):
+    """bench.py --gpus N: partition sharding (rank g owns sub-PIRs [4g/N ...) whole) and hint-set sharding both write
+    disjoint runs of ONE [hints][E] table that together equal the unsharded preprocessing"""
+    from oracle import oracle as o
+    from util import splitmix_db
+    n, E, batch = 8003, 4, 8
+    full = o.SimpleBatchPianoPIR(n, E * 8, batch, splitmix_db(n, E, seed=98).reshape(-1), 8)
+    hints = sum(full.sub(i).primary_hint_num + full.sub(i).set_size * full.sub(i).max_query_per_chunk for i in range(full.partition_num))
+    shm = tmp_path / "table.bin"
+    np.zeros((hints, E), np.uint64).tofile(shm)
+    result = tmp_path / "result.txt"
+    port = 29800 + os.getpid() % 1000 + world
+    mp.spawn(_table_worker, args=(world, port, str(result), mode, str(shm)), nprocs=world, join=True)
+    assert result.read_text() == "ok"
+
+
+def test_partition_sharding_needs_a_divisor():
+    from pacmann_b200 import sharding
+    with pytest.raises(ValueError):
+        sharding.partition_owner_range(16, 0, 3)
+    owned = [sharding.partition_owner_range(16, r, 8) for r in range(8)]
+    assert owned[0] == (0, 2) and owned[-1] == (14, 16) and all(owned[r][1] == owned[r + 1][0] for r in range(7))
+
+
 def test_shard_ranges_partition_the_hints():
     from pacmann_b200 import sharding
     for h in (0, 1, 7, 24416, 104448):
