@@ -148,3 +148,50 @@ func (c *Client) QueryBatchL2M(q []ClientQuery, out []uint64, status []int32, qu
 		(*C.int32_t)(unsafe.Pointer(&status[0])), (*C.float)(unsafe.Pointer(&queryVecs[0])), C.uint64_t(nVecs),
 		(*C.uint32_t)(unsafe.Pointer(&vecID[0])), C.uint64_t(dim), (*C.float)(unsafe.Pointer(&dist[0]))), "pm_client_query_batch_l2m")
 }
+
+// Search is the GPU-resident lock-step SearchKNN of the clients ("lanes") of one Client (INTEGRATION.md step 9): the
+// frontier of graphann.SearchKNN (search.go:114-234) and SimpleBatchPianoPIR.Query's bookkeeping live in HBM; a round is
+// Begin, maxStep x Fetch (enqueue only), Finish.  The Go side keeps what needs no entry data: the batch budget of every
+// lane (batch-pir.go:239-245: call Apply, then Client.Preprocess for the due lanes, then go on with Fetch(false)).
+type Search struct{ h *C.pm_search }
+
+type SearchConfig = C.pm_search_config
+
+func (c *Client) NewSearch(cfg *SearchConfig) *Search {
+	var h *C.pm_search
+	must(C.pm_search_create(c.h, cfg, &h), "pm_search_create")
+	return &Search{h}
+}
+func (s *Search) Close() { C.pm_search_destroy(s.h); s.h = nil }
+
+func (s *Search) SetStart(lane uint32, ids []int64, vectors []float32, neighbors []int32) {
+	must(C.pm_search_set_start(s.h, C.uint32_t(lane), (*C.int64_t)(unsafe.Pointer(&ids[0])), (*C.float)(unsafe.Pointer(&vectors[0])),
+		(*C.int32_t)(unsafe.Pointer(&neighbors[0]))), "pm_search_set_start")
+}
+func (s *Search) SetDummySeed(lane uint32, seeds []uint64) {
+	must(C.pm_search_set_dummy_seed(s.h, C.uint32_t(lane), (*C.uint64_t)(unsafe.Pointer(&seeds[0]))), "pm_search_set_dummy_seed")
+}
+func (s *Search) Begin(lanes []uint32, queries []float32, randSeeds []uint64, k uint64, benchmarking bool) {
+	b := C.int(0)
+	if benchmarking {
+		b = 1
+	}
+	must(C.pm_search_begin(s.h, (*C.uint32_t)(unsafe.Pointer(&lanes[0])), C.uint64_t(len(lanes)), (*C.float)(unsafe.Pointer(&queries[0])),
+		(*C.uint64_t)(unsafe.Pointer(&randSeeds[0])), C.uint64_t(k), b), "pm_search_begin")
+}
+func (s *Search) Fetch(applyPrevious bool) {
+	a := C.int(0)
+	if applyPrevious {
+		a = 1
+	}
+	must(C.pm_search_fetch(s.h, a), "pm_search_fetch")
+}
+func (s *Search) Apply() { must(C.pm_search_apply(s.h), "pm_search_apply") }
+func (s *Search) Finish(applyPrevious bool, ret, stepRet []int64, stats, finished []uint64) {
+	a := C.int(0)
+	if applyPrevious {
+		a = 1
+	}
+	must(C.pm_search_finish(s.h, a, (*C.int64_t)(unsafe.Pointer(&ret[0])), (*C.int64_t)(unsafe.Pointer(&stepRet[0])),
+		(*C.uint64_t)(unsafe.Pointer(&stats[0])), (*C.uint64_t)(unsafe.Pointer(&finished[0]))), "pm_search_finish")
+}
