@@ -27,10 +27,11 @@ def test_header_symbols_are_exported_and_bound(cabi):
 
 
 def test_hint_job_struct_layout_matches_header(cabi):
-    # struct pm_hint_job: 4 u64, 44 u32, 4 u64, 3 pointers
-    assert ctypes.sizeof(cabi.HintJob) == 4 * 8 + 44 * 4 + 4 * 8 + 3 * 8
+    # struct pm_hint_job: 4 u64, 44 u32, 4 u64, 4 pointers (offsets_out, the optional offset-index output, is the last)
+    assert ctypes.sizeof(cabi.HintJob) == 4 * 8 + 44 * 4 + 4 * 8 + 4 * 8
     assert cabi.HintJob.rk.offset == 32 and cabi.HintJob.hint_begin.offset == 32 + 176
     assert cabi.HintJob.parity_out.offset == 32 + 176 + 32 + 16
+    assert cabi.HintJob.offsets_out.offset == 32 + 176 + 32 + 24
 
 
 def test_version_and_host_library_load(cabi):
