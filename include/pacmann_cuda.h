@@ -99,7 +99,9 @@ int pm_buf_copy_dev(void *dst, const void *src, uint64_t bytes, int device, void
  * (usually inside the consumer's IPC-shared buffer, zeroed once): line i holds rank i's counter in its first uint32,
  * line n_flags a timeout marker.  pm_flag_signal_dev adds 1 to ONE counter (system-scope release) once everything
  * enqueued before it on `stream` has finished; pm_flag_wait_dev blocks `stream` until every one of the n_flags counters
- * has reached `target` (wrap-safe compare), or sets the marker to 1 after `timeout_ms` and lets the stream go on. */
+ * has reached `target` (wrap-safe compare), or sets the marker to 1 after `timeout_ms` and lets the stream go on.
+ * timeout_ms = 0: unbounded wait as stream memory operations (no polling kernel, no SM occupied -- needed when the waiting
+ * GPU launches cooperative one-CTA-per-SM kernels meanwhile). */
 int pm_flag_signal_dev(void *flag, int device, void *stream);
 int pm_flag_wait_dev(void *flags, uint32_t n_flags, uint32_t target, uint32_t timeout_ms, int device, void *stream);
 

@@ -427,6 +427,26 @@ PM_EXPORT int pm_flag_wait_dev(void *flags, uint32_t n_flags, uint32_t target, u
     if (!flags || n_flags == 0 || n_flags > 1024) return set_error(PM_ERR_ARG, "pm_flag_wait_dev: bad argument");
     int rc = ensure_device(device);
     if (rc) return rc;
+    if (timeout_ms == 0) {
+        // Unbounded form: a stream memory operation per counter (cuStreamWaitValue32, wrap-safe >=) instead of a polling
+        // kernel.  It occupies no SM -- a resident polling CTA keeps a cooperative launch of one-CTA-per-SM kernels (the hint
+        // kernel takes a whole register file) from starting until the wait is over, which serialised the consumer's next
+        // preprocessing behind the previous gather.
+        typedef int (*wait32_t)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+        static wait32_t wait32 = nullptr;
+        if (!wait32) {
+            void *fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            PM_CUDA(cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) return set_error(PM_ERR_UNSUPPORTED, "pm_flag_wait_dev: cuStreamWaitValue32 is not available");
+            wait32 = (wait32_t)fn;
+        }
+        for (uint32_t i = 0; i < n_flags; i++) {
+            const int e = wait32((cudaStream_t)stream, (unsigned long long)(uintptr_t)((unsigned int *)flags + 32 * i), target, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+            if (e != 0) return set_error(PM_ERR_CUDA, "pm_flag_wait_dev: cuStreamWaitValue32 failed (%d)", e);
+        }
+        return PM_OK;
+    }
     flag_wait_kernel<<<1, n_flags, 0, (cudaStream_t)stream>>>((unsigned int *)flags, target, (unsigned long long)timeout_ms * 1000000ull);
     PM_CHECK_LAUNCH();
     count_launch();

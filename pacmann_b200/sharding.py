@@ -19,12 +19,25 @@ def partition_owner_range(n_parts, rank, world):
     return n_parts * rank // world, n_parts * (rank + 1) // world
 
 
-def hints_of(mode, hints_per_part, rank, world):
+def hints_of(mode, hints_per_part, rank, world, relief=0.0):
     """per sub-PIR, the half-open hint range `rank` computes: mode "hintset" (every rank a slice of every sub-PIR, DB
-    replicated) or "partition" (every rank all hints of its own sub-PIRs, DB sharded by rows)"""
+    replicated) or "partition" (every rank all hints of its own sub-PIRs, DB sharded by rows).
+    relief (partition mode): rank 0 is also the consumer -- the other ranks' parities land in its HBM while its kernel
+    runs, which slows that kernel -- so the last `relief` of the hints of rank 0's sub-PIRs are computed by the other
+    ranks instead, 1/(world-1) each (they then also keep rank 0's rows)."""
     if mode == "partition":
         lo, hi = partition_owner_range(len(hints_per_part), rank, world)
-        return [(0, h) if lo <= i < hi else (0, 0) for i, h in enumerate(hints_per_part)]
+        out = [(0, h) if lo <= i < hi else (0, 0) for i, h in enumerate(hints_per_part)]
+        if relief > 0 and world > 1:
+            lo0, hi0 = partition_owner_range(len(hints_per_part), 0, world)
+            for i in range(lo0, hi0):
+                h = hints_per_part[i]
+                keep = h - int(h * relief)
+                if rank == 0:
+                    out[i] = (0, keep)
+                else:
+                    out[i] = (keep + (h - keep) * (rank - 1) // (world - 1), keep + (h - keep) * rank // (world - 1))
+        return out
     return [shard_range(h, rank, world) for h in hints_per_part]
 
 

@@ -105,3 +105,16 @@ def test_host_building_blocks_selftest(threads):
     (every index exactly once over thousands of loops, exception propagation): no GPU involved."""
     from pacmann_b200 import _host
     assert _host.lib().pmh_selftest(threads) == 0
+
+
+def test_tuning_knobs_need_no_gpu(cabi):
+    """launch knobs are plain process state: readable and settable without a device, unknown names are errors"""
+    for name in ("hg_sync", "hg_warps", "hg_ntab", "hg_tail_split", "hg_serpentine", "hg_xbytes", "hg_d2h_groups", "ans_split"):
+        old = cabi.tuning_get(name)
+        cabi.tuning_set(name, 3)
+        assert cabi.tuning_get(name) == 3
+        cabi.tuning_set(name, old)
+        assert cabi.tuning_get(name) == old
+    with pytest.raises(cabi.PacmannError) as e:
+        cabi.tuning_set("no_such_knob", 1)
+    assert e.value.code == cabi.PM_ERR_ARG

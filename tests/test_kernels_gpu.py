@@ -446,3 +446,30 @@ def test_ip_scan_tensor_core_accumulators_wrap_harmlessly(cabi, oracle):
     got_int, _ = cabi.ip_u32_scan(db, d, qs[:48], want_products=True)   # ... and the integer-pipe kernel on 48 of them
     assert (got[:48] == got_int).all()
     db.close()
+
+
+def test_completion_flags_and_device_copies(cabi):
+    """the pieces of the multi-GPU exchange on one GPU: pm_buf_copy_dev moves a table slice, pm_flag_signal_dev /
+    pm_flag_wait_dev order a consumer behind its producers, an unmet target times out visibly instead of hanging"""
+    n = 1 << 16
+    src, dst = cabi.buf_alloc(n * 8), cabi.buf_alloc(n * 8)
+    flags = cabi.buf_alloc(128 * 4)          # 3 counter lines + the timeout marker
+    cabi.buf_zero(flags, 128 * 4)
+    data = np.random.default_rng(1).integers(0, 2**64, n, dtype=np.uint64)
+    cabi.buf_upload(src, data)
+    cabi.buf_zero(dst, n * 8)
+    cabi.buf_copy_dev(dst + 1024, src + 1024, (n - 256) * 8)
+    for r in range(3):
+        cabi.flag_signal_dev(flags + 128 * r)
+        cabi.flag_signal_dev(flags + 128 * r)
+    cabi.flag_wait_dev(flags, 3, 2, timeout_ms=2000)          # every counter has reached 2: returns at once
+    cabi.flag_wait_dev(flags, 3, 2, timeout_ms=0)             # the same as stream memory operations (no polling kernel)
+    got = cabi.buf_download(dst, np.zeros(n, np.uint64))
+    assert (got[128:n - 128] == data[128:n - 128]).all() and (got[:128] == 0).all() and (got[n - 128:] == 0).all()
+    state = cabi.buf_download(flags, np.zeros(128 * 4 // 4, np.uint32))
+    assert state[0] == 2 and state[32] == 2 and state[64] == 2 and state[96] == 0
+    cabi.flag_wait_dev(flags, 3, 3, timeout_ms=50)            # nobody will signal a third time: reported, not hung
+    state = cabi.buf_download(flags, np.zeros(128 * 4 // 4, np.uint32))
+    assert state[96] == 1
+    for p in (src, dst, flags):
+        cabi.buf_free(p)

@@ -84,7 +84,8 @@ def _table_worker(rank, world, port, result_file, mode, shm_name):
     hints = [s.primary_hint_num + s.set_size * s.max_query_per_chunk for s in subs]
     offs = np.concatenate([[0], np.cumsum(hints)]).astype(np.int64)
     table = np.memmap(shm_name, dtype=np.uint64, mode="r+", shape=(int(offs[-1]), E))
-    ranges = sharding.hints_of(mode, hints, rank, world)
+    relief = 0.3 if mode == "partition_relief" else 0.0
+    ranges = sharding.hints_of("partition" if relief else mode, hints, rank, world, relief)
     local = np.zeros((sum(b - a for a, b in ranges), E), np.uint64)
     pos = 0
     for i, (a, b) in enumerate(ranges):
@@ -112,7 +113,7 @@ def _table_worker(rank, world, port, result_file, mode, shm_name):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,world", [("partition", 2), ("partition", 4), ("hintset", 3)])
+@pytest.mark.parametrize("mode,world", [("partition", 2), ("partition", 4), ("hintset", 3), ("partition_relief", 4)])
 def test_sharded_ranks_fill_one_table(mode, world, tmp_path):
     """bench.py --gpus N: partition sharding (rank g owns sub-PIRs [4g/N ...) whole) and hint-set sharding both write
     disjoint runs of ONE [hints][E] table that together equal the unsharded preprocessing"""
