@@ -66,7 +66,8 @@ uint64_t pm_launch_count(void);
  * Knobs: "hg_sync" (round barrier of the hint kernel: -1 auto, 0, 1), "hg_warps" (CTA width in warps: 0 auto, 1..16),
  * "hg_ntab" (AES T-tables: 0 auto, 1, 4), "hg_tail_split" (shared last round: -1 auto, 0 off, 1 on), "hg_serpentine"
  * (0, 1), "hg_xbytes" (chunk-id bytes the hoisted PRF rounds treat as varying: 0 auto, 2, 4), "ans_split" (CTAs per
- * sub-query: 0 auto, 1..8), "hg_d2h_groups" (launch groups of pm_hintgen: 0 auto, 1..16).  Initial values come from the
+ * sub-query: 0 auto, 1..8), "hg_d2h_groups" (launch groups of pm_hintgen: 0 auto, 1..16), "search_ans_stream" (read by
+ * pm_search_create: 1 = the answer kernel of a search step runs on a low-priority stream of its own, 0 = one stream).  Initial values come from the
  * environment (PM_HG_SYNC, PM_HG_WARPS, ...).  Results never depend on a knob. */
 int pm_tuning_set(const char *name, int value);
 int pm_tuning_get(const char *name, int *value);

@@ -524,7 +524,13 @@ PM_EXPORT int pm_client_create(pm_db *db, const pm_client_part *parts, uint64_t 
         cur += (P * 4 + 7) / 8;
         if ((uintptr_t)cur & 15) cur += 1;
     }
-    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    // the client's kernels are small and latency bound; they run on a high-priority stream so that, when several clients
+    // (or lock-step groups) share the GPU, their CTAs slip in between the CTAs of another group's HBM-bound answer kernel
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi);
+    }
     if (e != cudaSuccess) { cudaFree(c->arena); cudaFree(c->d_parts); delete c; return set_error(PM_ERR_CUDA, "pm_client_create: stream creation failed"); }
     *out = c;
     return PM_OK;

@@ -33,7 +33,7 @@ namespace pm {
 
 int set_error(int code, const char *fmt, ...);
 // launch-time tuning knobs (pm_tuning_set / environment), see pm_core.cu
-enum Tune { T_HG_SYNC, T_HG_WARPS, T_HG_NTAB, T_HG_TAIL_SPLIT, T_HG_SERPENTINE, T_HG_XBYTES, T_ANS_SPLIT, T_HG_D2H_GROUPS, T_COUNT };
+enum Tune { T_HG_SYNC, T_HG_WARPS, T_HG_NTAB, T_HG_TAIL_SPLIT, T_HG_SERPENTINE, T_HG_XBYTES, T_ANS_SPLIT, T_HG_D2H_GROUPS, T_SEARCH_ANS_STREAM, T_COUNT };
 int tune(Tune t);
 void count_launch(uint64_t n = 1);
 int ensure_device(int device);  // cudaSetDevice + one-time table upload; returns PM_OK / error

@@ -36,6 +36,7 @@ static TuneKnob g_knobs[T_COUNT] = {
     {"hg_xbytes", "PM_HG_XBYTES", 0, {0}, {false}},    // varying chunk-id bytes assumed by the hoisted PRF rounds: 0 auto, 1, 2, 4
     {"ans_split", "PM_ANS_SPLIT", 0, {0}, {false}},    // CTAs per sub-query of the answer kernel: 0 auto, 1..8
     {"hg_d2h_groups", "PM_HG_D2H_GROUPS", 0, {0}, {false}},   // launch groups of the host-buffer pm_hintgen: 0 auto, 1..16
+    {"search_ans_stream", "PM_SEARCH_ANS_STREAM", 1, {0}, {false}},   // device search: answer kernel on a low-priority stream of its own (0 = one stream)
 };
 int tune(Tune t) {
     TuneKnob &k = g_knobs[t];

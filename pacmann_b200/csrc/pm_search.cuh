@@ -520,6 +520,10 @@ struct pm_search {
     void *h_stage = nullptr;
     size_t h_stage_bytes = 0;
     uint64_t stride = 0;
+    // the HBM-bound answer kernel of a step runs on a LOW-priority stream of its own (ordered by events): the prepare / step /
+    // finish kernels of another group, on their high-priority client stream, then interleave with it instead of queueing
+    cudaStream_t ans_stream = nullptr;
+    cudaEvent_t ev_prep = nullptr, ev_ans = nullptr;
     size_t step_smem = 0, begin_smem = 0, final_smem = 0;
 };
 
@@ -622,6 +626,17 @@ PM_EXPORT int pm_search_create(pm_client *c, const pm_search_config *cfg, pm_sea
     cudaFuncSetAttribute(search_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->step_smem);
     cudaFuncSetAttribute(search_begin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->begin_smem);
     cudaFuncSetAttribute(search_final_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->final_smem);
+    {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (tune(T_SEARCH_ANS_STREAM) != 0 &&
+            (cudaStreamCreateWithPriority(&s->ans_stream, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+             cudaEventCreateWithFlags(&s->ev_prep, cudaEventDisableTiming) != cudaSuccess ||
+             cudaEventCreateWithFlags(&s->ev_ans, cudaEventDisableTiming) != cudaSuccess)) {
+            cudaGetLastError();
+            s->ans_stream = nullptr;     // fall back to one stream
+        }
+    }
     c->search = s;
     *out = s;
     return PM_OK;
@@ -631,6 +646,9 @@ PM_EXPORT int pm_search_destroy(pm_search *s) {
     if (!s) return PM_OK;
     if (pm::ensure_device(s->c->db->device) == PM_OK) {
         cudaStreamSynchronize(s->c->stream);
+        if (s->ans_stream) { cudaStreamSynchronize(s->ans_stream); cudaStreamDestroy(s->ans_stream); }
+        if (s->ev_prep) cudaEventDestroy(s->ev_prep);
+        if (s->ev_ans) cudaEventDestroy(s->ev_ans);
         cudaFree(s->arena);
         if (s->h_stage) cudaFreeHost(s->h_stage);
     }
@@ -745,7 +763,15 @@ PM_EXPORT int pm_search_fetch(pm_search *s, int apply_previous) {
                                                                                 s->d_meta, s->d_row0, s->d_nrows, s->d_chunk, s->d_set, mirror, s->d_part_map, D.per);
     PM_CHECK_LAUNCH();
     count_launch();
-    if ((rc = answer_enqueue(c->db, s->d_row0, s->d_nrows, s->d_chunk, s->d_set, s->d_off, s->stride, q, (uint32_t)s->stride, s->d_ans, c->stream))) return rc;
+    if (s->ans_stream) {
+        PM_CUDA(cudaEventRecord(s->ev_prep, c->stream));
+        PM_CUDA(cudaStreamWaitEvent(s->ans_stream, s->ev_prep, 0));
+        if ((rc = answer_enqueue(c->db, s->d_row0, s->d_nrows, s->d_chunk, s->d_set, s->d_off, s->stride, q, (uint32_t)s->stride, s->d_ans, s->ans_stream))) return rc;
+        PM_CUDA(cudaEventRecord(s->ev_ans, s->ans_stream));
+        PM_CUDA(cudaStreamWaitEvent(c->stream, s->ev_ans, 0));
+    } else if ((rc = answer_enqueue(c->db, s->d_row0, s->d_nrows, s->d_chunk, s->d_set, s->d_off, s->stride, q, (uint32_t)s->stride, s->d_ans, c->stream))) {
+        return rc;
+    }
     client_finish_kernel<<<(unsigned)nparts, 256, 0, c->stream>>>(c->d_parts, nullptr, nullptr, s->d_meta, D.E, s->d_ans, s->d_res,
                                                                   s->benchmarking ? nullptr : D.qvec, s->d_vid, D.dim, s->benchmarking ? nullptr : s->d_dist,
                                                                   s->d_part_map, D.per, D.out_rows);

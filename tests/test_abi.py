@@ -109,7 +109,7 @@ def test_host_building_blocks_selftest(threads):
 
 def test_tuning_knobs_need_no_gpu(cabi):
     """launch knobs are plain process state: readable and settable without a device, unknown names are errors"""
-    for name in ("hg_sync", "hg_warps", "hg_ntab", "hg_tail_split", "hg_serpentine", "hg_xbytes", "hg_d2h_groups", "ans_split"):
+    for name in ("hg_sync", "hg_warps", "hg_ntab", "hg_tail_split", "hg_serpentine", "hg_xbytes", "hg_d2h_groups", "ans_split", "search_ans_stream"):
         old = cabi.tuning_get(name)
         cabi.tuning_set(name, 3)
         assert cabi.tuning_get(name) == 3
