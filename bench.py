@@ -202,8 +202,9 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the other BASELINE.json configs (rank 0, N = 1 only)")
     ap.add_argument("--search-queries", type=int, default=5120, help="private ANN queries per GPU (lock-step measurement): 40 per client at "
                                                                         "the default 128 clients, i.e. inside every client's query budget of 45")
-    ap.add_argument("--search-lanes", type=int, default=64, help="clients per lock-step group (graphann.SearchKNNLockstep)")
-    ap.add_argument("--search-groups", type=int, default=2, help="lock-step groups per GPU, one host thread each")
+    ap.add_argument("--search-lanes", type=int, default=32, help="clients per lock-step group (graphann.SearchKNNLockstep)")
+    ap.add_argument("--search-groups", type=int, default=4, help="lock-step groups per GPU, one host thread each (measured, 128 clients: "
+                                                                   "2 x 64 10.5 k queries/s, 3 x 42 10.95 k, 4 x 32 11.0 k, 5 x 24 11.0 k)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -6,9 +6,9 @@
 //     search_step_kernel     apply the previous fetch (cache put, fresh vertices, distances of cache hits, heap pushes),
 //                            then pop `parallel` vertices, emit their neighbour lists as the next batch and build the
 //                            pm_client_query records of every lane straight from the neighbour lists in HBM
-//     client_prepare_kernel  \
-//     answer_kernel           > pm_client.cuh / pm_pir.cu, unchanged arithmetic (fixed record layout, part map)
-//     client_finish_kernel   /  (+ the distance of every answered vector to its lane's query)
+//     client_prepare_kernel  |
+//     answer_kernel          |  pm_client.cuh / pm_pir.cu, unchanged arithmetic (fixed record layout, part map)
+//     client_finish_kernel   |  (+ the distance of every answered vector to its lane's query)
 // Entries never travel to the host; a round of searches returns k ids and reach steps per lane.
 // Tie rules are those of the host mirror and the oracle: start ranking by (distance, position), explore queue
 // = container/heap's sift-up / sift-down on `dist <`, final ranking by (distance, id).  Every lane returns exactly what
