@@ -183,6 +183,10 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         for (uint64_t i = (P & ~3ull) + threadIdx.x; i < P; i += NT) s_pp[i] = D.pp32[i];
     }
     if (threadIdx.x == 0) { s_fin = *D.finished; s_hit = 0xffffffffu; }   // only this CTA changes the part's counters during the call
+    // with the offset index s_offs is free: it mirrors the per-chunk query counters, so that the slot a query consumes is
+    // known at once and its replacement index / backup tag are fetched alongside the column scan, not behind a counter load
+    if (indexed)
+        for (uint32_t c = threadIdx.x; c < S; c += NT) s_offs[c] = (uint32_t)D.hist[c];
     __syncthreads();
     const AesTab<8> T{s_tab + (threadIdx.x & 3)};
     const RkOfPtr R{s_rk};
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
         const uint64_t chunkId = Q.idx / C, offset = Q.idx % C;
         // ---- phase A: budget counters + first-match search (pir.go:386-414); s_hit was reset behind the last barrier ----
         if (threadIdx.x == 32 % NT) {   // a lane of another warp than the one that is busiest in the scan tail
-            const uint64_t fin = s_fin, h = D.hist[chunkId];
+            const uint64_t fin = s_fin, h = indexed ? (uint64_t)s_offs[chunkId] : D.hist[chunkId];
             const int st = fin >= D.max_query_num ? 2 : (h >= M ? 3 : 0);   // pir.go:386-391, 396-400
             s_status = st;
             s_ingroup = h;
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             if ((P & 7) == 0) {
                 const uint4 *col4 = reinterpret_cast<const uint4 *>(col);
                 const uint64_t nv = P / 8;
+                const uint32_t off2 = (uint32_t)offset | ((uint32_t)offset << 16);
                 for (uint64_t v0 = 0; v0 < nv; v0 += 4 * NT) {
                     uint4 w[4];
 #pragma unroll
@@ -242,10 +247,14 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
                         const uint64_t vi = v0 + u * NT + threadIdx.x;
                         if (vi >= nv) continue;
                         const uint32_t x[4] = {w[u].x, w[u].y, w[u].z, w[u].w};
+                        // two 16-bit offsets per compare (SIMD-in-word); a match is rare (P / ChunkSize per column)
+                        const uint32_t m0 = __vcmpeq2(x[0], off2), m1 = __vcmpeq2(x[1], off2), m2 = __vcmpeq2(x[2], off2), m3 = __vcmpeq2(x[3], off2);
+                        if ((m0 | m1 | m2 | m3) == 0) continue;
+                        const uint32_t m[4] = {m0, m1, m2, m3};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            consider(vi * 8 + 2 * e, x[e] & 0xffffu);
-                            consider(vi * 8 + 2 * e + 1, x[e] >> 16);
+                            if (m[e] & 0xffffu) consider(vi * 8 + 2 * e, (uint32_t)offset);
+                            if (m[e] >> 16) consider(vi * 8 + 2 * e + 1, (uint32_t)offset);
                         }
                     }
                 }
@@ -328,6 +337,7 @@ __global__ void __launch_bounds__(CL_THREADS) client_prepare_kernel(const Client
             s_fin += 1;
             *D.finished = s_fin;
             D.hist[chunkId] = inGroup + 1;
+            if (indexed) s_offs[chunkId] = (uint32_t)(inGroup + 1);
             s_hit = 0xffffffffu;
         }
         __threadfence_block();
