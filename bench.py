@@ -251,9 +251,10 @@ def main():
 
     relief = args.relief
     if relief < 0:
-        # measured at N = 8 (pipe): rank 0's kernel runs 8 % slower than its peers' while 540 GB/s of copies land in its HBM
-        # (0.555 against 0.51 ms); handing 7 % of its hints to the seven others evens that out (20 % overshoots: 0.455 / 0.55)
-        relief = 0.01 * (world - 1) if (sharding == "partition" and world >= 4 and args.exchange == "pipe") else 0.0
+        # measured at N = 8 (pipe), step times on one box: no relief 0.560 ms, 20 % 0.571 (rank 0 0.455 ms, its peers 0.55), and
+        # 7 % in two full runs 0.62-0.63 (rank 0's launch then ends in a large shared round, whose sweeps are not in lock step):
+        # evening out rank 0's slower kernel this way does not pay -- off by default, kept as an option
+        relief = 0.0
     if sharding != "partition":
         relief = 0.0
 
