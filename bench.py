@@ -3,21 +3,27 @@
 workload (BASELINE.json configs[3]: 3 201 821 entries x 896 B, batch 32 -> 16 sub-PIRs, FailureProbLog2 8).
 
 A "step" is one full SimpleBatchPianoPIR.Preprocessing() (pianopir/batch-pir.go:119-155): every primary and
-backup hint parity of all 16 sub-PIRs over the whole DB.  The DB is replicated per GPU and hints are sharded
-by hint set across ranks; with N > 1 the parities are gathered on rank 0 over NCCL inside the
-timed region, so the job is the same at every N ("strong" scaling: total work fixed).
+backup hint parity of all 16 sub-PIRs over the whole DB.  N > 1 (one process per GPU under torchrun): the work is
+sharded by partition (rank g owns whole sub-PIRs and only their rows; default when N | 16) or by hint set over a
+replicated DB, with no collective on the data path; the parities of every step are delivered into ONE
+table in rank 0's HBM inside the timed region -- by default pipelined: copy engines push step k over NVLink while
+step k+1 computes, per-rank completion flags end the step -- so the job is the same at every N ("strong" scaling).
 
-  value  = N*EB / t            DB-scan GB/s, DB resident in HBM, parities left in HBM (rank 0 after the gather)
-  e2e    = same metric through the host-buffer C-ABI call pm_hintgen(): job descriptors in, parities copied
-           back into pinned host memory inside the timed region (what the cgo bridge would do per Preprocessing)
+  value  = N*EB / t            DB-scan GB/s, DB resident in HBM, parities left in HBM (ONE table on rank 0)
+  e2e    = same metric through the host-buffer C-ABI call pm_hintgen(): job descriptors in, every parity copied
+           into ONE page-locked host table inside the timed region (what the cgo bridge would do per Preprocessing)
   roofline: algorithmic HBM bytes B_hbm = N*EB + sum_parts (P+B)*EB (DB read once + parities written once,
-           SURVEY.md 8d) / kernel time, against MEASURED_PEAKS.json hbm_gbs.  The kernel is NOT HBM-bound
-           (see DESIGN.md): xor_gather GB/s and PRF/s are reported next to it.
+           SURVEY.md 8d) / kernel time (CUDA events around every hint-kernel launch inside the timed loop), against
+           MEASURED_PEAKS.json hbm_gbs.  The kernel is NOT HBM-bound: binding_roofline gives the
+           L1 data-pipe wavefront rate that bounds it, xor_gather GB/s and PRF/s are reported next to it.
   cpu_baseline: the C oracle (a port: the reference is Go and cannot be built here) on 1 thread, as the
-           reference runs (ThreadNum = 1), on a bounded sample (4 of the 16 sub-PIRs).
+           reference runs (ThreadNum = 1), on the whole workload x 3.
+  private_ann / private_ann_sift1m: end-to-end private graph search queries/s (BASELINE configs[2] / [1]).
+  other_configs: the other BASELINE configs and the non-headline kernels, each with time, algorithmic bytes, fraction
+           of the measured peak and a CPU-oracle baseline (rank 0, N = 1).
   --impl reference: the same oracle with all host threads on the full workload (rank 0 only).
 
-Only the cpu_baseline / --impl reference legs import oracle/; the timed GPU path is the C-ABI library.
+Only the cpu_baseline legs, the spot check and --impl reference import oracle/; the timed GPU path is the C-ABI library.
 """
 import argparse
 import ctypes as C
@@ -562,6 +568,14 @@ def main():
                          "kernel_ms": kern_ms, "kernel_ms_per_rank": kern_ms_ranks, "kernel_ms_source": "CUDA events around each hint-kernel launch inside the timed loop, mean, max over ranks",
                          "algorithmic_bytes_per_launch": b_hbm_rank,
                          "binding_term": "not HBM: L1 data-pipe wavefronts (row gather 2/3 + AES T-table LDS 1/3) at 82 % of peak; see DESIGN.md",
+                         "binding_roofline": {
+                             "bound": "l1_data_pipe", "unit": "128-byte wavefronts/s",
+                             "wavefronts_per_launch": n_prf / world * (E * 8 / 128 + 111 / 32),
+                             "achieved": n_prf / world * (E * 8 / 128 + 111 / 32) / (kern_ms * 1e-3),
+                             "peak": 148 * (clocks.get("sm_mhz") or 1965.0) * 1e6,
+                             "frac": n_prf / world * (E * 8 / 128 + 111 / 32) / (kern_ms * 1e-3) / (148 * (clocks.get("sm_mhz") or 1965.0) * 1e6),
+                             "note": "per (hint, chunk) pair 7 wavefronts of row data + 111 conflict-free T-table lookups / 32 lanes; one wavefront "
+                                     "per SM per clock at the sampled SM clock; ncu measured 82 % of this pipe (profiles/r02_hintgen_msmarco_v4_ncu_full.csv)"},
                          "xor_gather_gbs": b_xor / world / (kern_ms * 1e-3) / 1e9,
                          "prf_per_s": n_prf / world / (kern_ms * 1e-3)},
             "verified_vs_oracle_prf": verified,

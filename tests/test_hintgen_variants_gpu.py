@@ -263,3 +263,34 @@ def test_every_preprocessing_draws_a_fresh_key(oracle):
     batch.Preprocessing()
     keys = {bytes(batch.subPIR(i).long_key()) for i in range(4)}
     assert len(keys) == 4
+
+
+@pytest.mark.parametrize("n_rows,E,tail", [(20000, 16, 1), (200114, 112, 1), (5000, 7, 0)])
+def test_offset_side_output_matches_the_prf(cabi, oracle, knobs, n_rows, E, tail):
+    """pm_hint_job.offsets_out: the kernel also stores PRF(rk, tag_h, c) & (ChunkSize-1) of every (hint, chunk) it evaluates
+    -- the resident client's offset index is built from it -- row-major per hint, rows padded to a multiple of 8."""
+    rows = splitmix_db(n_rows, E, seed=5 + E)
+    pir_o = oracle.PianoPIR(n_rows, E * 8, rows.reshape(-1), 8)
+    pir_o.preprocessing(KEY, repl_seed=2, threads=8)
+    want_par = oracle_parities(pir_o)
+    P, S, M, C = pir_o.primary_hint_num, pir_o.set_size, pir_o.max_query_per_chunk, pir_o.chunk_size
+    H, spad = P + S * M, (S + 7) & ~7
+    knobs(hg_tail_split=tail)
+    db = cabi.DB(rows)
+    rk = cabi.expand_key(KEY)
+    par = cabi.buf_alloc(H * E * 8)
+    off = cabi.buf_alloc(H * spad * 2)
+    cabi.buf_zero(off, H * spad * 2)
+    cabi.hintgen_dev(db, [cabi.make_job(0, n_rows, C, S, rk, 0, H, P, M, parity_out=par, offsets_out=off)])
+    db.sync()
+    got_par = cabi.buf_download(par, np.zeros((H, E), np.uint64))
+    got_off = cabi.buf_download(off, np.zeros((H, spad), np.uint16))
+    assert (got_par == want_par).all()
+    tags = np.repeat(np.arange(H, dtype=np.uint64), S)
+    cs = np.tile(np.arange(S, dtype=np.uint64), H)
+    want_off = (oracle.prf_batch(rk, tags, cs) & np.uint64(C - 1)).astype(np.uint16).reshape(H, S)
+    assert (got_off[:, :S] == want_off).all()
+    assert (got_off[:, S:] == 0).all()          # the padding columns are never written
+    for p_ in (par, off):
+        cabi.buf_free(p_)
+    db.close()
