@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--fail", type=int, default=8)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--shard", default="0/1", help="r/N: time rank r's share of the hints of an N-GPU run")
+    ap.add_argument("--sweep", default="", help="knob=v1,v2,...: time every value in this process (same DB) and check that the parities are bit-identical")
     a = ap.parse_args()
     torch.cuda.init()
     E = a.entry_u64
@@ -59,20 +60,31 @@ def main():
     print(f"parts={parts} chunk={c} set={s} primary={p} mqpc={mq} hints/part={H} prf={prf} xor_bytes={prf*E*8/1e9:.3f} GB db={nbytes/1e9:.3f} GB")
     stream = torch.cuda.Stream()
     st = stream.cuda_stream
-    with torch.cuda.stream(stream):
-        for _ in range(2):
-            cabi.hintgen_dev(db, jobs, st)
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ts = []
-        for _ in range(a.iters):
-            e0.record(stream)
-            cabi.hintgen_dev(db, jobs, st)
-            e1.record(stream)
+    knob, values = (a.sweep.split("=")[0], [int(v) for v in a.sweep.split("=")[1].split(",")]) if a.sweep else (None, [None])
+    ref = None
+    for v in values:
+        if knob:
+            cabi.tuning_set(knob, v)
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                cabi.hintgen_dev(db, jobs, st)
             torch.cuda.synchronize()
-            ts.append(e0.elapsed_time(e1))
-    ms = min(ts)
-    print(f"hintgen: {ms:.3f} ms (all {['%.3f' % x for x in ts]})  db-scan {nbytes/ms/1e6:.1f} GB/s  prf {prf/ms/1e6:.2f} G/s  xor-gather {prf*E*8/ms/1e6:.1f} GB/s")
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ts = []
+            for _ in range(a.iters):
+                e0.record(stream)
+                cabi.hintgen_dev(db, jobs, st)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+        ms = min(ts)
+        same = ""
+        if knob:
+            if ref is None:
+                ref = [o.clone() for o in outs]
+            else:
+                same = "  parities identical: %s" % all(torch.equal(x, y) for x, y in zip(ref, outs))
+        print(f"{knob}={v} " if knob else "", f"hintgen: {ms:.3f} ms (median {sorted(ts)[len(ts)//2]:.3f}, all {['%.3f' % x for x in ts]})  db-scan {nbytes/ms/1e6:.1f} GB/s  prf {prf/ms/1e6:.2f} G/s  xor-gather {prf*E*8/ms/1e6:.1f} GB/s{same}", flush=True)
 
 
 if __name__ == "__main__":
