@@ -73,6 +73,23 @@ __device__ void heap_push(HeapView &h, float dist, uint32_t slot) {
     }
     h.d[j] = dist; h.s[j] = slot;
 }
+// The same push by one whole warp (every lane calls it with the same arguments; n = entries before the push, the caller
+// counts).  The walk of heap_push only READS the ancestors of position n -- what it writes lies below what it still has to
+// read -- so the chain can be read at once: lane l holds the ancestor l+1 levels up, the first lane whose ancestor is not
+// greater than the new element is where the sequential walk stops, the ancestors below it move down one level each and the
+// new element takes the freed position.  Same comparisons, same final arrangement, one step instead of up to log2(n).
+__device__ __forceinline__ void heap_push_warp(float *d, uint32_t *s, uint32_t n, float dist, uint32_t slot) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t mine = ((n + 1) >> lane) - 1;                                  // position l levels up (lane 0: the new leaf); n + 1 < 2^31
+    const uint32_t up = lane < 31 ? (n + 1) >> (lane + 1) : 0;                    // 1-based position of its parent, 0 = none
+    const float du = up ? d[up - 1] : 0.f;
+    const uint32_t su = up ? s[up - 1] : 0;
+    const uint32_t stop = __ballot_sync(0xffffffffu, !up || !(dist < du));
+    const uint32_t k = __ffs(stop) - 1;                                           // lane 31 always stops
+    if (lane < k) { d[mine] = du; s[mine] = su; }
+    else if (lane == k) { d[mine] = dist; s[mine] = slot; }
+    __syncwarp();
+}
 __device__ uint32_t heap_pop(HeapView &h) {
     const uint32_t n = h.n - 1, top = h.s[0];
     const float x = h.d[n];          // heap.Pop: Swap(0, n-1), down(0, n-1): the last element sinks from the root
@@ -194,7 +211,11 @@ __global__ void __launch_bounds__(SR_THREADS) search_step_kernel(SearchDev S, co
     uint32_t *g_hs = S.heap_slot + (uint64_t)lane * S.cap;
     uint32_t *hk = S.hash_key + (uint64_t)lane * S.hcap, *hv = S.hash_val + (uint64_t)lane * S.hcap;
     uint32_t heap_n = l32[1];
-    for (uint32_t i = t; i < heap_n; i += SR_THREADS) { s_hd[i] = g_hd[i]; s_hs[i] = g_hs[i]; }
+    // cap is a multiple of 4 and every array 16-byte aligned: the heap moves as uint4 (the words past heap_n are don't-cares)
+    for (uint32_t i = t * 4; i < heap_n; i += SR_THREADS * 4) {
+        *reinterpret_cast<uint4 *>(s_hd + i) = *reinterpret_cast<const uint4 *>(g_hd + i);
+        *reinterpret_cast<uint4 *>(s_hs + i) = *reinterpret_cast<const uint4 *>(g_hs + i);
+    }
     if (t == 0) { s_known = l32[0]; s_nfresh = 0; s_succ = 0; s_server = 0; s_heap_n = heap_n; }
     __syncthreads();
     const ClientQueryDev *recs = S.records + (uint64_t)a * R;
@@ -318,28 +339,34 @@ __global__ void __launch_bounds__(SR_THREADS) search_step_kernel(SearchDev S, co
             s_flag[i] = 0x100u + rank;
         }
         __syncthreads();
-        // neighbour lists of the fresh vertices, flattened over (vertex, neighbour) so that the loads are independent
-        {
-            const uint32_t total = s_nfresh * m;
+        // warp 0: explore-queue pushes in batch order (container/heap semantics), one warp step per push.  Warps 1-3
+        // meanwhile copy the neighbour lists of the fresh vertices, flattened over (vertex, neighbour) so that the loads
+        // are independent.
+        if (t < 32) {
+            const uint32_t nfresh = s_nfresh;
+            uint32_t hn = s_heap_n;
+            __syncwarp();
+            for (uint32_t x = 0; x < nfresh; x++) heap_push_warp(s_hd, s_hs, hn++, s_pushd[x], s_pushs[x]);
+            if (t == 0) {
+                s_heap_n = hn;
+                s_known = known0 + nfresh;
+                l32[0] = known0 + nfresh;
+                l32[2] = this_step + 1;
+                l64[2] += B;            // totalQueryNum
+                l64[3] += s_succ;       // succQueryNum
+                l64[4] += s_server;     // server sub-queries answered for this lane (dummy + successful real)
+            }
+        } else {
+            const uint32_t mv = vec4 ? m / 4 : m, total = s_nfresh * mv;     // 16 bytes per copy where the layout allows
 #pragma unroll 4
-            for (uint32_t x = t; x < total; x += SR_THREADS) {
-                const uint32_t f = x / m, j = x % m, r = s_rslot[f], slot = s_pushs[f];
+            for (uint32_t x = t - 32; x < total; x += SR_THREADS - 32) {
+                const uint32_t f = x / mv, j = x % mv, r = s_rslot[f], slot = s_pushs[f];
                 if (slot >= S.cap) continue;
                 const uint32_t *nb = reinterpret_cast<const uint32_t *>(S.cache_entries + ((uint64_t)s_rpart[r] * S.cache_cap + s_rref[r]) * E) + S.dim;
-                S.nbr[((uint64_t)lane * S.cap + slot) * m + j] = nb[j];
+                uint32_t *dst = S.nbr + ((uint64_t)lane * S.cap + slot) * m;
+                if (vec4) reinterpret_cast<uint4 *>(dst)[j] = reinterpret_cast<const uint4 *>(nb)[j];
+                else dst[j] = nb[j];
             }
-        }
-        if (t == 0) {   // explore-queue pushes in batch order (container/heap semantics)
-            const uint32_t nfresh = s_nfresh;
-            HeapView hp{s_hd, s_hs, s_heap_n};
-            for (uint32_t x = 0; x < nfresh; x++) heap_push(hp, s_pushd[x], s_pushs[x]);
-            s_heap_n = hp.n;
-            s_known = known0 + nfresh;
-            l32[0] = s_known;
-            l32[2] = this_step + 1;
-            l64[2] += B;            // totalQueryNum
-            l64[3] += s_succ;       // succQueryNum
-            l64[4] += s_server;     // server sub-queries answered for this lane (dummy + successful real)
         }
         __syncthreads();
     }
@@ -450,7 +477,10 @@ __global__ void __launch_bounds__(SR_THREADS) search_step_kernel(SearchDev S, co
     }
     __syncthreads();
     heap_n = s_heap_n;
-    for (uint32_t i = t; i < heap_n; i += SR_THREADS) { g_hd[i] = s_hd[i]; g_hs[i] = s_hs[i]; }
+    for (uint32_t i = t * 4; i < heap_n; i += SR_THREADS * 4) {
+        *reinterpret_cast<uint4 *>(g_hd + i) = *reinterpret_cast<const uint4 *>(s_hd + i);
+        *reinterpret_cast<uint4 *>(g_hs + i) = *reinterpret_cast<const uint4 *>(s_hs + i);
+    }
     if (t == 0) l32[1] = heap_n;
 }
 
