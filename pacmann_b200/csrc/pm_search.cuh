@@ -86,8 +86,10 @@ __device__ __forceinline__ void heap_push_warp(float *d, uint32_t *s, uint32_t n
     const uint32_t su = up ? s[up - 1] : 0;
     const uint32_t stop = __ballot_sync(0xffffffffu, !up || !(dist < du));
     const uint32_t k = __ffs(stop) - 1;                                           // lane 31 always stops
-    if (lane < k) { d[mine] = du; s[mine] = su; }
-    else if (lane == k) { d[mine] = dist; s[mine] = slot; }
+    if (lane <= k) {            // one predicated store pair, no divergent paths
+        d[mine] = lane < k ? du : dist;
+        s[mine] = lane < k ? su : slot;
+    }
     __syncwarp();
 }
 __device__ uint32_t heap_pop(HeapView &h) {
@@ -346,7 +348,12 @@ __global__ void __launch_bounds__(SR_THREADS) search_step_kernel(SearchDev S, co
             const uint32_t nfresh = s_nfresh;
             uint32_t hn = s_heap_n;
             __syncwarp();
-            for (uint32_t x = 0; x < nfresh; x++) heap_push_warp(s_hd, s_hs, hn++, s_pushd[x], s_pushs[x]);
+            for (uint32_t x0 = 0; x0 < nfresh; x0 += 32) {      // the push list through registers: no load on the push-to-push chain
+                const float pd = x0 + t < nfresh ? s_pushd[x0 + t] : 0.f;
+                const uint32_t ps = x0 + t < nfresh ? s_pushs[x0 + t] : 0;
+                const uint32_t cnt = min(32u, nfresh - x0);
+                for (uint32_t x = 0; x < cnt; x++) heap_push_warp(s_hd, s_hs, hn++, __shfl_sync(0xffffffffu, pd, x), __shfl_sync(0xffffffffu, ps, x));
+            }
             if (t == 0) {
                 s_heap_n = hn;
                 s_known = known0 + nfresh;
