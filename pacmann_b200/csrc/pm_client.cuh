@@ -373,19 +373,29 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
         s_meta[k] = FinMeta{(uint32_t)m.hit, (uint32_t)m.slot, m.status};
     }
     __syncthreads();
+    // the parity of the hint a query consumed is fetched ahead too unless an earlier query of this part refreshed the same
+    // hint slot (then it is read at its turn, after that write)
+    __shared__ uint8_t s_dep[CL_MAX_LIST];
+    for (uint32_t k = threadIdx.x; k < n_mine; k += blockDim.x) {
+        bool dep = n_mine > 64;      // quadratic check: small calls only (a search step has <= `per` queries per part)
+        for (uint32_t e = 0; e < k && !dep; e++) dep = s_meta[e].status == 0 && s_meta[e].hit == s_meta[k].hit;
+        s_dep[k] = dep ? 1 : 0;
+    }
+    __syncthreads();
     const uint64_t *__restrict__ bparity = D.bparity, *__restrict__ rval = D.rval;
     constexpr int B = 4;
     for (uint32_t w = threadIdx.x; w < E; w += blockDim.x) {
         for (uint32_t k0 = 0; k0 < n_mine; k0 += B) {
-            uint64_t a[B], rv[B], bp[B];
+            uint64_t a[B], rv[B], bp[B], pp[B];
 #pragma unroll
             for (int j = 0; j < B; j++) {
-                a[j] = rv[j] = bp[j] = 0;
+                a[j] = rv[j] = bp[j] = pp[j] = 0;
                 if (k0 + j < n_mine && s_meta[k0 + j].status == 0) {
                     const uint64_t slot = s_meta[k0 + j].slot;
                     a[j] = answers[(uint64_t)s_list[k0 + j] * E + w];
                     rv[j] = rval[slot * E + w];
                     bp[j] = bparity[slot * E + w];
+                    if (!s_dep[k0 + j] && w < E4) pp[j] = D.parity[(uint64_t)s_meta[k0 + j].hit * E + w];
                 }
             }
 #pragma unroll
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(256) client_finish_kernel(const ClientPartDev 
                 uint64_t *par = D.parity + (uint64_t)s_meta[k0 + j].hit * E;
                 uint64_t r = a[j], np = bp[j];           // copy(primaryParity[hit], backupParity[slot])  pir.go:461
                 if (w < E4) {
-                    r ^= rv[j] ^ par[w];                 // pir.go:451,453
+                    r ^= rv[j] ^ (s_dep[k0 + j] ? par[w] : pp[j]);   // pir.go:451,453
                     np ^= r;                             // pir.go:463
                 }
                 par[w] = np;
