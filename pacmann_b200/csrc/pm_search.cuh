@@ -78,18 +78,24 @@ __device__ void heap_push(HeapView &h, float dist, uint32_t slot) {
 // read -- so the chain can be read at once: lane l holds the ancestor l+1 levels up, the first lane whose ancestor is not
 // greater than the new element is where the sequential walk stops, the ancestors below it move down one level each and the
 // new element takes the freed position.  Same comparisons, same final arrangement, one step instead of up to log2(n).
-__device__ __forceinline__ void heap_push_warp(float *d, uint32_t *s, uint32_t n, float dist, uint32_t slot) {
+// Pushes follow each other through shared memory, so the push-to-push chain is kept short: 32-bit shared addresses
+// (hd, hs = __cvta_generic_to_shared of the two arrays), lane masks instead of a find-first-set, predicated stores.
+__device__ __forceinline__ void heap_push_warp(uint32_t hd, uint32_t hs, uint32_t n, float dist, uint32_t slot, uint32_t lanemask_lt, uint32_t lanemask_le) {
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t mine = ((n + 1) >> lane) - 1;                                  // position l levels up (lane 0: the new leaf); n + 1 < 2^31
-    const uint32_t up = lane < 31 ? (n + 1) >> (lane + 1) : 0;                    // 1-based position of its parent, 0 = none
-    const float du = up ? d[up - 1] : 0.f;
-    const uint32_t su = up ? s[up - 1] : 0;
-    const uint32_t stop = __ballot_sync(0xffffffffu, !up || !(dist < du));
-    const uint32_t k = __ffs(stop) - 1;                                           // lane 31 always stops
-    if (lane <= k) {            // one predicated store pair, no divergent paths
-        d[mine] = lane < k ? du : dist;
-        s[mine] = lane < k ? su : slot;
-    }
+    const uint32_t mine = (n + 1) >> lane;        // 1-based position `lane` levels above the new leaf (0 = above the root); n + 1 < 2^31
+    const uint32_t up = mine >> 1;                // its parent, 0 = none
+    const uint32_t ua = (up ? up - 1 : 0) * 4;
+    float du;
+    uint32_t su;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(du) : "r"(hd + ua) : "memory");
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(su) : "r"(hs + ua) : "memory");
+    const uint32_t stop = __ballot_sync(0xffffffffu, !up || !(dist < du));       // the lane at the root always stops
+    const uint32_t wr = (stop & lanemask_lt) == 0;                                // lane <= first stopping lane: this position changes
+    const bool shift = (stop & lanemask_le) == 0;                                 // lane <  first stopping lane: its parent moves down into it
+    const float vd = shift ? du : dist;
+    const uint32_t vs = shift ? su : slot;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %4, 0;\n\t@p st.shared.f32 [%0], %1;\n\t@p st.shared.u32 [%2], %3;\n\t}"
+                 ::"r"(hd + (mine - 1) * 4), "f"(vd), "r"(hs + (mine - 1) * 4), "r"(vs), "r"(wr) : "memory");
     __syncwarp();
 }
 __device__ uint32_t heap_pop(HeapView &h) {
@@ -348,11 +354,14 @@ __global__ void __launch_bounds__(SR_THREADS) search_step_kernel(SearchDev S, co
             const uint32_t nfresh = s_nfresh;
             uint32_t hn = s_heap_n;
             __syncwarp();
+            const uint32_t hd_sa = (uint32_t)__cvta_generic_to_shared(s_hd), hs_sa = (uint32_t)__cvta_generic_to_shared(s_hs);
+            const uint32_t lt = (1u << t) - 1, le = lt | (1u << t);
             for (uint32_t x0 = 0; x0 < nfresh; x0 += 32) {      // the push list through registers: no load on the push-to-push chain
                 const float pd = x0 + t < nfresh ? s_pushd[x0 + t] : 0.f;
                 const uint32_t ps = x0 + t < nfresh ? s_pushs[x0 + t] : 0;
                 const uint32_t cnt = min(32u, nfresh - x0);
-                for (uint32_t x = 0; x < cnt; x++) heap_push_warp(s_hd, s_hs, hn++, __shfl_sync(0xffffffffu, pd, x), __shfl_sync(0xffffffffu, ps, x));
+                __syncwarp();
+                for (uint32_t x = 0; x < cnt; x++) heap_push_warp(hd_sa, hs_sa, hn++, __shfl_sync(0xffffffffu, pd, x), __shfl_sync(0xffffffffu, ps, x), lt, le);
             }
             if (t == 0) {
                 s_heap_n = hn;
