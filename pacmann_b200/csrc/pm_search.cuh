@@ -299,7 +299,12 @@ __global__ void __launch_bounds__(SR_THREADS) search_step_kernel(SearchDev S, co
             }
             if (correct) atomicAdd(&s_succ, 1u);
             bool fresh = !benchmarking && ok && hash_find(hk, hv, S.hcap - 1, id) < 0;
-            for (uint32_t j = 0; fresh && j < i; j++) fresh = s_ids[j] != id;     // a repeated id is known by its second occurrence
+            if (fresh) {        // a repeated id is known by its second occurrence (no early exit: the loads stay independent)
+                bool rep = false;
+#pragma unroll 8
+                for (uint32_t j = 0; j < i; j++) rep |= s_ids[j] == id;
+                fresh = !rep;
+            }
             s_flag[i] = fresh ? (have_dist ? 1u : 2u) : 0u;
             s_fd[i] = d;
             s_aux[i] = loc;
