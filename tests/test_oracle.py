@@ -239,3 +239,90 @@ def test_robust_prune_restatement_properties(oracle):
         assert got[0] == cand[np.argmin(d)]
         loose = oracle.robust_prune(vec, u, cand, m, 1e9)
         assert (loose == cand[np.argsort(d, kind="stable")[:m]]).all()
+
+
+# ---- an independent restatement of graphann/search.go:87-234 in plain Python (Go's container/heap included), used only to
+# pin the C oracle's SearchKNN: two transcriptions of the same Go function, written apart, must agree id for id --------------
+def _go_heap_push(h, item):          # container/heap.Push: append + up(len-1); Less = dist < (search.go:95-97)
+    h.append(item)
+    j = len(h) - 1
+    while True:
+        i = (j - 1) // 2
+        if i == j or j == 0 or not (h[j][0] < h[i][0]):
+            break
+        h[i], h[j] = h[j], h[i]
+        j = i
+
+
+def _go_heap_pop(h):                 # container/heap.Pop: Swap(0, n), down(0, n), remove last
+    n = len(h) - 1
+    h[0], h[n] = h[n], h[0]
+    i = 0
+    while True:
+        j1 = 2 * i + 1
+        if j1 >= n:
+            break
+        j = j1
+        if j1 + 1 < n and h[j1 + 1][0] < h[j1][0]:
+            j = j1 + 1
+        if not (h[j][0] < h[i][0]):
+            break
+        h[i], h[j] = h[j], h[i]
+        i = j
+    return h.pop()
+
+
+def _search_knn_py(oracle, vec, graph, start_ids, q, k, max_step, parallel):
+    """search.go:114-234, non-private graph (GetVertexInfo returns every requested vertex, in order).  Where Go leaves the
+    order open (sort.Sort is not stable, map iteration + sort.Slice) the rules of DESIGN.md 2 apply: start ranking by
+    (distance, position), final ranking by (distance, id)."""
+    dist = lambda v: float(oracle.l2dist(vec[v], q))
+    reach, known, heap = {}, {}, []
+    ranked = sorted(range(len(start_ids)), key=lambda p: (dist(int(start_ids[p])), p))
+    for p in ranked:
+        if len(heap) >= parallel:
+            break
+        v = int(start_ids[p])
+        if v in known:
+            continue
+        known[v] = True
+        _go_heap_push(heap, (dist(v), v))
+        reach[v] = 0
+    for step in range(max_step):
+        batch = []
+        for _ in range(parallel):
+            assert heap, "the test data keeps the queue non-empty (the random-id branch needs Go's rand stream)"
+            _, v = _go_heap_pop(heap)
+            batch.extend(int(x) for x in graph[v])
+        for v in batch:
+            if v in known:
+                continue
+            if not any(int(x) != 0 for x in graph[v]):
+                continue
+            known[v] = True
+            reach[v] = step
+            _go_heap_push(heap, (dist(v), v))
+    order = sorted(known, key=lambda v: (dist(v), v))
+    ret = [order[i] if i < len(order) else -1 for i in range(k)]
+    return ret, [reach[v] if v >= 0 else -1 for v in ret]
+
+
+@pytest.mark.parametrize("integer,dim,m,par,steps", [(False, 16, 8, 2, 8), (True, 8, 8, 3, 7), (True, 4, 6, 2, 10)])
+def test_search_knn_matches_an_independent_restatement(oracle, integer, dim, m, par, steps):
+    """integer-valued low-dimensional vectors make most distances tie (and fp32 exact in any order): the explore queue's
+    arrangement, not just its minimum, then decides which vertex is explored next"""
+    from test_graphann_gpu import make_dataset
+    n, k = 700, 12
+    vec, graph = make_dataset(n, dim, m, 31 + dim, integer)
+    if integer:
+        vec = np.floor(vec / 64).astype(np.float32)         # values 0..3
+    start = np.random.default_rng(3).choice(n, 26, replace=False)
+    queries = vec[np.random.default_rng(4).integers(0, n, 8)] + np.float32(0.0 if integer else 0.05)
+    ret, step = oracle.search_knn_basic(vec, graph, start, queries, k, steps, par)
+    ties = 0
+    for i, q in enumerate(queries):
+        p_ret, p_step = _search_knn_py(oracle, vec, graph, start, q, k, steps, par)
+        assert list(ret[i]) == p_ret and list(step[i]) == p_step, f"query {i}"
+        d = [float(oracle.l2dist(vec[v], q)) for v in p_ret if v >= 0]
+        ties += sum(1 for a, b in zip(d, d[1:]) if a == b)
+    assert not integer or ties > 0          # the tie rules were really exercised
